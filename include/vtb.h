@@ -1,0 +1,85 @@
+/* vtb.h — C ABI of libvtb_b200.so: the B200-native (sm_100a) execution layer behind
+ * vision_toolbox's ConvNormAct / Darknet / VoVNet hot path.
+ *
+ * The reference (gau-nernst/vision-toolbox) is pure Python: its "operator interface" for this path is
+ * the torch.nn module stack built in vision_toolbox/components.py:13-46 (ConvNormAct = Conv2d(bias=False)
+ * -> BatchNorm2d -> ReLU(inplace)), vision_toolbox/backbones/darknet.py:20-55 (residual / CSP blocks) and
+ * vision_toolbox/backbones/vovnet.py:20-63 (eSE / OSA blocks).  Each entry point below replaces one torch
+ * library call made from those lines; the comment on each function names the call site it stands in for.
+ *
+ * Conventions
+ *  - plain C: pointers, ints, sizes.  No torch / C++ types.  `stream` is a cudaStream_t passed as void*.
+ *  - the CALLER owns all device memory; the library never allocates, frees or synchronises.
+ *  - activations are NHWC bf16 "views": base pointer + pixel pitch `ld` (elements) so a tensor may be a
+ *    channel slice of a wider concat buffer (ld >= C, ld % 8 == 0, base 16-byte aligned).
+ *  - parameters / statistics / parameter gradients are fp32 in the reference's own layouts (OIHW, [C]).
+ *  - every function returns 0 on success, a negative VTB_E* code otherwise; vtb_last_error() gives text.
+ *  - all functions are asynchronous on `stream` and re-entrant per stream.
+ */
+#ifndef VTB_H_
+#define VTB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTB_OK 0
+#define VTB_EINVAL (-1)   /* unsupported / inconsistent arguments */
+#define VTB_ECUDA (-2)    /* CUDA runtime / driver error          */
+#define VTB_ENODEV (-3)   /* no sm_100 device / driver too old    */
+
+/* Geometry of one square convolution (nn.Conv2d(cin, cout, k, stride, padding=pad, bias=False),
+ * components.py:26-35).  `cin` is the channel count of the NHWC operand (the 3-channel image is stored
+ * padded to 16 channels; everything else is already a multiple of 16). */
+typedef struct VtbConv {
+  int n, h, w;  /* input batch / height / width */
+  int cin, cout;
+  int k, stride, pad;
+} VtbConv;
+
+const char* vtb_last_error(void);
+int vtb_version(void);
+/* number of SMs of the current device (grid sizing), <0 on error */
+int vtb_num_sms(void);
+/* total kernels launched by this library in this process (bench.py's gpu_launches claim) */
+long long vtb_launch_count(void);
+
+/* ---- shape / workspace queries (host only, no GPU needed) ---- */
+int vtb_conv_out_hw(const VtbConv* c, int* ho, int* wo);
+/* rows of the per-CTA statistics scratch written by vtb_conv_fprop: floats = rows * cout * 2 */
+int vtb_conv_stats_rows(const VtbConv* c);
+size_t vtb_conv_wgrad_workspace_bytes(const VtbConv* c);
+
+/* ---- weights ----
+ * Re-pack an OIHW fp32 master weight (nn.Conv2d.weight, components.py:26) into the two bf16 matrices the
+ * tensor-core kernels consume: wf[cout][k*k][cin] (fprop / wgrad K-order) and wd[cin][k*k][cout] (dgrad).
+ * cin_real <= c->cin is the channel count of the fp32 tensor (3 for the image stem). wd may be NULL. */
+int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* wf, void* wd, void* stream);
+
+/* ---- convolution: replaces aten::convolution (cuDNN) at components.py:26-35 ----
+ * y[n,ho,wo,:] = conv(x)  (bf16, fp32 accumulate).
+ * stats_partial != NULL: also accumulates per-channel sum / sum of squares of the bf16-rounded result
+ *   (the quantities BatchNorm2d needs, components.py:36) into [vtb_conv_stats_rows][cout][2] floats
+ *   (the call zeroes the buffer first).
+ * scale/shift != NULL: fused eval-mode epilogue y = conv*scale[c] + shift[c], then ReLU if relu != 0,
+ *   then + residual (bf16 NHWC, pitch ldr) if residual != NULL (darknet.py:28, vovnet.py:60-61). */
+int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
+                   const float* scale, const float* shift, int relu, const void* residual, int ldr, void* stream);
+
+/* ---- convolution backward: replaces aten::convolution_backward (autograd of components.py:26-35) ----
+ * dgrad: dx = conv_transpose(dy, w); accumulate != 0 adds into dx (gradient fan-in of residual / CSP /
+ * OSA branches: darknet.py:28,53 ; vovnet.py:55,61) with bf16 rounding of each addend like autograd. */
+int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
+                   void* stream);
+/* wgrad: dw_oihw (fp32, [cout][cin_real][k][k]) (+)= sum over pixels dy * im2col(x).
+ * workspace: vtb_conv_wgrad_workspace_bytes(c) bytes of scratch. Deterministic (no atomics). */
+int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,
+                   float* dw_oihw, int cin_real, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTB_H_ */

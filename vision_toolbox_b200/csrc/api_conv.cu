@@ -1,0 +1,397 @@
+// C-ABI entry points for the convolution family (include/vtb.h): geometry -> tensor maps + kernel params.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/vtb.h"
+#include "common.cuh"
+#include "igemm.cuh"
+#include "tmap.cuh"
+
+namespace vtb {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_cuda(int e, const char* what) {
+  if (e == 0) return VTB_OK;
+  return fail(VTB_ECUDA, "%s: %s", what, cudaGetErrorString((cudaError_t)e));
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int sms = [] {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return n;
+  }();
+  return sms;
+}
+
+static int chunk_of(int c) { return (c % 64 == 0) ? 64 : (c % 32 == 0 ? 32 : 16); }
+// largest multiple of 16 that divides c and is <= 256
+static int block_of(int c) {
+  for (int b = 256; b >= 16; b -= 16)
+    if (c % b == 0) return b;
+  return 0;
+}
+static bool conv_ok(const VtbConv* c) {
+  return c && c->n > 0 && c->h > 0 && c->w > 0 && c->cin > 0 && c->cout > 0 && c->cin % 16 == 0 && c->cout % 16 == 0 &&
+         c->k >= 1 && c->k * c->k <= kMaxTaps && c->stride >= 1 && c->stride <= 2 && c->pad >= 0 &&
+         (c->h + 2 * c->pad - c->k) >= 0 && (c->w + 2 * c->pad - c->k) >= 0;
+}
+static void out_hw(const VtbConv* c, int* ho, int* wo) {
+  *ho = (c->h + 2 * c->pad - c->k) / c->stride + 1;
+  *wo = (c->w + 2 * c->pad - c->k) / c->stride + 1;
+}
+static int conv_stages(int block_n) {
+  const int per_stage = kBlockM * kStageK * 2 + ((block_n * kStageK * 2 + 1023) / 1024) * 1024;
+  const int fixed = 2 * kBlockM * 128 + 256 + 1024;
+  int s = (232448 - fixed) / per_stage;
+  return std::max(2, std::min(s, 8));
+}
+static int conv_grid(long long M, int cout, int block_n) {
+  const long long tiles = ((M + kBlockM - 1) / kBlockM) * (cout / block_n);
+  const int sms = std::max(1, num_sms());
+  return (int)std::min<long long>(tiles, sms);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin_real, int cin, int kk,
+                                   __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const long long total = (long long)cout * kk * cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int t = (int)((i / cin) % kk);
+    const int co = (int)(i / ((long long)cin * kk));
+    const float v = (ci < cin_real) ? w[((long long)co * cin_real + ci) * kk + t] : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    wf[i] = b;
+    if (wd) wd[((long long)ci * kk + t) * cout + co] = b;
+  }
+}
+
+// dw[co][ci][t] (+)= sum_split ws[split][co][t*cin + ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, int cin_real, int kk,
+                                    float* __restrict__ dw, int accumulate) {
+  const long long total = (long long)cout * cin_real * kk;
+  const long long split_stride = (long long)cout * kk * cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % kk);
+    const int ci = (int)((i / kk) % cin_real);
+    const int co = (int)(i / ((long long)kk * cin_real));
+    const float* src = ws + ((long long)co * kk + t) * cin + ci;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
+    dw[i] = accumulate ? dw[i] + acc : acc;
+  }
+}
+
+struct WgradPlan {
+  int ca, cc, sub_n, subs_per_tile, total_subs, n_tiles, m_tiles, splits, kblocks, stages;
+  long long mpix;
+};
+static WgradPlan plan_wgrad(const VtbConv* c) {
+  WgradPlan w;
+  int ho, wo;
+  out_hw(c, &ho, &wo);
+  w.mpix = (long long)c->n * ho * wo;
+  w.ca = chunk_of(c->cout);
+  w.sub_n = block_of(c->cin);
+  w.cc = chunk_of(w.sub_n);
+  const int taps = c->k * c->k;
+  w.total_subs = taps * (c->cin / w.sub_n);
+  w.subs_per_tile = std::max(1, 256 / w.sub_n);
+  w.subs_per_tile = std::min(w.subs_per_tile, w.total_subs);
+  w.n_tiles = (w.total_subs + w.subs_per_tile - 1) / w.subs_per_tile;
+  w.m_tiles = (c->cout + 127) / 128;
+  w.kblocks = (int)((w.mpix + kStageK - 1) / kStageK);
+  const int ctas = w.n_tiles * w.m_tiles;
+  const int sms = std::max(1, num_sms() > 0 ? num_sms() : 148);
+  int splits = std::max(1, sms / ctas);
+  splits = std::min(splits, std::max(1, w.kblocks / 4));
+  w.splits = splits;
+  const int b_stage = ((w.subs_per_tile * w.sub_n * kStageK * 2 + 1023) / 1024) * 1024;
+  const int per_stage = kStageK * 128 * 2 + b_stage;
+  w.stages = std::max(2, std::min(8, (232448 - 256 - 1024) / per_stage));
+  return w;
+}
+
+}  // namespace vtb
+
+using namespace vtb;
+
+extern "C" {
+
+const char* vtb_last_error(void) { return g_err; }
+int vtb_version(void) { return 100; }
+int vtb_num_sms(void) { return num_sms(); }
+long long vtb_launch_count(void) { return g_launches.load(); }
+
+int vtb_conv_out_hw(const VtbConv* c, int* ho, int* wo) {
+  if (!conv_ok(c) || !ho || !wo) return fail(VTB_EINVAL, "vtb_conv_out_hw: bad geometry");
+  out_hw(c, ho, wo);
+  return VTB_OK;
+}
+
+int vtb_conv_stats_rows(const VtbConv* c) {
+  if (!conv_ok(c)) return fail(VTB_EINVAL, "vtb_conv_stats_rows: bad geometry");
+  int ho, wo;
+  out_hw(c, &ho, &wo);
+  const int bn = block_of(c->cout);
+  const int pw = chunk_of(bn);
+  const int groups = 256 / pw;
+  // sized for the largest grid we may ever launch (device-independent upper bound: 148-SM B200; queried if present)
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  const long long tiles = (((long long)c->n * ho * wo + kBlockM - 1) / kBlockM) * (c->cout / bn);
+  return (int)std::min<long long>(tiles, sms) * groups;
+}
+
+size_t vtb_conv_wgrad_workspace_bytes(const VtbConv* c) {
+  if (!conv_ok(c)) return 0;
+  const WgradPlan w = plan_wgrad(c);
+  return (size_t)w.splits * c->cout * c->k * c->k * c->cin * sizeof(float);
+}
+
+int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* wf, void* wd, void* stream) {
+  if (!conv_ok(c) || !w_oihw || !wf || cin_real <= 0 || cin_real > c->cin)
+    return fail(VTB_EINVAL, "vtb_pack_weight: bad arguments");
+  const long long total = (long long)c->cout * c->k * c->k * c->cin;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
+  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, c->cout, cin_real, c->cin, c->k * c->k,
+                                                               (__nv_bfloat16*)wf, (__nv_bfloat16*)wd);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "pack_weight_kernel");
+}
+
+int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
+                   const float* scale, const float* shift, int relu, const void* residual, int ldr, void* stream) {
+  if (!conv_ok(c) || !x || !wf || !y) return fail(VTB_EINVAL, "vtb_conv_fprop: bad arguments");
+  if (ldx < c->cin || ldy < c->cout || ldx % 8 || ldy % 8) return fail(VTB_EINVAL, "vtb_conv_fprop: bad pitch");
+  if ((scale == nullptr) != (shift == nullptr)) return fail(VTB_EINVAL, "vtb_conv_fprop: scale/shift must pair");
+  if (residual && (ldr < c->cout || ldr % 8)) return fail(VTB_EINVAL, "vtb_conv_fprop: bad residual pitch");
+  if (!driver_api().ok) return fail(VTB_ENODEV, "cuTensorMapEncode* not available from this driver");
+  int ho, wo;
+  out_hw(c, &ho, &wo);
+  const int taps = c->k * c->k;
+  ConvIgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = c->n * ho * wo;
+  p.Wq = wo;
+  p.Hp = ho;
+  p.stride = c->stride;
+  p.lower_w = p.lower_h = -c->pad;
+  p.ntaps = taps;
+  p.cin = c->cin;
+  p.kc = chunk_of(c->cin);
+  p.block_n = block_of(c->cout);
+  p.cout = c->cout;
+  p.num_stages = conv_stages(p.block_n);
+  for (int r = 0; r < c->k; ++r)
+    for (int s = 0; s < c->k; ++s) {
+      const int t = r * c->k + s;
+      p.tap_ow[t] = (uint16_t)s;
+      p.tap_oh[t] = (uint16_t)r;
+      p.tap_kofs[t] = t * c->cin;
+    }
+  p.store_mode = kStoreTma;
+  p.panel_w = chunk_of(p.block_n);
+  p.stats_partial = stats_partial;
+  p.scale = scale;
+  p.shift = shift;
+  p.relu = relu;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.ldr = ldr;
+  const int upper = c->pad - (c->k - 1);
+  CUtensorMap tmA, tmB, tmD;
+  if (!tmap_im2col_nhwc(&tmA, x, c->cin, c->w, c->h, c->n, ldx, -c->pad, -c->pad, upper, upper, p.kc, kBlockM,
+                        c->stride, p.kc * 2))
+    return fail(VTB_ECUDA, "vtb_conv_fprop: im2col tensor map for x failed");
+  if (!tmap_tiled_2d(&tmB, wf, (uint64_t)taps * c->cin, c->cout, (uint64_t)taps * c->cin * 2, p.kc, p.block_n,
+                     p.kc * 2))
+    return fail(VTB_ECUDA, "vtb_conv_fprop: tensor map for weights failed");
+  if (!tmap_tiled_2d(&tmD, y, c->cout, p.M, (uint64_t)ldy * 2, p.panel_w, kBlockM, p.panel_w * 2))
+    return fail(VTB_ECUDA, "vtb_conv_fprop: tensor map for y failed");
+  const int grid = conv_grid(p.M, c->cout, p.block_n);
+  if (stats_partial) {
+    const int groups = 256 / p.panel_w;
+    int e = (int)cudaMemsetAsync(stats_partial, 0, (size_t)grid * groups * c->cout * 2 * sizeof(float),
+                                 (cudaStream_t)stream);
+    if (e) return check_cuda(e, "stats memset");
+  }
+  count_launch(1);
+  return check_cuda(launch_conv_igemm(tmA, tmB, tmD, p, grid, (cudaStream_t)stream), "conv_igemm_kernel(fprop)");
+}
+
+int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
+                   void* stream) {
+  if (!conv_ok(c) || !dy || !wd || !dx) return fail(VTB_EINVAL, "vtb_conv_dgrad: bad arguments");
+  if (lddy < c->cout || lddx < c->cin || lddy % 8 || lddx % 8) return fail(VTB_EINVAL, "vtb_conv_dgrad: bad pitch");
+  if (!driver_api().ok) return fail(VTB_ENODEV, "cuTensorMapEncode* not available from this driver");
+  int ho, wo;
+  out_hw(c, &ho, &wo);
+  const int k = c->k, pad = c->pad;
+  ConvIgemmParams p;
+  memset(&p, 0, sizeof(p));
+  // GEMM: dX[pixels][cin] = im2col(dY)[pixels][taps*cout] * Wd[cin][taps*cout]^T
+  p.cin = c->cout;   // channels per tap of the activation operand (dY)
+  p.cout = c->cin;   // GEMM N
+  p.kc = chunk_of(c->cout);
+  p.block_n = block_of(c->cin);
+  p.panel_w = chunk_of(p.block_n);
+  p.num_stages = conv_stages(p.block_n);
+  CUtensorMap tmA, tmB, tmD;
+  if (!tmap_tiled_2d(&tmB, wd, (uint64_t)k * k * c->cout, c->cin, (uint64_t)k * k * c->cout * 2, p.kc, p.block_n,
+                     p.kc * 2))
+    return fail(VTB_ECUDA, "vtb_conv_dgrad: tensor map for weights failed");
+
+  if (c->stride == 1) {
+    if (ho != c->h + 2 * pad - k + 1) return fail(VTB_EINVAL, "vtb_conv_dgrad: internal shape error");
+    const int lo = -(k - 1 - pad);
+    const int up = -pad;  // positions = ho + up - lo = ho + k - 1 - 2*pad = h
+    p.M = c->n * c->h * c->w;
+    p.Wq = c->w;
+    p.Hp = c->h;
+    p.stride = 1;
+    p.lower_w = p.lower_h = lo;
+    p.ntaps = k * k;
+    for (int r = 0; r < k; ++r)
+      for (int s = 0; s < k; ++s) {
+        const int t = r * k + s;
+        p.tap_ow[t] = (uint16_t)(k - 1 - s);
+        p.tap_oh[t] = (uint16_t)(k - 1 - r);
+        p.tap_kofs[t] = t * c->cout;
+      }
+    p.store_mode = accumulate ? kStoreTmaAdd : kStoreTma;
+    if (!tmap_im2col_nhwc(&tmA, dy, c->cout, wo, ho, c->n, lddy, lo, lo, up, up, p.kc, kBlockM, 1, p.kc * 2))
+      return fail(VTB_ECUDA, "vtb_conv_dgrad: im2col tensor map for dy failed");
+    if (!tmap_tiled_2d(&tmD, dx, c->cin, p.M, (uint64_t)lddx * 2, p.panel_w, kBlockM, p.panel_w * 2))
+      return fail(VTB_ECUDA, "vtb_conv_dgrad: tensor map for dx failed");
+    count_launch(1);
+    return check_cuda(launch_conv_igemm(tmA, tmB, tmD, p, conv_grid(p.M, p.cout, p.block_n), (cudaStream_t)stream),
+                      "conv_igemm_kernel(dgrad s1)");
+  }
+
+  // stride 2: one launch per output-parity phase (ph, pw); each is a dense stride-1 walk over dY.
+  tmD = tmB;  // unused in scatter mode, but must be a valid map
+  for (int ph = 0; ph < 2; ++ph) {
+    for (int pq = 0; pq < 2; ++pq) {
+      const int Hph = (c->h - ph + 1) / 2, Wph = (c->w - pq + 1) / 2;
+      if (Hph <= 0 || Wph <= 0) continue;
+      // taps r with (ph + pad - r) even: ho = h' + (ph + pad - r)/2
+      int rs[8], dhs[8], nr = 0, ss[8], dws[8], ns = 0;
+      for (int r = 0; r < k; ++r)
+        if (((ph + pad - r) % 2 + 2) % 2 == 0) {
+          rs[nr] = r;
+          dhs[nr++] = (ph + pad - r) / 2;  // exact: numerator even
+        }
+      for (int s = 0; s < k; ++s)
+        if (((pq + pad - s) % 2 + 2) % 2 == 0) {
+          ss[ns] = s;
+          dws[ns++] = (pq + pad - s) / 2;
+        }
+      ConvIgemmParams q = p;
+      q.M = c->n * Hph * Wph;
+      q.Wq = Wph;
+      q.Hp = Hph;
+      q.stride = 1;
+      q.store_mode = accumulate ? kStoreScatterAdd : kStoreScatter;
+      q.out = (__nv_bfloat16*)dx;
+      q.OH = c->h;
+      q.OW = c->w;
+      q.os = 2;
+      q.oph = ph;
+      q.opw = pq;
+      q.ldo = lddx;
+      if (nr == 0 || ns == 0) {
+        // no contributing taps: this phase of dx is zero. Not reachable for k=3,p=1 / k=1,p=0 handled below.
+        return fail(VTB_EINVAL, "vtb_conv_dgrad: stride-2 geometry with an empty phase is unsupported");
+      }
+      int lo_h = dhs[0], lo_w = dws[0];
+      for (int i = 0; i < nr; ++i) lo_h = std::min(lo_h, dhs[i]);
+      for (int i = 0; i < ns; ++i) lo_w = std::min(lo_w, dws[i]);
+      q.lower_h = lo_h;
+      q.lower_w = lo_w;
+      q.ntaps = nr * ns;
+      for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < ns; ++j) {
+          const int t = i * ns + j;
+          q.tap_oh[t] = (uint16_t)(dhs[i] - lo_h);
+          q.tap_ow[t] = (uint16_t)(dws[j] - lo_w);
+          q.tap_kofs[t] = (rs[i] * k + ss[j]) * c->cout;
+        }
+      const int up_h = Hph - ho + lo_h, up_w = Wph - wo + lo_w;
+      if (!tmap_im2col_nhwc(&tmA, dy, c->cout, wo, ho, c->n, lddy, lo_w, lo_h, up_w, up_h, q.kc, kBlockM, 1, q.kc * 2))
+        return fail(VTB_ECUDA, "vtb_conv_dgrad: im2col tensor map for dy (phase %d,%d) failed", ph, pq);
+      count_launch(1);
+      int e = launch_conv_igemm(tmA, tmB, tmD, q, conv_grid(q.M, q.cout, q.block_n), (cudaStream_t)stream);
+      if (e) return check_cuda(e, "conv_igemm_kernel(dgrad s2)");
+    }
+  }
+  return VTB_OK;
+}
+
+int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,
+                   float* dw_oihw, int cin_real, int accumulate, void* stream) {
+  if (!conv_ok(c) || !dy || !x || !workspace || !dw_oihw || cin_real <= 0 || cin_real > c->cin)
+    return fail(VTB_EINVAL, "vtb_conv_wgrad: bad arguments");
+  if (lddy < c->cout || ldx < c->cin || lddy % 8 || ldx % 8) return fail(VTB_EINVAL, "vtb_conv_wgrad: bad pitch");
+  if (!driver_api().ok) return fail(VTB_ENODEV, "cuTensorMapEncode* not available from this driver");
+  int ho, wo;
+  out_hw(c, &ho, &wo);
+  const WgradPlan w = plan_wgrad(c);
+  WgradIgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.Mpix = (int)w.mpix;
+  p.Wq = wo;
+  p.Hp = ho;
+  p.stride = c->stride;
+  p.lower_w = p.lower_h = -c->pad;
+  p.cout = c->cout;
+  p.cin = c->cin;
+  p.ntaps = c->k * c->k;
+  p.cc = w.cc;
+  p.ca = w.ca;
+  p.sub_n = w.sub_n;
+  p.subs_per_tile = w.subs_per_tile;
+  p.n_tiles = w.n_tiles;
+  p.total_subs = w.total_subs;
+  p.splits = w.splits;
+  p.kblocks = w.kblocks;
+  p.num_stages = w.stages;
+  for (int r = 0; r < c->k; ++r)
+    for (int s = 0; s < c->k; ++s) {
+      p.tap_ow[r * c->k + s] = (uint16_t)s;
+      p.tap_oh[r * c->k + s] = (uint16_t)r;
+    }
+  p.ws = (float*)workspace;
+  const int upper = c->pad - (c->k - 1);
+  CUtensorMap tmDY, tmX;
+  if (!tmap_tiled_2d(&tmDY, dy, c->cout, (uint64_t)w.mpix, (uint64_t)lddy * 2, w.ca, kStageK, w.ca * 2))
+    return fail(VTB_ECUDA, "vtb_conv_wgrad: tensor map for dy failed");
+  if (!tmap_im2col_nhwc(&tmX, x, c->cin, c->w, c->h, c->n, ldx, -c->pad, -c->pad, upper, upper, w.cc, kStageK,
+                        c->stride, w.cc * 2))
+    return fail(VTB_ECUDA, "vtb_conv_wgrad: im2col tensor map for x failed");
+  count_launch(2);
+  int e = launch_wgrad_igemm(tmDY, tmX, p, w.m_tiles * w.n_tiles, (cudaStream_t)stream);
+  if (e) return check_cuda(e, "wgrad_igemm_kernel");
+  const long long total = (long long)c->cout * cin_real * p.ntaps;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 2048);
+  wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, w.splits, c->cout, c->cin,
+                                                                cin_real, p.ntaps, dw_oihw, accumulate);
+  return check_cuda((int)cudaGetLastError(), "wgrad_reduce_kernel");
+}
+
+}  // extern "C"
