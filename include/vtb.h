@@ -79,6 +79,70 @@ int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, v
 int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,
                    float* dw_oihw, int cin_real, int accumulate, void* stream);
 
+/* ---- BatchNorm2d training forward: replaces aten::native_batch_norm at components.py:36 ----
+ * The conv epilogue leaves per-CTA partial sums; these calls finish the job.
+ *  vtb_bn_stats_reduce : partial[rows][c][2] -> sums[c][2] (double). Only needed for SyncBN, where `sums`
+ *                        is all-reduced across ranks before vtb_bn_finalize (configs/base.yaml:22).
+ *  vtb_bn_finalize     : from `partial` (single GPU) or `sums` (exactly one non-NULL) and the element count
+ *                        per channel (`count`, the GLOBAL N*H*W under SyncBN): mean, invstd = 1/sqrt(var+eps)
+ *                        (biased var), scale = gamma*invstd, shift = beta - mean*scale, and the running-stat
+ *                        update running = (1-momentum)*running + momentum*stat with UNBIASED var, plus
+ *                        num_batches_tracked += 1 (int64). running_* / num_batches_tracked may be NULL.
+ *  vtb_bn_eval_affine  : eval mode, scale/shift from the running statistics. */
+int vtb_bn_stats_reduce(const float* partial, int rows, int c, double* sums, void* stream);
+int vtb_bn_finalize(const float* partial, int rows, const double* sums, double count, int c, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
+                    void* stream);
+int vtb_bn_eval_affine(int c, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, void* stream);
+
+/* out = [relu](y*scale + shift) [+ residual]: the BatchNorm normalise + nn.ReLU(inplace) of
+ * components.py:36-39 and the post-activation residual add of darknet.py:28 / vovnet.py:60-61 in one pass.
+ * `out` may be a channel slice of a concat buffer (replaces torch.cat, darknet.py:53 / vovnet.py:55). */
+int vtb_bn_act(const void* y, int ldy, long long pixels, int c, const float* scale, const float* shift, int relu,
+               const void* residual, int ldr, void* out, int ldo, void* stream);
+
+/* ---- BatchNorm2d + ReLU backward: replaces threshold_backward + native_batch_norm_backward ----
+ * dz = dout * [y*scale+shift > 0]  (ReLU mask recomputed from the saved conv output y)
+ *  reduce  : partial[rows][c][2] = per-block sums of (dz, dz*xhat), rows = vtb_bn_bwd_rows(pixels, c)
+ *  finalize: dgamma (+)= sum dz*xhat, dbeta (+)= sum dz (LOCAL sums: `local_sums` if given, else the reduced
+ *            input), coef[c][2] = (sum dz, sum dz*xhat)/count. Pass `sums_out` to only publish the local
+ *            double sums (SyncBN step 1: all-reduce them, then call again with `sums` = reduced values).
+ *  apply   : dy = scale * (dz - coef0 - xhat*coef1), bf16. */
+int vtb_bn_bwd_rows(long long pixels, int c);
+int vtb_bn_bwd_reduce(const void* dout, int lddo, const void* y, int ldy, long long pixels, int c,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, int relu,
+                      float* partial, void* stream);
+int vtb_bn_bwd_finalize(const float* partial, int rows, const double* sums, const double* local_sums, double count,
+                        int c, float* dgamma, float* dbeta, int accumulate, float* coef, double* sums_out,
+                        void* stream);
+int vtb_bn_bwd_apply(const void* dout, int lddo, const void* y, int ldy, long long pixels, int c, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, int relu, const float* coef,
+                     void* dy, int lddy, void* stream);
+
+/* dst (+)= src on bf16 NHWC views: gradient fan-out of the residual add (darknet.py:28) when it cannot be
+ * aliased, and injection of incoming feature-map gradients. */
+int vtb_grad_add(void* dst, int ldd, const void* src, int lds, long long pixels, int c, int accumulate, void* stream);
+
+/* NCHW fp32 (the layout model(x) receives, tests/test_backbones.py:21) -> NHWC bf16, channels zero-padded
+ * to cpad (the 3-channel image is stored with 16 channels for the tensor-core stem). */
+int vtb_nchw_to_nhwc(const float* x, int n, int c, int h, int w, void* out, int cpad, void* stream);
+
+/* ---- VoVNet-only ops ----
+ * MaxPool2d(3, 2, 1) (vovnet.py:94): -inf padding, first maximum wins ties in backward. */
+int vtb_maxpool3s2_fwd(const void* x, int ldx, int n, int h, int w, int c, void* out, int ldo, void* stream);
+int vtb_maxpool3s2_bwd(const void* x, int ldx, int n, int h, int w, int c, const void* dout, int lddo, void* dx,
+                       int lddx, int accumulate, void* stream);
+/* ESEBlock (vovnet.py:20-28): out = x * hardsigmoid(W * mean_hw(x) + b) [+ residual] (vovnet.py:58-61).
+ * weight [c][c] fp32 (the (C,C,1,1) Conv2d weight), bias [c]; pool/z/gate: [n][c] fp32 saved for backward.
+ * bwd scratch: 3*n*c floats. dweight/dbias are fp32 parameter gradients. */
+int vtb_ese_fwd(const void* x, int ldx, int n, int hw, int c, const float* weight, const float* bias,
+                const void* residual, int ldr, void* out, int ldo, float* pool, float* z, float* gate, void* stream);
+int vtb_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weight, const float* pool, const float* z,
+                const float* gate, const void* dout, int lddo, void* dx, int lddx, int accumulate_dx, float* dweight,
+                float* dbias, int accumulate_dw, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

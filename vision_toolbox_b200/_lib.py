@@ -1,0 +1,107 @@
+"""ctypes binding of libvtb_b200.so (the C ABI declared in include/vtb.h).
+
+The library is built in-tree by ``make -C vision_toolbox_b200/csrc`` (or ``__graft_entry__.build()``).
+There is deliberately NO fallback: a CUDA tensor reaching the backbone without this library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libvtb_b200.so"
+CSRC = _PKG / "csrc"
+
+
+class VtbConv(C.Structure):
+    """struct VtbConv of include/vtb.h (geometry of nn.Conv2d at reference components.py:26-35)."""
+
+    _fields_ = [(k, C.c_int) for k in ("n", "h", "w", "cin", "cout", "k", "stride", "pad")]
+
+
+_p = C.c_void_p
+_i = C.c_int
+_ll = C.c_longlong
+_f = C.c_float
+_d = C.c_double
+_cp = C.POINTER(VtbConv)
+
+# name -> (restype, argtypes); mirrors include/vtb.h one to one (tests/test_abi.py checks the symbol list)
+SIGNATURES = {
+    "vtb_last_error": (C.c_char_p, []),
+    "vtb_version": (_i, []),
+    "vtb_num_sms": (_i, []),
+    "vtb_launch_count": (_ll, []),
+    "vtb_conv_out_hw": (_i, [_cp, C.POINTER(_i), C.POINTER(_i)]),
+    "vtb_conv_stats_rows": (_i, [_cp]),
+    "vtb_conv_wgrad_workspace_bytes": (C.c_size_t, [_cp]),
+    "vtb_pack_weight": (_i, [_cp, _p, _i, _p, _p, _p]),
+    "vtb_conv_fprop": (_i, [_cp, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _p]),
+    "vtb_conv_dgrad": (_i, [_cp, _p, _i, _p, _p, _i, _i, _p]),
+    "vtb_conv_wgrad": (_i, [_cp, _p, _i, _p, _i, _p, _p, _i, _i, _p]),
+    "vtb_bn_stats_reduce": (_i, [_p, _i, _i, _p, _p]),
+    "vtb_bn_finalize": (_i, [_p, _i, _p, _d, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vtb_bn_eval_affine": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _p]),
+    "vtb_bn_act": (_i, [_p, _i, _ll, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
+    "vtb_bn_bwd_rows": (_i, [_ll, _i]),
+    "vtb_bn_bwd_reduce": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _p, _p]),
+    "vtb_bn_bwd_finalize": (_i, [_p, _i, _p, _p, _d, _i, _p, _p, _i, _p, _p, _p]),
+    "vtb_bn_bwd_apply": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p]),
+    "vtb_grad_add": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p]),
+    "vtb_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),
+    "vtb_maxpool3s2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "vtb_maxpool3s2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p]),
+    "vtb_ese_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
+    "vtb_ese_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i, _i, _p, _p, _i, _p, _p]),
+}
+
+_lib = None
+
+
+class VtbError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile libvtb_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", str(CSRC), "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise VtbError("building libvtb_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises VtbError when the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if os.environ.get("VTB_AUTOBUILD", "1") == "1" and (CSRC / "Makefile").exists():
+            build()
+        if not LIB_PATH.exists():
+            raise VtbError(
+                f"{LIB_PATH} not found: build it with `make -C {CSRC}`; vision_toolbox_b200 has no CPU/torch "
+                "fallback for CUDA tensors"
+            )
+    h = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(h, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = h
+    return h
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().vtb_last_error().decode(errors="replace")
+        raise VtbError(f"{what or 'vtb call'} failed ({rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().vtb_launch_count())

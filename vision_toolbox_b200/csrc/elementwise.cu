@@ -1,0 +1,465 @@
+// HBM-bound pieces of the ConvNormAct path: BatchNorm statistics finalisation, normalise(+ReLU)(+residual)
+// materialisation, BatchNorm/ReLU backward (reduce + apply), gradient fan-in adds, layout conversion.
+// All activations are NHWC bf16 views (pointer + pixel pitch); one thread handles 8 channels (16 bytes).
+#include <algorithm>
+#include <cstdint>
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/vtb.h"
+#include "common.cuh"
+
+namespace vtb {
+
+__device__ __forceinline__ float lo16(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float hi16(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = lo16(u.x); f[1] = hi16(u.x); f[2] = lo16(u.y); f[3] = hi16(u.y);
+  f[4] = lo16(u.z); f[5] = hi16(u.z); f[6] = lo16(u.w); f[7] = hi16(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack2(f[0], f[1]); u.y = pack2(f[2], f[3]); u.z = pack2(f[4], f[5]); u.w = pack2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ void load8f(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+static int ew_grid(long long vecs, int block) {
+  const int sms = std::max(1, num_sms());
+  return (int)std::max<long long>(1, std::min<long long>((vecs + block - 1) / block, (long long)sms * 16));
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm statistics: partial rows -> (optionally) double sums -> mean/invstd/scale/shift + running stats
+// ---------------------------------------------------------------------------------------------
+// one warp per channel
+__global__ void bn_stats_reduce_kernel(const float* __restrict__ partial, int rows, int c, double* __restrict__ sums) {
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ch >= c) return;
+  double s = 0, q = 0;
+  for (int r = lane; r < rows; r += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(partial + ((size_t)r * c + ch) * 2);
+    s += v.x;
+    q += v.y;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    sums[ch * 2] = s;
+    sums[ch * 2 + 1] = q;
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, const double* __restrict__ sums_in,
+                                   double count, int c, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                                   float* running_var, long long* nbt, float* mean_out, float* invstd_out,
+                                   float* scale, float* shift) {
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ch >= c) return;
+  double s = 0, q = 0;
+  if (sums_in) {
+    s = sums_in[ch * 2];
+    q = sums_in[ch * 2 + 1];
+  } else {
+    for (int r = lane; r < rows; r += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(partial + ((size_t)r * c + ch) * 2);
+      s += v.x;
+      q += v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0) var = 0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma[ch], b = beta[ch];
+    mean_out[ch] = (float)mean;
+    invstd_out[ch] = invstd;
+    const float sc = g * invstd;
+    scale[ch] = sc;
+    shift[ch] = b - (float)mean * sc;
+    if (running_mean) {
+      const double unbiased = count > 1 ? var * (count / (count - 1.0)) : var;
+      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+    }
+    if (nbt && ch == 0) *nbt += 1;
+  }
+}
+
+__global__ void bn_eval_affine_kernel(int c, const float* gamma, const float* beta, const float* rm, const float* rv,
+                                      float eps, float* scale, float* shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const float sc = gamma[ch] / sqrtf(rv[ch] + eps);
+  scale[ch] = sc;
+  shift[ch] = beta[ch] - rm[ch] * sc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out = [relu](y*scale + shift) [+ residual]     (bf16 rounding after the affine+relu, then after the add:
+// the reference adds two bf16 tensors, darknet.py:28 / vovnet.py:61)
+// ---------------------------------------------------------------------------------------------
+template <bool RELU, bool RES>
+__global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int c8,
+                              const float* __restrict__ scale, const float* __restrict__ shift,
+                              const __nv_bfloat16* __restrict__ res, int ldr, __nv_bfloat16* __restrict__ out,
+                              int ldo) {
+  const long long total = pixels * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / c8;
+    const int ch = (int)(i - pix * c8) * 8;
+    float f[8], sc[8], sh[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y + pix * ldy + ch)), f);
+    load8f(scale + ch, sc);
+    load8f(shift + ch, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (RELU) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (RES) {
+      float r[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(res + pix * ldr + ch)), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = rbf(f[j]) + r[j];
+    }
+    *reinterpret_cast<uint4*>(out + pix * ldo + ch) = pack8(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm(+ReLU) backward, stage 1: per-channel sums of dz and dz*xhat
+//   z = y*scale+shift, dz = dout * (z > 0) (ReLU mask recomputed from the saved conv output), xhat = (y-mean)*invstd
+// block = 256 threads handling ppi = 256/cvec pixels x cvec channel-vectors per iteration
+// ---------------------------------------------------------------------------------------------
+template <bool RELU>
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo,
+                                     const __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int c8, int cvec,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     float* __restrict__ partial, int c) {
+  __shared__ float red[256][17];
+  const int ppi = 256 / cvec;
+  const int t = threadIdx.x;
+  const int v_local = t % cvec;
+  const int pl = t / cvec;
+  const int v = blockIdx.y * cvec + v_local;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (pl < ppi && v < c8) {
+    const int ch = v * 8;
+    float sc[8], sh[8], mu[8], is[8];
+    load8f(scale + ch, sc);
+    load8f(shift + ch, sh);
+    load8f(mean + ch, mu);
+    load8f(invstd + ch, is);
+    for (long long pix = (long long)blockIdx.x * ppi + pl; pix < pixels; pix += (long long)gridDim.x * ppi) {
+      float g[8], yy[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dout + pix * lddo + ch)), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(y + pix * ldy + ch)), yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(yy[j], sc[j], sh[j]);
+        const float dz = (!RELU || z > 0.f) ? g[j] : 0.f;
+        s1[j] += dz;
+        s2[j] = fmaf(dz, (yy[j] - mu[j]) * is[j], s2[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[t][j] = s1[j];
+    red[t][8 + j] = s2[j];
+  }
+  __syncthreads();
+  // outputs: cvec vectors x 16 values; sum over pl in fixed order (deterministic)
+  for (int o = t; o < cvec * 16; o += 256) {
+    const int vl = o / 16, j = o % 16;
+    const int vg = blockIdx.y * cvec + vl;
+    if (vg >= c8) continue;
+    float acc = 0.f;
+    for (int q = 0; q < ppi; ++q) acc += red[q * cvec + vl][j];
+    const int ch = vg * 8 + (j & 7);
+    partial[((size_t)blockIdx.x * c + ch) * 2 + (j >> 3)] = acc;
+  }
+}
+
+// stage 2: partial rows (or cross-rank-reduced double sums) -> dgamma/dbeta (local sums) and the two means
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, const double* __restrict__ sums_in,
+                                       double count, int c, float* dgamma, float* dbeta, int accumulate,
+                                       const double* __restrict__ local_sums, float* __restrict__ coef,
+                                       double* __restrict__ sums_out) {
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ch >= c) return;
+  double s = 0, q = 0;
+  if (sums_in) {
+    s = sums_in[ch * 2];
+    q = sums_in[ch * 2 + 1];
+  } else {
+    for (int r = lane; r < rows; r += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(partial + ((size_t)r * c + ch) * 2);
+      s += v.x;
+      q += v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+  }
+  if (lane == 0) {
+    if (sums_out) {  // SyncBN step 1: publish local sums only
+      sums_out[ch * 2] = s;
+      sums_out[ch * 2 + 1] = q;
+      return;
+    }
+    // parameter gradients use the LOCAL sums (DDP averages them afterwards), the dx formula the global ones
+    const double ls = local_sums ? local_sums[ch * 2] : s;
+    const double lq = local_sums ? local_sums[ch * 2 + 1] : q;
+    if (dgamma) dgamma[ch] = accumulate ? dgamma[ch] + (float)lq : (float)lq;
+    if (dbeta) dbeta[ch] = accumulate ? dbeta[ch] + (float)ls : (float)ls;
+    coef[ch * 2] = (float)(s / count);
+    coef[ch * 2 + 1] = (float)(q / count);
+  }
+}
+
+// stage 3: dy = scale * (dz - mean_dz - xhat * mean_dzxhat)
+template <bool RELU>
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo,
+                                    const __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int c8,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy, int lddy) {
+  const long long total = pixels * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / c8;
+    const int ch = (int)(i - pix * c8) * 8;
+    float g[8], yy[8], sc[8], sh[8], mu[8], is[8], cf[16];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dout + pix * lddo + ch)), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y + pix * ldy + ch)), yy);
+    load8f(scale + ch, sc);
+    load8f(shift + ch, sh);
+    load8f(mean + ch, mu);
+    load8f(invstd + ch, is);
+    load8f(coef + ch * 2, cf);
+    load8f(coef + ch * 2 + 8, cf + 8);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(yy[j], sc[j], sh[j]);
+      const float dz = (!RELU || z > 0.f) ? g[j] : 0.f;
+      const float xh = (yy[j] - mu[j]) * is[j];
+      o[j] = sc[j] * (dz - cf[2 * j] - xh * cf[2 * j + 1]);
+    }
+    *reinterpret_cast<uint4*>(dy + pix * lddy + ch) = pack8(o);
+  }
+}
+
+// dst (+)= src   (bf16 views; fan-out copies / fan-in adds of activation gradients)
+template <bool ADD>
+__global__ void grad_add_kernel(__nv_bfloat16* __restrict__ dst, int ldd, const __nv_bfloat16* __restrict__ src,
+                                int lds, long long pixels, int c8) {
+  const long long total = pixels * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / c8;
+    const int ch = (int)(i - pix * c8) * 8;
+    uint4 s = __ldg(reinterpret_cast<const uint4*>(src + pix * lds + ch));
+    if (ADD) {
+      float a[8], b[8];
+      unpack8(s, a);
+      unpack8(*reinterpret_cast<const uint4*>(dst + pix * ldd + ch), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += b[j];
+      s = pack8(a);
+    }
+    *reinterpret_cast<uint4*>(dst + pix * ldd + ch) = s;
+  }
+}
+
+// NCHW fp32 image -> NHWC bf16 with channels zero-padded to cpad (multiple of 8)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, long long hw,
+                                    __nv_bfloat16* __restrict__ out, int cpad) {
+  const long long total = (long long)n * hw;
+  const int v8 = cpad / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw, p = i - img * hw;
+    for (int v = 0; v < v8; ++v) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = v * 8 + j;
+        f[j] = ch < c ? __ldg(x + (img * c + ch) * hw + p) : 0.f;
+      }
+      *reinterpret_cast<uint4*>(out + i * cpad + v * 8) = pack8(f);
+    }
+  }
+}
+
+}  // namespace vtb
+
+using namespace vtb;
+
+#define VIEW_OK(ptr, ld, c) ((ptr) != nullptr && (ld) >= (c) && (ld) % 8 == 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0)
+
+extern "C" {
+
+int vtb_bn_bwd_rows(long long pixels, int c) {
+  if (pixels <= 0 || c <= 0 || c % 8) return fail(VTB_EINVAL, "vtb_bn_bwd_rows: bad arguments");
+  const int c8 = c / 8, cvec = std::min(c8, 256), ppi = 256 / cvec;
+  const int chunks = (c8 + cvec - 1) / cvec;
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  const long long want = (pixels + (long long)ppi * 8 - 1) / ((long long)ppi * 8);  // >= 8 pixels per thread
+  return (int)std::max<long long>(1, std::min<long long>(want, std::max(1, sms * 4 / chunks)));
+}
+
+int vtb_bn_stats_reduce(const float* partial, int rows, int c, double* sums, void* stream) {
+  if (!partial || !sums || rows <= 0 || c <= 0) return fail(VTB_EINVAL, "vtb_bn_stats_reduce: bad arguments");
+  bn_stats_reduce_kernel<<<(c * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, rows, c, sums);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "bn_stats_reduce_kernel");
+}
+
+int vtb_bn_finalize(const float* partial, int rows, const double* sums, double count, int c, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
+                    void* stream) {
+  if ((partial == nullptr) == (sums == nullptr) || c <= 0 || count <= 0 || !gamma || !beta || !mean || !invstd ||
+      !scale || !shift || (partial && rows <= 0) || ((running_mean == nullptr) != (running_var == nullptr)))
+    return fail(VTB_EINVAL, "vtb_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(c * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      partial, rows, sums, count, c, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, mean,
+      invstd, scale, shift);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "bn_finalize_kernel");
+}
+
+int vtb_bn_eval_affine(int c, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, void* stream) {
+  if (c <= 0 || !gamma || !beta || !running_mean || !running_var || !scale || !shift)
+    return fail(VTB_EINVAL, "vtb_bn_eval_affine: bad arguments");
+  bn_eval_affine_kernel<<<(c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c, gamma, beta, running_mean, running_var,
+                                                                           eps, scale, shift);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "bn_eval_affine_kernel");
+}
+
+int vtb_bn_act(const void* y, int ldy, long long pixels, int c, const float* scale, const float* shift, int relu,
+               const void* residual, int ldr, void* out, int ldo, void* stream) {
+  if (pixels <= 0 || c <= 0 || c % 8 || !VIEW_OK(y, ldy, c) || !VIEW_OK(out, ldo, c) || !scale || !shift ||
+      (residual && !VIEW_OK(residual, ldr, c)))
+    return fail(VTB_EINVAL, "vtb_bn_act: bad arguments");
+  const int c8 = c / 8;
+  const int grid = ew_grid(pixels * c8, 256);
+  const __nv_bfloat16* yy = (const __nv_bfloat16*)y;
+  const __nv_bfloat16* rr = (const __nv_bfloat16*)residual;
+  __nv_bfloat16* oo = (__nv_bfloat16*)out;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (relu && rr) bn_act_kernel<true, true><<<grid, 256, 0, st>>>(yy, ldy, pixels, c8, scale, shift, rr, ldr, oo, ldo);
+  else if (relu) bn_act_kernel<true, false><<<grid, 256, 0, st>>>(yy, ldy, pixels, c8, scale, shift, rr, ldr, oo, ldo);
+  else if (rr) bn_act_kernel<false, true><<<grid, 256, 0, st>>>(yy, ldy, pixels, c8, scale, shift, rr, ldr, oo, ldo);
+  else bn_act_kernel<false, false><<<grid, 256, 0, st>>>(yy, ldy, pixels, c8, scale, shift, rr, ldr, oo, ldo);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "bn_act_kernel");
+}
+
+int vtb_bn_bwd_reduce(const void* dout, int lddo, const void* y, int ldy, long long pixels, int c,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, int relu,
+                      float* partial, void* stream) {
+  if (pixels <= 0 || c <= 0 || c % 8 || !VIEW_OK(dout, lddo, c) || !VIEW_OK(y, ldy, c) || !scale || !shift || !mean ||
+      !invstd || !partial)
+    return fail(VTB_EINVAL, "vtb_bn_bwd_reduce: bad arguments");
+  const int c8 = c / 8, cvec = std::min(c8, 256);
+  const int chunks = (c8 + cvec - 1) / cvec;
+  const int rows = vtb_bn_bwd_rows(pixels, c);
+  dim3 grid(rows, chunks);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (relu)
+    bn_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+                                                     pixels, c8, cvec, scale, shift, mean, invstd, partial, c);
+  else
+    bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+                                                      pixels, c8, cvec, scale, shift, mean, invstd, partial, c);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "bn_bwd_reduce_kernel");
+}
+
+int vtb_bn_bwd_finalize(const float* partial, int rows, const double* sums, const double* local_sums, double count,
+                        int c, float* dgamma, float* dbeta, int accumulate, float* coef, double* sums_out,
+                        void* stream) {
+  if ((partial == nullptr) == (sums == nullptr) || c <= 0 || count <= 0 || (!coef && !sums_out) ||
+      (partial && rows <= 0))
+    return fail(VTB_EINVAL, "vtb_bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<(c * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      partial, rows, sums, count, c, dgamma, dbeta, accumulate, local_sums, coef, sums_out);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "bn_bwd_finalize_kernel");
+}
+
+int vtb_bn_bwd_apply(const void* dout, int lddo, const void* y, int ldy, long long pixels, int c, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, int relu, const float* coef,
+                     void* dy, int lddy, void* stream) {
+  if (pixels <= 0 || c <= 0 || c % 8 || !VIEW_OK(dout, lddo, c) || !VIEW_OK(y, ldy, c) || !VIEW_OK(dy, lddy, c) ||
+      !scale || !shift || !mean || !invstd || !coef)
+    return fail(VTB_EINVAL, "vtb_bn_bwd_apply: bad arguments");
+  const int c8 = c / 8;
+  const int grid = ew_grid(pixels * c8, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (relu)
+    bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+                                                    pixels, c8, scale, shift, mean, invstd, coef, (__nv_bfloat16*)dy,
+                                                    lddy);
+  else
+    bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+                                                     pixels, c8, scale, shift, mean, invstd, coef, (__nv_bfloat16*)dy,
+                                                     lddy);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "bn_bwd_apply_kernel");
+}
+
+int vtb_grad_add(void* dst, int ldd, const void* src, int lds, long long pixels, int c, int accumulate, void* stream) {
+  if (pixels <= 0 || c <= 0 || c % 8 || !VIEW_OK(dst, ldd, c) || !VIEW_OK(src, lds, c))
+    return fail(VTB_EINVAL, "vtb_grad_add: bad arguments");
+  const int c8 = c / 8;
+  const int grid = ew_grid(pixels * c8, 256);
+  if (accumulate)
+    grad_add_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dst, ldd, (const __nv_bfloat16*)src,
+                                                                  lds, pixels, c8);
+  else
+    grad_add_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dst, ldd, (const __nv_bfloat16*)src,
+                                                                   lds, pixels, c8);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "grad_add_kernel");
+}
+
+int vtb_nchw_to_nhwc(const float* x, int n, int c, int h, int w, void* out, int cpad, void* stream) {
+  if (!x || !out || n <= 0 || c <= 0 || h <= 0 || w <= 0 || cpad < c || cpad % 8)
+    return fail(VTB_EINVAL, "vtb_nchw_to_nhwc: bad arguments");
+  const long long total = (long long)n * h * w;
+  nchw_to_nhwc_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(x, n, c, (long long)h * w,
+                                                                             (__nv_bfloat16*)out, cpad);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "nchw_to_nhwc_kernel");
+}
+
+}  // extern "C"

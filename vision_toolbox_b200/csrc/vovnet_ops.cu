@@ -1,0 +1,358 @@
+// VoVNet-only HBM-bound ops: MaxPool2d(3,2,1) (vovnet.py:94) and the eSE channel gate (vovnet.py:20-28),
+// forward and backward, on NHWC bf16 views.
+#include <algorithm>
+#include <cstdint>
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/vtb.h"
+#include "common.cuh"
+
+namespace vtb {
+
+__device__ __forceinline__ float v_lo16(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float v_hi16(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t v_pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float v_rbf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ void v_unpack8(const uint4& u, float* f) {
+  f[0] = v_lo16(u.x); f[1] = v_hi16(u.x); f[2] = v_lo16(u.y); f[3] = v_hi16(u.y);
+  f[4] = v_lo16(u.z); f[5] = v_hi16(u.z); f[6] = v_lo16(u.w); f[7] = v_hi16(u.w);
+}
+__device__ __forceinline__ uint4 v_pack8(const float* f) {
+  uint4 u;
+  u.x = v_pack2(f[0], f[1]); u.y = v_pack2(f[2], f[3]); u.z = v_pack2(f[4], f[5]); u.w = v_pack2(f[6], f[7]);
+  return u;
+}
+
+static int vgrid(long long work, int block) {
+  const int sms = std::max(1, num_sms());
+  return (int)std::max<long long>(1, std::min<long long>((work + block - 1) / block, (long long)sms * 16));
+}
+
+// ------------------------------------------------------------------ MaxPool2d(k=3, s=2, p=1)
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int c8, int ho,
+                                   int wo, __nv_bfloat16* __restrict__ out, int ldo) {
+  const long long total = (long long)n * ho * wo * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c8);
+    long long t = i / c8;
+    const int ow = (int)(t % wo);
+    t /= wo;
+    const int oh = (int)(t % ho);
+    const int img = (int)(t / ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= h) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= w) continue;
+        float f[8];
+        v_unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)img * h + ih) * w + iw) * ldx + v * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = (f[j] > m[j] || f[j] != f[j]) ? f[j] : m[j];
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (((long long)img * ho + oh) * wo + ow) * ldo + v * 8) = v_pack8(m);
+  }
+}
+
+// dx[pixel] (+)= sum over the <=4 windows containing it of dout[window] * [argmax(window) == pixel]
+// (first maximum in row-major window order wins ties, as in aten max_pool2d_with_indices)
+template <bool ADD>
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int c8, int ho,
+                                   int wo, const __nv_bfloat16* __restrict__ dout, int lddo,
+                                   __nv_bfloat16* __restrict__ dx, int lddx) {
+  const long long total = (long long)n * h * w * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c8);
+    long long t = i / c8;
+    const int iw0 = (int)(t % w);
+    t /= w;
+    const int ih0 = (int)(t % h);
+    const int img = (int)(t / h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int oh_lo = max(0, (ih0) / 2), oh_hi = min(ho - 1, (ih0 + 1) / 2);
+    const int ow_lo = max(0, (iw0) / 2), ow_hi = min(wo - 1, (iw0 + 1) / 2);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        // is (ih0, iw0) inside this window?
+        const int r0 = ih0 - (oh * 2 - 1), s0 = iw0 - (ow * 2 - 1);
+        if (r0 < 0 || r0 > 2 || s0 < 0 || s0 > 2) continue;
+        float m[8];
+        int arg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; arg[j] = -1; }
+        for (int r = 0; r < 3; ++r) {
+          const int ih = oh * 2 - 1 + r;
+          if (ih < 0 || ih >= h) continue;
+          for (int s = 0; s < 3; ++s) {
+            const int iw = ow * 2 - 1 + s;
+            if (iw < 0 || iw >= w) continue;
+            float f[8];
+            v_unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)img * h + ih) * w + iw) * ldx + v * 8)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (f[j] > m[j] || f[j] != f[j]) { m[j] = f[j]; arg[j] = r * 3 + s; }
+          }
+        }
+        float g[8];
+        v_unpack8(__ldg(reinterpret_cast<const uint4*>(dout + (((long long)img * ho + oh) * wo + ow) * lddo + v * 8)), g);
+        const int me = r0 * 3 + s0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (arg[j] == me) acc[j] += g[j];
+      }
+    __nv_bfloat16* dst = dx + (((long long)img * h + ih0) * w + iw0) * lddx + v * 8;
+    if (ADD) {
+      float o[8];
+      v_unpack8(*reinterpret_cast<const uint4*>(dst), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = v_rbf(acc[j]) + o[j];
+    }
+    *reinterpret_cast<uint4*>(dst) = v_pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------ eSE
+// per-(image, channel) sums over H*W of a (optionally a*b) : block = 32 channel-vectors x 8 pixel lanes
+template <bool PRODUCT>
+__global__ void hw_reduce_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b,
+                                 int ldb, int hw, int c8, float* __restrict__ out, int c, float mul) {
+  __shared__ float red[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int v = blockIdx.x * 32 + tx;
+  const int img = blockIdx.y;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (v < c8) {
+    for (int p = ty; p < hw; p += 8) {
+      float f[8];
+      v_unpack8(__ldg(reinterpret_cast<const uint4*>(a + ((long long)img * hw + p) * lda + v * 8)), f);
+      if (PRODUCT) {
+        float g[8];
+        v_unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((long long)img * hw + p) * ldb + v * 8)), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = fmaf(f[j], g[j], s[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += f[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx][j] = s[j];
+  __syncthreads();
+  if (ty == 0 && v < c8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float acc = 0.f;
+      for (int q = 0; q < 8; ++q) acc += red[q][tx][j];
+      out[(long long)img * c + v * 8 + j] = acc * mul;
+    }
+  }
+}
+
+// z[n][co] = bf16(sum_ci bf16(W[co][ci]) * bf16(pool[n][ci]) + bf16(b[co])); gate = bf16(hardsigmoid(z))
+// one warp per (n, co); mirrors the bf16 autocast rounding points of nn.Conv2d(C, C, 1) + nn.Hardsigmoid
+__global__ void ese_fc_fwd_kernel(const float* __restrict__ pool, const float* __restrict__ W,
+                                  const float* __restrict__ bias, int n, int c, float* __restrict__ z,
+                                  float* __restrict__ gate) {
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long long)n * c) return;
+  const int img = (int)(wid / c), co = (int)(wid % c);
+  float acc = 0.f;
+  for (int ci = lane; ci < c; ci += 32) acc = fmaf(v_rbf(W[(long long)co * c + ci]), v_rbf(pool[(long long)img * c + ci]), acc);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const float zz = v_rbf(acc + v_rbf(bias[co]));
+    z[wid] = zz;
+    gate[wid] = v_rbf(fminf(fmaxf(zz * (1.f / 6.f) + 0.5f, 0.f), 1.f));
+  }
+}
+
+// out = x * gate[n][c] (+ residual)
+template <bool RES>
+__global__ void ese_scale_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gate, int hw,
+                                 long long pixels, int c8, const __nv_bfloat16* __restrict__ res, int ldr,
+                                 __nv_bfloat16* __restrict__ out, int ldo) {
+  const long long total = pixels * c8;
+  const int c = c8 * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / c8;
+    const int ch = (int)(i - pix * c8) * 8;
+    const long long img = pix / hw;
+    float f[8];
+    v_unpack8(__ldg(reinterpret_cast<const uint4*>(x + pix * ldx + ch)), f);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + img * c + ch));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + img * c + ch) + 1);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= g[j];
+    if (RES) {
+      float r[8];
+      v_unpack8(__ldg(reinterpret_cast<const uint4*>(res + pix * ldr + ch)), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = v_rbf(f[j]) + r[j];
+    }
+    *reinterpret_cast<uint4*>(out + pix * ldo + ch) = v_pack8(f);
+  }
+}
+
+// dz[n][co] = dgate * hardsigmoid'(z)
+__global__ void ese_dz_kernel(const float* __restrict__ dgate, const float* __restrict__ z, long long total,
+                              float* __restrict__ dz) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float t = z[i] * (1.f / 6.f) + 0.5f;
+  dz[i] = (t > 0.f && t < 1.f) ? dgate[i] * (1.f / 6.f) : 0.f;
+}
+// dpool[n][ci] = sum_co dz[n][co] * bf16(W[co][ci]) ; scaled by 1/hw for the mean
+__global__ void ese_dpool_kernel(const float* __restrict__ dz, const float* __restrict__ W, int n, int c, float inv_hw,
+                                 float* __restrict__ dpool) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * c) return;
+  const int img = (int)(i / c), ci = (int)(i % c);
+  float acc = 0.f;
+  for (int co = 0; co < c; ++co) acc = fmaf(dz[(long long)img * c + co], v_rbf(W[(long long)co * c + ci]), acc);
+  dpool[i] = acc * inv_hw;
+}
+// dW[co][ci] (+)= sum_n dz[n][co]*bf16(pool[n][ci]); db[co] (+)= sum_n dz[n][co]
+__global__ void ese_dw_kernel(const float* __restrict__ dz, const float* __restrict__ pool, int n, int c,
+                              float* __restrict__ dW, float* __restrict__ db, int accumulate) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)c * c) return;
+  const int co = (int)(i / c), ci = (int)(i % c);
+  float acc = 0.f, accb = 0.f;
+  for (int img = 0; img < n; ++img) {
+    const float d = dz[(long long)img * c + co];
+    acc = fmaf(d, v_rbf(pool[(long long)img * c + ci]), acc);
+    accb += d;
+  }
+  dW[i] = accumulate ? dW[i] + acc : acc;
+  if (ci == 0) db[co] = accumulate ? db[co] + accb : accb;
+}
+// dx (+)= dout * gate + dpool[n][c]
+template <bool ADD>
+__global__ void ese_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const float* __restrict__ gate,
+                                  const float* __restrict__ dpool, int hw, long long pixels, int c8,
+                                  __nv_bfloat16* __restrict__ dx, int lddx) {
+  const long long total = pixels * c8;
+  const int c = c8 * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / c8;
+    const int ch = (int)(i - pix * c8) * 8;
+    const long long img = pix / hw;
+    float f[8];
+    v_unpack8(__ldg(reinterpret_cast<const uint4*>(dout + pix * lddo + ch)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], gate[img * c + ch + j], dpool[img * c + ch + j]);
+    __nv_bfloat16* dst = dx + pix * lddx + ch;
+    if (ADD) {
+      float o[8];
+      v_unpack8(*reinterpret_cast<const uint4*>(dst), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = v_rbf(f[j]) + o[j];
+    }
+    *reinterpret_cast<uint4*>(dst) = v_pack8(f);
+  }
+}
+
+}  // namespace vtb
+
+using namespace vtb;
+#define VVIEW_OK(ptr, ld, c) ((ptr) != nullptr && (ld) >= (c) && (ld) % 8 == 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0)
+
+extern "C" {
+
+int vtb_maxpool3s2_fwd(const void* x, int ldx, int n, int h, int w, int c, void* out, int ldo, void* stream) {
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 || !VVIEW_OK(x, ldx, c) || !VVIEW_OK(out, ldo, c))
+    return fail(VTB_EINVAL, "vtb_maxpool3s2_fwd: bad arguments");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const long long total = (long long)n * ho * wo * (c / 8);
+  maxpool_fwd_kernel<<<vgrid(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, n, h, w, c / 8,
+                                                                          ho, wo, (__nv_bfloat16*)out, ldo);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "maxpool_fwd_kernel");
+}
+
+int vtb_maxpool3s2_bwd(const void* x, int ldx, int n, int h, int w, int c, const void* dout, int lddo, void* dx,
+                       int lddx, int accumulate, void* stream) {
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 || !VVIEW_OK(x, ldx, c) || !VVIEW_OK(dout, lddo, c) ||
+      !VVIEW_OK(dx, lddx, c))
+    return fail(VTB_EINVAL, "vtb_maxpool3s2_bwd: bad arguments");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const long long total = (long long)n * h * w * (c / 8);
+  if (accumulate)
+    maxpool_bwd_kernel<true><<<vgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, ho, wo, (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx);
+  else
+    maxpool_bwd_kernel<false><<<vgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, ho, wo, (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "maxpool_bwd_kernel");
+}
+
+int vtb_ese_fwd(const void* x, int ldx, int n, int hw, int c, const float* weight, const float* bias,
+                const void* residual, int ldr, void* out, int ldo, float* pool, float* z, float* gate, void* stream) {
+  if (n <= 0 || hw <= 0 || c <= 0 || c % 8 || !VVIEW_OK(x, ldx, c) || !VVIEW_OK(out, ldo, c) || !weight || !bias ||
+      !pool || !z || !gate || (residual && !VVIEW_OK(residual, ldr, c)))
+    return fail(VTB_EINVAL, "vtb_ese_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int c8 = c / 8;
+  hw_reduce_kernel<false><<<dim3((c8 + 31) / 32, n), 256, 0, st>>>((const __nv_bfloat16*)x, ldx, nullptr, 0, hw, c8,
+                                                                   pool, c, 1.f / hw);
+  const long long warps = (long long)n * c;
+  ese_fc_fwd_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(pool, weight, bias, n, c, z, gate);
+  const long long pixels = (long long)n * hw;
+  if (residual)
+    ese_scale_kernel<true><<<vgrid(pixels * c8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, ldx, gate, hw, pixels, c8,
+                                                                    (const __nv_bfloat16*)residual, ldr,
+                                                                    (__nv_bfloat16*)out, ldo);
+  else
+    ese_scale_kernel<false><<<vgrid(pixels * c8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, ldx, gate, hw, pixels, c8,
+                                                                     nullptr, 0, (__nv_bfloat16*)out, ldo);
+  count_launch(3);
+  return check_cuda((int)cudaGetLastError(), "ese forward kernels");
+}
+
+int vtb_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weight, const float* pool, const float* z,
+                const float* gate, const void* dout, int lddo, void* dx, int lddx, int accumulate_dx, float* dweight,
+                float* dbias, int accumulate_dw, float* scratch, void* stream) {
+  if (n <= 0 || hw <= 0 || c <= 0 || c % 8 || !VVIEW_OK(x, ldx, c) || !VVIEW_OK(dout, lddo, c) ||
+      !VVIEW_OK(dx, lddx, c) || !weight || !pool || !z || !gate || !dweight || !dbias || !scratch)
+    return fail(VTB_EINVAL, "vtb_ese_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int c8 = c / 8;
+  const long long nc = (long long)n * c;
+  float* dgate = scratch;          // [n][c]
+  float* dz = scratch + nc;        // [n][c]
+  float* dpool = scratch + 2 * nc; // [n][c]
+  hw_reduce_kernel<true><<<dim3((c8 + 31) / 32, n), 256, 0, st>>>((const __nv_bfloat16*)dout, lddo,
+                                                                  (const __nv_bfloat16*)x, ldx, hw, c8, dgate, c, 1.f);
+  ese_dz_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(dgate, z, nc, dz);
+  ese_dpool_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(dz, weight, n, c, 1.f / hw, dpool);
+  ese_dw_kernel<<<(unsigned)(((long long)c * c + 255) / 256), 256, 0, st>>>(dz, pool, n, c, dweight, dbias,
+                                                                            accumulate_dw);
+  const long long pixels = (long long)n * hw;
+  if (accumulate_dx)
+    ese_bwd_dx_kernel<true><<<vgrid(pixels * c8, 256), 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, gate, dpool, hw,
+                                                                     pixels, c8, (__nv_bfloat16*)dx, lddx);
+  else
+    ese_bwd_dx_kernel<false><<<vgrid(pixels * c8, 256), 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, gate, dpool, hw,
+                                                                      pixels, c8, (__nv_bfloat16*)dx, lddx);
+  count_launch(5);
+  return check_cuda((int)cudaGetLastError(), "ese backward kernels");
+}
+
+}  // extern "C"

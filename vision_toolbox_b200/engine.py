@@ -1,0 +1,630 @@
+"""Graph planner + executor behind the drop-in modules.
+
+A module tree (ConvNormAct, DarknetBlock, CSPDarknetStage, OSABlock, Darknet, VoVNet ...) *emits* itself into
+a :class:`Graph` once per (input shape, mode).  The graph is a static list of ops over NHWC bf16 views that
+live in one activation arena (concatenations are channel slices of one buffer, so ``torch.cat`` of reference
+darknet.py:53 / vovnet.py:55 never runs).  :class:`Runner` replays that list through the C ABI
+(``include/vtb.h``) on the current CUDA stream, forward and backward; autograd sees ONE node per call.
+
+No op here has a torch/cuDNN implementation: if libvtb_b200.so is missing, loading it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import VtbConv, check
+
+BF16 = 2
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+# ----------------------------------------------------------------------------------------------------
+# symbolic tensors
+# ----------------------------------------------------------------------------------------------------
+class Buffer:
+    """A dense NHWC bf16 allocation of `pixels` x `c` elements inside the activation (or gradient) arena."""
+
+    def __init__(self, idx: int, n: int, h: int, w: int, c: int, kind: str):
+        self.idx, self.n, self.h, self.w, self.c, self.kind = idx, n, h, w, c, kind
+        self.offset = -1  # bytes, assigned by Graph.finalize
+        self.exclusive_owner: Optional["TView"] = None
+
+    @property
+    def pixels(self) -> int:
+        return self.n * self.h * self.w
+
+    @property
+    def nbytes(self) -> int:
+        return self.pixels * self.c * BF16
+
+
+class TView:
+    """Channel slice [coff, coff+c) of a Buffer: what every kernel sees as (pointer, pixel pitch)."""
+
+    def __init__(self, buf: Buffer, coff: int, c: int):
+        self.buf, self.coff, self.c = buf, coff, c
+        self.consumers: list[int] = []
+        self.is_output = False
+        self.is_input = False
+        self.grad_alias: Optional["TView"] = None  # gradient lives in another view's gradient memory
+
+    n = property(lambda s: s.buf.n)
+    h = property(lambda s: s.buf.h)
+    w = property(lambda s: s.buf.w)
+    ld = property(lambda s: s.buf.c)
+    pixels = property(lambda s: s.buf.pixels)
+
+    def byte_offset(self) -> int:
+        return self.buf.offset + self.coff * BF16
+
+    def __repr__(self):
+        return f"TView(buf{self.buf.idx}[{self.coff}:{self.coff + self.c}] {self.n}x{self.h}x{self.w} ld{self.ld})"
+
+
+@dataclass
+class ConvOp:
+    mod: Any  # ConvNormAct
+    x: TView
+    y: Optional[TView]  # raw conv output (None in fused eval mode)
+    out: TView
+    residual: Optional[TView]
+    relu: bool
+    geom: VtbConv
+    cin_real: int
+    pidx: int = -1  # index of (weight, gamma, beta) in the parameter list
+    st: dict = field(default_factory=dict)  # float offsets into the stat arena
+    kind: str = "conv"
+
+
+@dataclass
+class PoolOp:
+    x: TView
+    out: TView
+    kind: str = "pool"
+
+
+@dataclass
+class EseOp:
+    mod: Any  # ESEBlock
+    x: TView
+    out: TView
+    residual: Optional[TView]
+    pidx: int = -1
+    st: dict = field(default_factory=dict)
+    kind: str = "ese"
+
+
+# ----------------------------------------------------------------------------------------------------
+# graph builder
+# ----------------------------------------------------------------------------------------------------
+class Graph:
+    def __init__(self, training: bool, need_grad: bool):
+        self.training = training
+        self.need_grad = need_grad
+        # BN uses batch statistics only in training mode; the 1-kernel fused epilogue needs frozen statistics
+        self.fused_eval = (not training) and (not need_grad)
+        self.buffers: list[Buffer] = []
+        self.ops: list[Any] = []
+        self.params: list[torch.Tensor] = []
+        self.outputs: list[TView] = []
+        self.input: Optional[TView] = None
+        self.input_c = 0
+        self.stat_floats = 0
+        self.ws_bytes = 0
+        self.dy_bytes = 0
+        self.act_bytes = 0
+
+    # -- allocation
+    def new_buffer(self, n: int, h: int, w: int, c: int, kind: str = "act") -> Buffer:
+        b = Buffer(len(self.buffers), n, h, w, c, kind)
+        self.buffers.append(b)
+        return b
+
+    def new_tensor(self, n: int, h: int, w: int, c: int, kind: str = "act") -> TView:
+        b = self.new_buffer(n, h, w, c, kind)
+        t = TView(b, 0, c)
+        b.exclusive_owner = t
+        return t
+
+    def slice(self, buf: Buffer, coff: int, c: int) -> TView:
+        assert coff % 8 == 0 and c % 8 == 0 and coff + c <= buf.c
+        return TView(buf, coff, c)
+
+    def rehome(self, t: TView, buf: Buffer, coff: int) -> bool:
+        """Move a not-yet-allocated standalone tensor into a channel slice of `buf` (in-place concat)."""
+        old = t.buf
+        if old.exclusive_owner is not t or t.is_input or old is buf:
+            return False
+        if (old.n, old.h, old.w) != (buf.n, buf.h, buf.w):
+            return False
+        self.buffers.remove(old)
+        for i, b in enumerate(self.buffers):
+            b.idx = i
+        t.buf, t.coff = buf, coff
+        return True
+
+    def _stat(self, op, name: str, floats: int) -> None:
+        self.stat_floats = _round_up(self.stat_floats, 64)
+        op.st[name] = self.stat_floats
+        self.stat_floats += floats
+
+    # -- ops
+    def input_image(self, n: int, c: int, h: int, w: int) -> TView:
+        cpad = _round_up(c, 16)
+        t = self.new_tensor(n, h, w, cpad, "act")
+        t.is_input = True
+        self.input, self.input_c = t, c
+        return t
+
+    def conv_norm_act(self, mod, x: TView, residual: Optional[TView] = None, out: Optional[TView] = None) -> TView:
+        conv, norm = mod.conv, mod.norm
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        cin_real, cout = conv.in_channels, conv.out_channels
+        if not mod.native_supported():
+            raise NotImplementedError(
+                "ConvNormAct options outside the Darknet/VoVNet hot path (groups/dilation/norm='none'/act other than "
+                "relu|none) have no sm_100a kernel; run that module on its own"
+            )
+        if cout % 16 or x.c < cin_real or x.c % 16:
+            raise NotImplementedError(f"channel counts must be multiples of 16 (got {cin_real}->{cout})")
+        geom = VtbConv(x.n, x.h, x.w, x.c, cout, k, s, p)
+        ho = (x.h + 2 * p - k) // s + 1
+        wo = (x.w + 2 * p - k) // s + 1
+        if out is None:
+            out = self.new_tensor(x.n, ho, wo, cout)
+        assert (out.n, out.h, out.w, out.c) == (x.n, ho, wo, cout)
+        y = None if self.fused_eval else self.new_tensor(x.n, ho, wo, cout, "raw")
+        op = ConvOp(mod, x, y, out, residual, mod.act_is_relu(), geom, cin_real)
+        idx = len(self.ops)
+        x.consumers.append(idx)
+        if residual is not None:
+            assert (residual.n, residual.h, residual.w, residual.c) == (out.n, out.h, out.w, out.c)
+            residual.consumers.append(idx)
+        op.pidx = len(self.params)
+        self.params += [conv.weight, norm.weight, norm.bias]
+        L = _lib.lib()
+        rows_f = L.vtb_conv_stats_rows(C.byref(geom))
+        if rows_f <= 0:
+            check(-1, "vtb_conv_stats_rows")
+        rows_b = L.vtb_bn_bwd_rows(out.pixels, cout)
+        for name in ("mean", "invstd", "scale", "shift"):
+            self._stat(op, name, cout)
+        self._stat(op, "partial_f", rows_f * cout * 2)
+        self._stat(op, "sums", cout * 4)  # double[c][2]
+        if self.need_grad:
+            self._stat(op, "partial_b", rows_b * cout * 2)
+            self._stat(op, "coef", cout * 2)
+            self._stat(op, "sums_b", cout * 4)
+            self._stat(op, "lsums_b", cout * 4)
+            self.ws_bytes = max(self.ws_bytes, int(L.vtb_conv_wgrad_workspace_bytes(C.byref(geom))))
+            self.dy_bytes = max(self.dy_bytes, out.pixels * cout * BF16)
+        op.rows_f, op.rows_b = rows_f, rows_b
+        self.ops.append(op)
+        return out
+
+    def maxpool(self, x: TView, out: Optional[TView] = None) -> TView:
+        ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
+        if out is None:
+            out = self.new_tensor(x.n, ho, wo, x.c)
+        x.consumers.append(len(self.ops))
+        self.ops.append(PoolOp(x, out))
+        return out
+
+    def ese(self, mod, x: TView, residual: Optional[TView] = None, out: Optional[TView] = None) -> TView:
+        if out is None:
+            out = self.new_tensor(x.n, x.h, x.w, x.c)
+        op = EseOp(mod, x, out, residual)
+        idx = len(self.ops)
+        x.consumers.append(idx)
+        if residual is not None:
+            residual.consumers.append(idx)
+        op.pidx = len(self.params)
+        self.params += [mod.linear.weight, mod.linear.bias]
+        for name in ("pool", "z", "gate"):
+            self._stat(op, name, x.n * x.c)
+        if self.need_grad:
+            self._stat(op, "scratch", 3 * x.n * x.c)
+        self.ops.append(op)
+        return out
+
+    def add_residual(self, a: TView, b: TView) -> TView:
+        raise NotImplementedError("bare adds are fused into the producing ConvNormAct / ESE op")
+
+    def mark_output(self, t: TView) -> None:
+        t.is_output = True
+        self.outputs.append(t)
+
+    def finalize(self) -> None:
+        # materialised activations first (the gradient arena mirrors exactly this prefix), raw conv outputs after
+        off = 0
+        for b in self.buffers:
+            if b.kind == "act":
+                b.offset = off
+                off += _round_up(b.nbytes, 1024)
+        self.grad_bytes = off
+        for b in self.buffers:
+            if b.kind != "act":
+                b.offset = off
+                off += _round_up(b.nbytes, 1024)
+        self.act_bytes = off
+        # Residual gradient aliasing: for out = res + f(res) the gradient of `res` can live in the gradient memory
+        # of `out` (every other contribution is accumulated into it) iff nothing consumes `res` after this op.
+        for i, op in enumerate(self.ops):
+            res = getattr(op, "residual", None)
+            if res is not None and not res.is_output and not res.is_input and max(res.consumers) == i:
+                res.grad_alias = op.out
+
+
+# ----------------------------------------------------------------------------------------------------
+# executor
+# ----------------------------------------------------------------------------------------------------
+class Run:
+    """Device state of one forward call that backward needs (activation + statistics arenas)."""
+
+    __slots__ = ("act", "stat", "x_shape", "x_dtype", "x_requires_grad", "count_scale")
+
+
+class DistConfig:
+    """Data-parallel hooks (vision_toolbox_b200.parallel fills this in)."""
+
+    def __init__(self, group=None, sync_bn: bool = True):
+        import torch.distributed as dist
+
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.sync_bn = sync_bn and self.world > 1
+
+    def all_reduce_(self, t: torch.Tensor) -> None:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class Runner:
+    def __init__(self, graph: Graph, device: torch.device):
+        self.g = graph
+        self.device = device
+        self.L = _lib.lib()
+        self.dist: Optional[DistConfig] = None
+
+    # -- helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @staticmethod
+    def _packed(op: ConvOp, L, stream: int):
+        """bf16 re-pack of the fp32 master weight, refreshed whenever the parameter was modified in place."""
+        w = op.mod.conv.weight
+        cache = op.mod.__dict__.get("_vtb_wpack")
+        key = (w.data_ptr(), w._version, op.geom.cin)
+        if cache is None or cache[0] != key:
+            g = op.geom
+            n = g.cout * g.k * g.k * g.cin
+            wf = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+            wd = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+            wsrc = w.detach()
+            if wsrc.dtype != torch.float32 or not wsrc.is_contiguous():
+                wsrc = wsrc.float().contiguous()
+            check(L.vtb_pack_weight(C.byref(g), wsrc.data_ptr(), op.cin_real, wf.data_ptr(), wd.data_ptr(), stream),
+                  "vtb_pack_weight")
+            cache = (key, wf, wd, wsrc)
+            op.mod.__dict__["_vtb_wpack"] = cache
+        return cache[1], cache[2]
+
+    def view_tensor(self, arena: torch.Tensor, t: TView) -> torch.Tensor:
+        """Zero-copy logical-NCHW (channels_last strided) bf16 tensor over a view of the arena."""
+        base = arena[t.buf.offset : t.buf.offset + t.buf.nbytes].view(torch.bfloat16)
+        ld = t.ld
+        return base.as_strided((t.n, t.c, t.h, t.w), (t.h * t.w * ld, 1, t.w * ld, ld), t.coff)
+
+    # -- forward
+    def forward(self, x: torch.Tensor):
+        g, L = self.g, self.L
+        st = self._stream()
+        dev = x.device
+        run = Run()
+        run.act = torch.empty(g.act_bytes, dtype=torch.uint8, device=dev)
+        run.stat = torch.empty(g.stat_floats + 64, dtype=torch.float32, device=dev)
+        run.x_shape, run.x_dtype, run.x_requires_grad = tuple(x.shape), x.dtype, x.requires_grad
+        abase, sbase = run.act.data_ptr(), run.stat.data_ptr()
+        sbase = (sbase + 255) // 256 * 256
+
+        # input layout conversion (NCHW float -> NHWC bf16, channels padded to a multiple of 16)
+        xin = x.detach()
+        if xin.dtype != torch.float32 or not xin.is_contiguous():
+            xin = xin.float().contiguous()
+        n, c, h, w = xin.shape
+        t_in = g.input
+        check(L.vtb_nchw_to_nhwc(xin.data_ptr(), n, c, h, w, abase + t_in.byte_offset(), t_in.c, st), "vtb_nchw_to_nhwc")
+
+        world = self.dist.world if (self.dist is not None and self.dist.sync_bn) else 1
+        for op in g.ops:
+            if op.kind == "conv":
+                self._conv_forward(op, abase, sbase, run, st, world)
+            elif op.kind == "pool":
+                xx, oo = op.x, op.out
+                check(L.vtb_maxpool3s2_fwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h, xx.w, xx.c,
+                                           abase + oo.byte_offset(), oo.ld, st), "vtb_maxpool3s2_fwd")
+            elif op.kind == "ese":
+                xx, oo, rr = op.x, op.out, op.residual
+                lin = op.mod.linear
+                check(L.vtb_ese_fwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h * xx.w, xx.c,
+                                    lin.weight.data_ptr(), lin.bias.data_ptr(),
+                                    0 if rr is None else abase + rr.byte_offset(), 0 if rr is None else rr.ld,
+                                    abase + oo.byte_offset(), oo.ld, sbase + 4 * op.st["pool"], sbase + 4 * op.st["z"],
+                                    sbase + 4 * op.st["gate"], st), "vtb_ese_fwd")
+        outs = [self.view_tensor(run.act, t) for t in g.outputs]
+        return outs, run
+
+    def _conv_forward(self, op: ConvOp, abase: int, sbase: int, run: Run, st: int, world: int) -> None:
+        g, L = self.g, self.L
+        geom, norm = op.geom, op.mod.norm
+        wf, _ = self._packed(op, L, st)
+        x, out, res = op.x, op.out, op.residual
+        f = lambda name: sbase + 4 * op.st[name]
+        cout = geom.cout
+        res_p = 0 if res is None else abase + res.byte_offset()
+        res_ld = 0 if res is None else res.ld
+        if g.fused_eval:
+            check(L.vtb_bn_eval_affine(cout, norm.weight.data_ptr(), norm.bias.data_ptr(), norm.running_mean.data_ptr(),
+                                       norm.running_var.data_ptr(), norm.eps, f("scale"), f("shift"), st),
+                  "vtb_bn_eval_affine")
+            check(L.vtb_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(),
+                                   abase + out.byte_offset(), out.ld, 0, f("scale"), f("shift"), int(op.relu), res_p,
+                                   res_ld, st), "vtb_conv_fprop(eval)")
+            return
+        y = op.y
+        use_batch_stats = g.training
+        check(L.vtb_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(), abase + y.byte_offset(),
+                               y.ld, f("partial_f") if use_batch_stats else 0, 0, 0, 0, 0, 0, st), "vtb_conv_fprop")
+        if use_batch_stats:
+            mom = norm.momentum if norm.momentum is not None else 0.1
+            track = norm.track_running_stats and norm.running_mean is not None
+            rm = norm.running_mean.data_ptr() if track else 0
+            rv = norm.running_var.data_ptr() if track else 0
+            nbt = norm.num_batches_tracked.data_ptr() if track else 0
+            count = float(out.pixels)
+            if world > 1:
+                check(L.vtb_bn_stats_reduce(f("partial_f"), op.rows_f, cout, f("sums"), st), "vtb_bn_stats_reduce")
+                sums = run.stat_view_f64(op.st["sums"], cout * 2, sbase)
+                self.dist.all_reduce_(sums)
+                check(L.vtb_bn_finalize(0, 0, f("sums"), count * world, cout, norm.weight.data_ptr(),
+                                        norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt, f("mean"), f("invstd"),
+                                        f("scale"), f("shift"), st), "vtb_bn_finalize")
+            else:
+                check(L.vtb_bn_finalize(f("partial_f"), op.rows_f, 0, count, cout, norm.weight.data_ptr(),
+                                        norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt, f("mean"), f("invstd"),
+                                        f("scale"), f("shift"), st), "vtb_bn_finalize")
+        else:
+            # frozen statistics but autograd requested: affine from running stats, mean/invstd kept for backward
+            check(L.vtb_bn_eval_affine(cout, norm.weight.data_ptr(), norm.bias.data_ptr(), norm.running_mean.data_ptr(),
+                                       norm.running_var.data_ptr(), norm.eps, f("scale"), f("shift"), st),
+                  "vtb_bn_eval_affine")
+            mean = run.stat_view_f32(op.st["mean"], cout, sbase)
+            invstd = run.stat_view_f32(op.st["invstd"], cout, sbase)
+            mean.copy_(norm.running_mean)
+            invstd.copy_(torch.rsqrt(norm.running_var + norm.eps))
+        check(L.vtb_bn_act(abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"), f("shift"), int(op.relu),
+                           res_p, res_ld, abase + out.byte_offset(), out.ld, st), "vtb_bn_act")
+
+    # -- backward
+    def backward(self, run: Run, gouts):
+        g, L = self.g, self.L
+        if not g.need_grad:
+            raise RuntimeError("this plan was built without gradient support")
+        st = self._stream()
+        dev = run.act.device
+        abase, sbase = run.act.data_ptr(), (run.stat.data_ptr() + 255) // 256 * 256
+        gact = torch.empty(g.grad_bytes, dtype=torch.uint8, device=dev)  # mirrors the "act" prefix of the arena
+        gbase = gact.data_ptr()
+        dyraw = torch.empty(g.dy_bytes + 1024, dtype=torch.uint8, device=dev)
+        dybase = (dyraw.data_ptr() + 1023) // 1024 * 1024
+        ws = torch.empty(g.ws_bytes + 1024, dtype=torch.uint8, device=dev)
+        wsbase = (ws.data_ptr() + 1023) // 1024 * 1024
+        pgrads = [torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format) for p in g.params]
+        world = self.dist.world if (self.dist is not None and self.dist.sync_bn) else 1
+
+        # which gradient memory is already valid: buffer idx -> list of (c0, c1)
+        init: dict[int, list[tuple[int, int]]] = {}
+
+        def gview(t: TView) -> TView:
+            while t.grad_alias is not None:
+                t = t.grad_alias
+            return t
+
+        def is_init(t: TView) -> bool:
+            t = gview(t)
+            return any(a <= t.coff and t.coff + t.c <= b for a, b in init.get(t.buf.idx, ()))
+
+        def mark(t: TView) -> None:
+            t = gview(t)
+            init.setdefault(t.buf.idx, []).append((t.coff, t.coff + t.c))
+
+        def gp(t: TView) -> int:
+            return gbase + gview(t).byte_offset()
+
+        def gld(t: TView) -> int:
+            return gview(t).ld
+
+        # seed with the incoming feature-map gradients
+        for t, go in zip(g.outputs, gouts):
+            if go is None:
+                continue
+            go = go.detach()
+            if go.dtype != torch.bfloat16:
+                go = go.to(torch.bfloat16)
+            go = go.contiguous(memory_format=torch.channels_last)
+            check(L.vtb_grad_add(gp(t), gld(t), go.data_ptr(), t.c, t.pixels, t.c, int(is_init(t)), st), "vtb_grad_add")
+            mark(t)
+
+        handles = []
+        for i in range(len(g.ops) - 1, -1, -1):
+            op = g.ops[i]
+            if not is_init(op.out):
+                # no gradient reaches this op: its parameters get zero gradient
+                if op.kind in ("conv", "ese"):
+                    n_p = 3 if op.kind == "conv" else 2
+                    for j in range(n_p):
+                        pgrads[op.pidx + j].zero_()
+                continue
+            if op.kind == "conv":
+                self._conv_backward(op, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world)
+            elif op.kind == "pool":
+                xx, oo = op.x, op.out
+                if not (xx.is_input and not run.x_requires_grad):
+                    check(L.vtb_maxpool3s2_bwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h, xx.w, xx.c, gp(oo), gld(oo),
+                                               gp(xx), gld(xx), int(is_init(xx)), st), "vtb_maxpool3s2_bwd")
+                    mark(xx)
+            elif op.kind == "ese":
+                xx, oo, rr = op.x, op.out, op.residual
+                lin = op.mod.linear
+                check(L.vtb_ese_bwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h * xx.w, xx.c, lin.weight.data_ptr(),
+                                    sbase + 4 * op.st["pool"], sbase + 4 * op.st["z"], sbase + 4 * op.st["gate"],
+                                    gp(oo), gld(oo), gp(xx), gld(xx), int(is_init(xx)),
+                                    pgrads[op.pidx].data_ptr(), pgrads[op.pidx + 1].data_ptr(), 0,
+                                    sbase + 4 * op.st["scratch"], st), "vtb_ese_bwd")
+                mark(xx)
+                if rr is not None and gview(rr) is not gview(oo):
+                    check(L.vtb_grad_add(gp(rr), gld(rr), gp(oo), gld(oo), oo.pixels, oo.c, int(is_init(rr)), st),
+                          "vtb_grad_add")
+                    mark(rr)
+
+        gx = None
+        if run.x_requires_grad:
+            t = g.input
+            if is_init(t):
+                gin = self.view_tensor(gact, t)[:, : run.x_shape[1]]
+                gx = gin.to(run.x_dtype).contiguous()
+            else:
+                gx = torch.zeros(run.x_shape, dtype=run.x_dtype, device=dev)
+        # cast parameter gradients to the parameter dtype if a user keeps non-fp32 masters
+        out_grads = [pg if pg.dtype == p.dtype else pg.to(p.dtype) for pg, p in zip(pgrads, g.params)]
+        return gx, out_grads
+
+    def _conv_backward(self, op: ConvOp, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world):
+        g, L = self.g, self.L
+        geom, cout = op.geom, op.geom.cout
+        x, y, out, res = op.x, op.y, op.out, op.residual
+        f = lambda name: sbase + 4 * op.st[name]
+        dout_p, dout_ld = gp(out), gld(out)
+        check(L.vtb_bn_bwd_reduce(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
+                                  f("shift"), f("mean"), f("invstd"), int(op.relu), f("partial_b"), st),
+              "vtb_bn_bwd_reduce")
+        dgamma, dbeta = pgrads[op.pidx + 1].data_ptr(), pgrads[op.pidx + 2].data_ptr()
+        count = float(out.pixels)
+        if g.training and world > 1:
+            check(L.vtb_bn_bwd_finalize(f("partial_b"), op.rows_b, 0, 0, count, cout, 0, 0, 0, 0, f("lsums_b"), st),
+                  "vtb_bn_bwd_finalize(local)")
+            sums = run.stat_view_f64(op.st["sums_b"], cout * 2, sbase)
+            sums.copy_(run.stat_view_f64(op.st["lsums_b"], cout * 2, sbase))
+            self.dist.all_reduce_(sums)
+            check(L.vtb_bn_bwd_finalize(0, 0, f("sums_b"), f("lsums_b"), count * world, cout, dgamma, dbeta, 0,
+                                        f("coef"), 0, st), "vtb_bn_bwd_finalize")
+        else:
+            check(L.vtb_bn_bwd_finalize(f("partial_b"), op.rows_b, 0, 0, count, cout, dgamma, dbeta, 0, f("coef"), 0,
+                                        st), "vtb_bn_bwd_finalize")
+            if not g.training:
+                # frozen statistics: mean/var are constants, so dy = scale * dz (no mean-subtraction terms)
+                run.stat_view_f32(op.st["coef"], cout * 2, sbase).zero_()
+        check(L.vtb_bn_bwd_apply(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
+                                 f("shift"), f("mean"), f("invstd"), int(op.relu), f("coef"), dybase, cout, st),
+              "vtb_bn_bwd_apply")
+        _, wd = self._packed(op, L, st)
+        if not (x.is_input and not run.x_requires_grad):
+            check(L.vtb_conv_dgrad(C.byref(geom), dybase, cout, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
+                  "vtb_conv_dgrad")
+            mark(x)
+        check(L.vtb_conv_wgrad(C.byref(geom), dybase, cout, abase + x.byte_offset(), x.ld, wsbase,
+                               pgrads[op.pidx].data_ptr(), op.cin_real, 0, st), "vtb_conv_wgrad")
+        if res is not None:
+            rv = res
+            while rv.grad_alias is not None:
+                rv = rv.grad_alias
+            ov = out
+            while ov.grad_alias is not None:
+                ov = ov.grad_alias
+            if rv is not ov:
+                check(L.vtb_grad_add(gp(res), gld(res), dout_p, dout_ld, out.pixels, out.c, int(is_init(res)), st),
+                      "vtb_grad_add")
+                mark(res)
+            # aliased: the gradient of `res` already sits in out's gradient memory (initialised by definition)
+
+
+def _stat_view_f32(self, off_floats: int, n: int, sbase: int) -> torch.Tensor:
+    start = (sbase - self.stat.data_ptr()) // 4 + off_floats
+    return self.stat[start : start + n]
+
+
+def _stat_view_f64(self, off_floats: int, n: int, sbase: int) -> torch.Tensor:
+    start = (sbase - self.stat.data_ptr()) // 4 + off_floats
+    return self.stat[start : start + 2 * n].view(torch.float64)
+
+
+Run.stat_view_f32 = _stat_view_f32
+Run.stat_view_f64 = _stat_view_f64
+
+
+# ----------------------------------------------------------------------------------------------------
+# autograd glue + plan cache
+# ----------------------------------------------------------------------------------------------------
+class _NativeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner: Runner, x: torch.Tensor, *params):
+        outs, run = runner.forward(x)
+        ctx.runner, ctx.run = runner, run
+        return tuple(outs)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):
+        gx, pgrads = ctx.runner.backward(ctx.run, gouts)
+        ctx.run = None
+        return (None, gx, *pgrads)
+
+
+def run_native(module: nn.Module, x: torch.Tensor) -> list[torch.Tensor]:
+    """Execute `module` (anything with ``_emit(graph, tview) -> tview | list[tview]``) on a CUDA tensor."""
+    if not x.is_cuda:
+        raise ValueError("run_native expects a CUDA tensor")
+    if x.dim() != 4:
+        raise ValueError(f"expected an (N, C, H, W) tensor, got shape {tuple(x.shape)}")
+    need_grad = torch.is_grad_enabled() and (
+        x.requires_grad or any(p.requires_grad for p in module.parameters())
+    )
+    key = (tuple(x.shape), module.training, need_grad, x.device.index)
+    plans = module.__dict__.setdefault("_vtb_plans", {})
+    runner = plans.get(key)
+    if runner is None:
+        with torch.cuda.device(x.device):
+            g = Graph(module.training, need_grad)
+            t_in = g.input_image(*x.shape)
+            outs = module._emit(g, t_in)
+            if isinstance(outs, TView):
+                outs = [outs]
+            for t in outs:
+                g.mark_output(t)
+            g.finalize()
+            runner = Runner(g, x.device)
+        plans[key] = runner
+        if len(plans) > 8:  # bound the cache (each plan only holds metadata)
+            plans.pop(next(iter(plans)))
+    runner.dist = module.__dict__.get("_vtb_dist")
+    with torch.cuda.device(x.device):
+        if need_grad:
+            outs = _NativeFn.apply(runner, x, *runner.g.params)
+        else:
+            outs, _ = runner.forward(x)
+    return list(outs)
