@@ -257,10 +257,12 @@ class Graph:
                 off += _round_up(b.nbytes, 1024)
         self.act_bytes = off
         # Residual gradient aliasing: for out = res + f(res) the gradient of `res` can live in the gradient memory
-        # of `out` (every other contribution is accumulated into it) iff nothing consumes `res` after this op.
+        # of `out` (every other contribution is accumulated into it) iff nothing consumes `res` after this op
+        # and `res` is a standalone tensor.
         for i, op in enumerate(self.ops):
             res = getattr(op, "residual", None)
-            if res is not None and not res.is_output and not res.is_input and max(res.consumers) == i:
+            if (res is not None and not res.is_output and not res.is_input and max(res.consumers) == i
+                    and res.buf.exclusive_owner is res):  # a concat slice also receives gradient through the full view
                 res.grad_alias = op.out
 
 
@@ -328,7 +330,7 @@ class Runner:
         """Zero-copy logical-NCHW (channels_last strided) bf16 tensor over a view of the arena."""
         base = arena[t.buf.offset : t.buf.offset + t.buf.nbytes].view(torch.bfloat16)
         ld = t.ld
-        return base.as_strided((t.n, t.c, t.h, t.w), (t.h * t.w * ld, 1, t.w * ld, ld), t.coff)
+        return base.as_strided((t.n, t.c, t.h, t.w), (t.h * t.w * ld, 1, t.w * ld, ld), base.storage_offset() + t.coff)
 
     # -- forward
     def forward(self, x: torch.Tensor):
@@ -470,9 +472,20 @@ class Runner:
             check(L.vtb_grad_add(gp(t), gld(t), go.data_ptr(), t.c, t.pixels, t.c, int(is_init(t)), st), "vtb_grad_add")
             mark(t)
 
-        handles = []
+        pending: list[tuple[TView, TView]] = []
+
+        def flush_pending(force_for: Optional[TView]) -> None:
+            for item in list(pending):
+                rr, src = item
+                if is_init(rr) or rr is force_for:
+                    check(L.vtb_grad_add(gp(rr), gld(rr), gp(src), gld(src), src.pixels, src.c, int(is_init(rr)), st),
+                          "vtb_grad_add")
+                    mark(rr)
+                    pending.remove(item)
+
         for i in range(len(g.ops) - 1, -1, -1):
             op = g.ops[i]
+            flush_pending(op.out)
             if not is_init(op.out):
                 # no gradient reaches this op: its parameters get zero gradient
                 if op.kind in ("conv", "ese"):
@@ -498,13 +511,15 @@ class Runner:
                                     sbase + 4 * op.st["scratch"], st), "vtb_ese_bwd")
                 mark(xx)
                 if rr is not None and gview(rr) is not gview(oo):
-                    check(L.vtb_grad_add(gp(rr), gld(rr), gp(oo), gld(oo), oo.pixels, oo.c, int(is_init(rr)), st),
-                          "vtb_grad_add")
-                    mark(rr)
+                    # `rr` may be slice 0 of a concat buffer whose gradient is about to be (over)written as a whole
+                    # by out_conv's dgrad: defer the identity contribution until that memory is initialised
+                    pending.append((rr, oo))
+            flush_pending(False)
 
         gx = None
         if run.x_requires_grad:
             t = g.input
+            flush_pending(t)
             if is_init(t):
                 gin = self.view_tensor(gact, t)[:, : run.x_shape[1]]
                 gx = gin.to(run.x_dtype).contiguous()
