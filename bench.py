@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native ConvNormAct/Darknet/VoVNet path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model cspdarknet53 ...]
+
+Metric (BASELINE.json): train images/sec, CSPDarknet-53, 176 px, batch 256 per GPU, bf16, synthetic
+ImageNet-shaped data, random-init weights.  One "step" = forward + loss + backward + SGD update of
+backbone + classifier head (reference classifier.py:59-64, 83-95, 141-169), data-parallel with SyncBN for N > 1.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` includes the pinned-host -> device
+copy of every step's images/labels and a device -> host read of the loss.  `roofline` describes the dominant
+kernel (the tcgen05 implicit-GEMM convolution), `cpu_baseline` times the CPU oracle port of the same step.
+`--impl reference` times the reference's CPU path (oracle port; the reference is pure Python over torch CPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+MODELS = {
+    # name: (family, factory args, train GFLOP/img at `res` from BASELINE.md §2, default res, default batch/GPU)
+    "cspdarknet53": ("darknet", 17.83, 176, 256),
+    "darknet53": ("darknet", 27.16, 176, 256),
+    "darknet19": ("darknet", 16.36, 224, 256),
+    "vovnet99_ese": ("vovnet", 103.09, 224, 128),
+}
+
+
+def build_model(name: str):
+    from vision_toolbox_b200 import backbones
+
+    return getattr(backbones, name)()
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"tflops": d["bf16_tflops_sustained"], "tflops_burst": d["bf16_tflops"], "gbs": d["hbm_gbs"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class ProfilingLib:
+    """Proxy over the ctypes library that brackets every C-ABI call with CUDA events on the launching stream."""
+
+    def __init__(self, real):
+        self._real, self.records = real, []
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+        if not name.startswith("vtb_") or name in ("vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows",
+                                                   "vtb_conv_wgrad_workspace_bytes", "vtb_launch_count"):
+            return fn
+
+        def wrapped(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            self.records.append((name, args[0] if name.startswith("vtb_conv_") else None, e0, e1))
+            return rc
+
+        return wrapped
+
+
+def conv_flops(geom, cin_real=None) -> float:
+    g = geom._obj if hasattr(geom, "_obj") else geom
+    ho = (g.h + 2 * g.pad - g.k) // g.stride + 1
+    wo = (g.w + 2 * g.pad - g.k) // g.stride + 1
+    cin = g.cin if g.cin > 16 or cin_real is None else cin_real
+    return 2.0 * g.n * ho * wo * g.cout * g.k * g.k * cin
+
+
+def reference_arm(args, rank: int, world: int) -> None:
+    """CPU reference path: the oracle port of the training step on the host cores (bounded sample)."""
+    if rank != 0:
+        return
+    from oracle import vt_oracle as O
+
+    fam, gflop, res, _ = MODELS[args.model]
+    res = args.res or res
+    nb = args.cpu_batch
+    torch.manual_seed(0)
+    model = build_model(args.model)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    head_w = (torch.randn(1000, model.out_channels_list[-1]) * 0.01).requires_grad_(True)
+    head_b = torch.zeros(1000, requires_grad=True)
+    plist = list(params.values()) + [head_w, head_b]
+    mom = [torch.zeros_like(p) for p in plist]
+    x = torch.rand(nb, 3, res, res)
+    y = torch.randint(0, 1000, (nb,))
+
+    def step():
+        new_stats = {}
+        loss = O.classifier_loss(fam, sd, head_w, head_b, x, y, "fp32", 0.1, new_stats)
+        grads = torch.autograd.grad(loss, plist)
+        with torch.no_grad():
+            for p, g, m in zip(plist, grads, mom):
+                m.mul_(0.9).add_(g)
+                p.add_(m, alpha=-0.05)
+            for k, v in new_stats.items():
+                sd[k] = v
+        return float(loss)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = nb / dt
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "train images/sec", "value": val, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} train step {res}px, CPU sample batch {nb}", "model": args.model},
+        "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {nb} @ {res}px through oracle/vt_oracle.py (torch CPU fp32)"},
+        "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(model_name: str, res: int, seconds: float = 15.0) -> dict:
+    from oracle import vt_oracle as O
+
+    fam = MODELS[model_name][0]
+    torch.manual_seed(0)
+    model = build_model(model_name)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    head_w = (torch.randn(1000, model.out_channels_list[-1]) * 0.01).requires_grad_(True)
+    head_b = torch.zeros(1000, requires_grad=True)
+    nb = 8
+    x, y = torch.rand(nb, 3, res, res), torch.randint(0, 1000, (nb,))
+
+    def step():
+        loss = O.classifier_loss(fam, sd, head_w, head_b, x, y, "fp32", 0.1, {})
+        torch.autograd.grad(loss, params + [head_w, head_b])
+
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step(); n += 1
+        if time.perf_counter() - t0 > seconds or n >= 20:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": nb / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} fwd+bwd steps of batch {nb} @ {res}px, oracle/vt_oracle.py on torch CPU fp32"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="cspdarknet53", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--res", type=int, default=0)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sync-bn", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+
+    from vision_toolbox_b200 import _lib, parallel
+
+    fam, gflop_img, dres, dbatch = MODELS[args.model]
+    res, nb = args.res or dres, args.batch or dbatch
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    torch.manual_seed(0)
+    model = build_model(args.model).to(dev).train()
+    head = torch.nn.Linear(model.out_channels_list[-1], 1000).to(dev)
+    trainer = parallel.Trainer(model, head, lr=0.05, momentum=0.9, weight_decay=2e-5, label_smoothing=0.1,
+                               sync_bn=not args.no_sync_bn, process_group=dist.group.WORLD if world > 1 else None)
+
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    n_host = 2
+    host_x = [torch.rand(nb, 3, res, res, generator=g).pin_memory() for _ in range(n_host)]
+    host_y = [torch.randint(0, 1000, (nb,), generator=g).pin_memory() for _ in range(n_host)]
+    dev_x = [h.to(dev) for h in host_x]
+    dev_y = [h.to(dev) for h in host_y]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ----------------
+    for i in range(W):
+        trainer.step(dev_x[i % n_host], dev_y[i % n_host])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = trainer.step(dev_x[i % n_host], dev_y[i % n_host])
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    clocks = sampler.stop() if rank == 0 else None
+    value = nb * world * K / (ms_total / 1e3)
+    final_loss = float(loss)
+
+    # ---------------- end to end: pinned host -> device every step, loss read back every step ----------------
+    copy_stream = torch.cuda.Stream(dev)
+    bufs_x = [torch.empty_like(dev_x[0]) for _ in range(2)]
+    bufs_y = [torch.empty_like(dev_y[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            bufs_x[s].copy_(host_x[i % n_host], non_blocking=True)
+            bufs_y[s].copy_(host_y[i % n_host], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            consumed[s].record()
+        prefetch(0)
+        out = 0.0
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[s])
+            l = trainer.step(bufs_x[s], bufs_y[s])
+            consumed[s].record()
+            out = float(l)  # device -> host read of the step's result
+        return out
+
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_loop(K)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = nb * world * K / (float(ms2) / 1e3)
+    h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
+
+    # ---------------- roofline of the dominant kernel (instrumented extra step, rank 0) ----------------
+    roofline, breakdown = None, None
+    if rank == 0:
+        from vision_toolbox_b200 import engine
+
+        prof = ProfilingLib(_lib.lib())
+        runners = list(model.__dict__.get("_vtb_plans", {}).values())
+        for r in runners:
+            r.L = prof
+        torch.cuda.synchronize()
+        torch.cuda._sleep(30_000_000)  # let the host run ahead so event intervals contain no launch gaps
+        trainer.step(dev_x[0], dev_y[0])
+        torch.cuda.synchronize()
+        for r in runners:
+            r.L = _lib.lib()
+        agg = {}
+        for name, geom, a, b in prof.records:
+            t = a.elapsed_time(b)
+            fl = conv_flops(geom) if geom is not None and name in ("vtb_conv_fprop", "vtb_conv_dgrad", "vtb_conv_wgrad") else 0.0
+            d = agg.setdefault(name, [0.0, 0.0, 0])
+            d[0] += t; d[1] += fl; d[2] += 1
+        pk = peaks()
+        igemm_ms = agg.get("vtb_conv_fprop", [0, 0, 0])[0] + agg.get("vtb_conv_dgrad", [0, 0, 0])[0]
+        igemm_fl = agg.get("vtb_conv_fprop", [0, 0, 0])[1] + agg.get("vtb_conv_dgrad", [0, 0, 0])[1]
+        igemm_n = agg.get("vtb_conv_fprop", [0, 0, 0])[2] + agg.get("vtb_conv_dgrad", [0, 0, 0])[2]
+        achieved = igemm_fl / (igemm_ms / 1e3) / 1e12 if igemm_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (fprop + dgrad launches)", "achieved": achieved,
+                    "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                    "peak_source": pk["source"] + ", sustained cuBLAS bf16", "launches": igemm_n,
+                    "avg_launch_ms": igemm_ms / max(igemm_n, 1)}
+        tot = sum(v[0] for v in agg.values())
+        breakdown = {k: {"ms": round(v[0], 3), "share": round(v[0] / tot, 3), "calls": v[2],
+                         **({"tflops": round(v[1] / (v[0] / 1e3) / 1e12, 1)} if v[1] else {})}
+                     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.model, res)
+
+    if rank == 0:
+        pk = peaks()
+        line = {
+            "metric": "train images/sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model} train step (fwd+loss+bwd+SGD), {res}px, batch {nb}/GPU, bf16, "
+                                   f"{'SyncBN+DDP' if world > 1 else 'single GPU'}",
+                       "model": args.model, "global_batch": nb * world, "resolution": res,
+                       "parallelism": f"dp{world}", "l2_policy": "inputs+activations >> L2 (multi-GB working set per step)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "model_tflops": value * gflop_img / 1e3,
+            "model_frac_of_tensor_peak": value * gflop_img / 1e3 / pk["tflops"],
+            "final_loss": final_loss,
+            "kernel_breakdown": breakdown,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
