@@ -301,6 +301,7 @@ class Runner:
         self.device = device
         self.L = _lib.lib()
         self.dist: Optional[DistConfig] = None
+        self.grad_sink = False
 
     # -- helpers
     def _stream(self) -> int:
@@ -436,7 +437,17 @@ class Runner:
         dybase = (dyraw.data_ptr() + 1023) // 1024 * 1024
         ws = torch.empty(g.ws_bytes + 1024, dtype=torch.uint8, device=dev)
         wsbase = (ws.data_ptr() + 1023) // 1024 * 1024
-        pgrads = [torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format) for p in g.params]
+        # parameter gradients: fresh fp32 tensors handed to autograd, or (grad_sink mode, used by parallel.Trainer)
+        # written straight into the existing fp32 `.grad` storage — e.g. views of one flat all-reduce buffer —
+        # which skips autograd's per-parameter accumulate kernels.  Sink mode OVERWRITES .grad.
+        pgrads, direct = [], []
+        for p in g.params:
+            gr = p.grad if self.grad_sink else None
+            if gr is not None and gr.dtype == torch.float32 and gr.is_contiguous() and gr.device == dev:
+                pgrads.append(gr); direct.append(True)
+            else:
+                pgrads.append(torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format))
+                direct.append(False)
         world = self.dist.world if (self.dist is not None and self.dist.sync_bn) else 1
 
         # which gradient memory is already valid: buffer idx -> list of (c0, c1)
@@ -526,7 +537,8 @@ class Runner:
             else:
                 gx = torch.zeros(run.x_shape, dtype=run.x_dtype, device=dev)
         # cast parameter gradients to the parameter dtype if a user keeps non-fp32 masters
-        out_grads = [pg if pg.dtype == p.dtype else pg.to(p.dtype) for pg, p in zip(pgrads, g.params)]
+        out_grads = [None if d else (pg if pg.dtype == p.dtype else pg.to(p.dtype))
+                     for pg, p, d in zip(pgrads, g.params, direct)]
         return gx, out_grads
 
     def _conv_backward(self, op: ConvOp, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world):
@@ -600,6 +612,7 @@ class _NativeFn(torch.autograd.Function):
     def forward(ctx, runner: Runner, x: torch.Tensor, *params):
         outs, run = runner.forward(x)
         ctx.runner, ctx.run = runner, run
+        ctx.set_materialize_grads(False)  # unused feature maps get no zero-filled gradient tensors
         return tuple(outs)
 
     @staticmethod
@@ -637,6 +650,7 @@ def run_native(module: nn.Module, x: torch.Tensor) -> list[torch.Tensor]:
         if len(plans) > 8:  # bound the cache (each plan only holds metadata)
             plans.pop(next(iter(plans)))
     runner.dist = module.__dict__.get("_vtb_dist")
+    runner.grad_sink = bool(module.__dict__.get("_vtb_grad_sink", False))
     with torch.cuda.device(x.device):
         if need_grad:
             outs = _NativeFn.apply(runner, x, *runner.g.params)

@@ -69,6 +69,8 @@ class Trainer:
         for p, n in zip(self.params, sizes):
             p.grad = self.flat[off : off + n].view_as(p)
             off += n
+        # the native backward writes backbone gradients straight into these views (engine.Runner grad_sink mode)
+        backbone.__dict__["_vtb_grad_sink"] = True
         self.buckets = bucket_ranges(sizes, int(bucket_mb * 1024 * 1024 / 4))
         decay, no_decay = split_decay_groups([backbone, head])
         self.opt = torch.optim.SGD(
