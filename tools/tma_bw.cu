@@ -46,7 +46,7 @@ tma_bw_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ Pa
   const int per = p.stages / p.producers;
   const long long t0 = clock64();
   if (warp < p.producers) {
-    if (lane == 0) {
+    if (elect_one()) {
       const int s0 = warp * per;
       uint32_t phase = 0;
       int st = 0;
@@ -107,20 +107,22 @@ int main() {
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   printf("%-8s %5s %5s %3s %3s %4s | %9s %9s %8s\n", "mode", "rowB", "rows", "S", "P", "cta", "B/cyc/SM", "GB/s", "cyc/row");
-  for (size_t ws_mb : {32, 1024})
+  for (size_t ws_mb : {32})
   for (int mode = 0; mode < 2; ++mode)
     for (int rb : {32, 64, 128})
-      for (int rows : {128, 256})
-        for (int ctas_per_sm : {1, 2})
-          for (int producers : {1, 2}) {
-            if (mode == 1 && rows > 256) continue;
+      for (int rows : {128, 256, 512, 1024})
+        for (int ctas_per_sm : {1})
+          for (int producers : {1, 2, 3}) {
+            if (mode == 0 && rows > 256) continue;
+            if (rows > 256 && rb == 128 && rows * rb * 3 > 200000) continue;
             Params p{};
             p.mode = mode;
             p.row_bytes = rb;
             p.rows = rows;
             const int C = rb / 2;
-            p.stages = (ctas_per_sm == 1 ? 6 : 3) * 1;
-            if (producers == 2) p.stages = (p.stages / 2) * 2;
+            p.stages = 6;
+            while (p.stages * (((rows * rb) + 1023) & ~1023) > 200000) --p.stages;
+            p.stages = (p.stages / producers) * producers;
             if (p.stages < producers) continue;
             p.producers = producers;
             p.iters = 4000 / producers;

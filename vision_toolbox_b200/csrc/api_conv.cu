@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/vtb.h"
@@ -54,16 +55,74 @@ static void out_hw(const VtbConv* c, int* ho, int* wo) {
   *ho = (c->h + 2 * c->pad - c->k) / c->stride + 1;
   *wo = (c->w + 2 * c->pad - c->k) / c->stride + 1;
 }
-static int conv_stages(int block_n) {
-  const int per_stage = kBlockM * kStageK * 2 + ((block_n * kStageK * 2 + 1023) / 1024) * 1024;
-  const int fixed = 2 * kBlockM * 128 + 256 + 1024;
-  int s = (232448 - fixed) / per_stage;
-  return std::max(2, std::min(s, 8));
+// development overrides (tools/bench_conv): VTB_BLOCK_M / VTB_BLOCK_N / VTB_STAGES, read once per process
+static int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
 }
-static int conv_grid(long long M, int cout, int block_n) {
-  const long long tiles = ((M + kBlockM - 1) / kBlockM) * (cout / block_n);
-  const int sms = std::max(1, num_sms());
-  return (int)std::min<long long>(tiles, sms);
+static unsigned long long* g_dbg = nullptr;
+// Tiling decisions of one conv_igemm_kernel launch (GEMM: M pixels x ncols channels).
+struct ConvTiling {
+  int block_m, block_n, panel_w, stages, panel_bufs, grid, n_blocks, stat_rows, ksplit;
+};
+// M pixels x ncols channels, K = total_k16 slices of 16 elements
+static ConvTiling plan_conv_tiling(long long M, int ncols, int total_k16) {
+  ConvTiling t;
+  const int sms = num_sms() > 0 ? num_sms() : 148;
+  t.block_n = block_of(ncols);
+  static const int o_bn = env_int("VTB_BLOCK_N");
+  if (o_bn >= 16 && ncols % o_bn == 0 && o_bn <= 256) t.block_n = o_bn;
+  // the epilogue keeps per-panel statistics in registers: at most kMaxPanels panels per accumulator
+  while (t.block_n > 16 && t.block_n / std::min(32, chunk_of(t.block_n)) > kMaxPanels) {
+    int b = t.block_n - 16;
+    while (b > 16 && ncols % b) b -= 16;
+    t.block_n = b;
+  }
+  // staged output panels: at most 32 columns (the 16 epilogue warps each stage 32 rows x 64 B), and at least two
+  // panels per accumulator so that all four epilogue groups have work
+  t.panel_w = std::min(32, chunk_of(t.block_n));
+  if (t.block_n / t.panel_w < 2 && t.panel_w > 16) t.panel_w /= 2;
+  t.n_blocks = ncols / t.block_n;
+  // 256-row tiles halve the weight traffic per FLOP and double the bytes per TMA request; use them whenever
+  // there are enough of them to occupy most of the machine
+  const long long tiles256 = ((M + 255) / 256) * t.n_blocks;
+  t.block_m = (tiles256 * 4 >= (long long)sms * 3) ? 256 : 128;
+  static const int o_bm = env_int("VTB_BLOCK_M");
+  if (o_bm == 128 || o_bm == 256) t.block_m = o_bm;
+  const long long tiles = ((M + t.block_m - 1) / t.block_m) * t.n_blocks;
+  long long grid = std::min<long long>(tiles, sms);
+  grid = std::max<long long>(t.n_blocks, grid / t.n_blocks * t.n_blocks);
+  t.grid = (int)grid;
+  const int per_stage = t.block_m * kStageK * 2 + ((t.block_n * kStageK * 2 + 1023) / 1024) * 1024;
+  t.panel_bufs = 1;
+  int s = (kSmemBudget - (kEpiWarps * 2048 + 256 + 1024)) / per_stage;
+  t.stages = std::max(2, std::min(s, 8));
+  // independent accumulation chains (see igemm.cu): up to 4 per tile; a long K loop prefers chains over TMEM
+  // double buffering, a short one (1x1 convolutions) keeps two sets so the epilogue overlaps the next tile
+  {
+    const int halves = t.block_m / kBlockM;
+    const int acc_stride = (t.block_n + 31) & ~31;
+    int ks = 4 / halves;
+    while (ks > 1 && (halves * ks * acc_stride > 512 || ks > total_k16)) ks >>= 1;
+    if (total_k16 < 32)
+      while (ks > 1 && 2 * halves * ks * acc_stride > 512) ks >>= 1;
+    static const int o_ks = env_int("VTB_KSPLIT");
+    if (o_ks > 0 && halves * o_ks * acc_stride <= 512 && o_ks <= total_k16) ks = o_ks;
+    t.ksplit = ks;
+  }
+  static const int o_stages = env_int("VTB_STAGES");
+  if (o_stages > 0) t.stages = std::min(t.stages, o_stages);
+  t.stat_rows = (t.grid / t.n_blocks) * 4 * (t.block_m / kBlockM);  // one row per 32-row slice of a tile
+  return t;
+}
+static void apply_tiling(ConvIgemmParams& p, const ConvTiling& t) {
+  p.dbg = g_dbg;
+  p.block_m = t.block_m;
+  p.block_n = t.block_n;
+  p.panel_w = t.panel_w;
+  p.num_stages = t.stages;
+  p.panel_bufs = t.panel_bufs;
+  p.ksplit = t.ksplit;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -136,6 +195,8 @@ using namespace vtb;
 extern "C" {
 
 const char* vtb_last_error(void) { return g_err; }
+// development aid, not part of include/vtb.h: device buffer of [grid][8] role wait-cycle counters (nullptr = off)
+void vtb_debug_counters(unsigned long long* dev_buf) { g_dbg = dev_buf; }
 int vtb_version(void) { return 100; }
 int vtb_num_sms(void) { return num_sms(); }
 long long vtb_launch_count(void) { return g_launches.load(); }
@@ -150,13 +211,7 @@ int vtb_conv_stats_rows(const VtbConv* c) {
   if (!conv_ok(c)) return fail(VTB_EINVAL, "vtb_conv_stats_rows: bad geometry");
   int ho, wo;
   out_hw(c, &ho, &wo);
-  const int bn = block_of(c->cout);
-  const int pw = chunk_of(bn);
-  const int groups = 256 / pw;
-  // sized for the largest grid we may ever launch (device-independent upper bound: 148-SM B200; queried if present)
-  const int sms = num_sms() > 0 ? num_sms() : 148;
-  const long long tiles = (((long long)c->n * ho * wo + kBlockM - 1) / kBlockM) * (c->cout / bn);
-  return (int)std::min<long long>(tiles, sms) * groups;
+  return plan_conv_tiling((long long)c->n * ho * wo, c->cout, c->k * c->k * c->cin / 16).stat_rows;
 }
 
 size_t vtb_conv_wgrad_workspace_bytes(const VtbConv* c) {
@@ -196,9 +251,10 @@ int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, voi
   p.ntaps = taps;
   p.cin = c->cin;
   p.kc = chunk_of(c->cin);
-  p.block_n = block_of(c->cout);
   p.cout = c->cout;
-  p.num_stages = conv_stages(p.block_n);
+  const ConvTiling tl = plan_conv_tiling(p.M, c->cout, taps * c->cin / 16);
+  apply_tiling(p, tl);
+  p.a_tiled = (c->k == 1 && c->stride == 1 && c->pad == 0) ? 1 : 0;
   for (int r = 0; r < c->k; ++r)
     for (int s = 0; s < c->k; ++s) {
       const int t = r * c->k + s;
@@ -207,7 +263,8 @@ int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, voi
       p.tap_kofs[t] = t * c->cin;
     }
   p.store_mode = kStoreTma;
-  p.panel_w = chunk_of(p.block_n);
+  p.out = (__nv_bfloat16*)y;
+  p.ldo = ldy;
   p.stats_partial = stats_partial;
   p.scale = scale;
   p.shift = shift;
@@ -216,23 +273,19 @@ int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, voi
   p.ldr = ldr;
   const int upper = c->pad - (c->k - 1);
   CUtensorMap tmA, tmB, tmD;
-  if (!tmap_im2col_nhwc(&tmA, x, c->cin, c->w, c->h, c->n, ldx, -c->pad, -c->pad, upper, upper, p.kc, kBlockM,
-                        c->stride, p.kc * 2))
+  if (p.a_tiled) {
+    if (!tmap_tiled_2d(&tmA, x, c->cin, p.M, (uint64_t)ldx * 2, p.kc, p.block_m, p.kc * 2))
+      return fail(VTB_ECUDA, "vtb_conv_fprop: tensor map for x failed");
+  } else if (!tmap_im2col_nhwc(&tmA, x, c->cin, c->w, c->h, c->n, ldx, -c->pad, -c->pad, upper, upper, p.kc,
+                               p.block_m, c->stride, p.kc * 2))
     return fail(VTB_ECUDA, "vtb_conv_fprop: im2col tensor map for x failed");
   if (!tmap_tiled_2d(&tmB, wf, (uint64_t)taps * c->cin, c->cout, (uint64_t)taps * c->cin * 2, p.kc, p.block_n,
                      p.kc * 2))
     return fail(VTB_ECUDA, "vtb_conv_fprop: tensor map for weights failed");
-  if (!tmap_tiled_2d(&tmD, y, c->cout, p.M, (uint64_t)ldy * 2, p.panel_w, kBlockM, p.panel_w * 2))
+  if (!tmap_tiled_2d(&tmD, y, c->cout, p.M, (uint64_t)ldy * 2, p.panel_w, 32, p.panel_w * 2))
     return fail(VTB_ECUDA, "vtb_conv_fprop: tensor map for y failed");
-  const int grid = conv_grid(p.M, c->cout, p.block_n);
-  if (stats_partial) {
-    const int groups = 256 / p.panel_w;
-    int e = (int)cudaMemsetAsync(stats_partial, 0, (size_t)grid * groups * c->cout * 2 * sizeof(float),
-                                 (cudaStream_t)stream);
-    if (e) return check_cuda(e, "stats memset");
-  }
   count_launch(1);
-  return check_cuda(launch_conv_igemm(tmA, tmB, tmD, p, grid, (cudaStream_t)stream), "conv_igemm_kernel(fprop)");
+  return check_cuda(launch_conv_igemm(tmA, tmB, tmD, p, tl.grid, (cudaStream_t)stream), "conv_igemm_kernel(fprop)");
 }
 
 int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
@@ -249,19 +302,19 @@ int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, v
   p.cin = c->cout;   // channels per tap of the activation operand (dY)
   p.cout = c->cin;   // GEMM N
   p.kc = chunk_of(c->cout);
-  p.block_n = block_of(c->cin);
-  p.panel_w = chunk_of(p.block_n);
-  p.num_stages = conv_stages(p.block_n);
   CUtensorMap tmA, tmB, tmD;
-  if (!tmap_tiled_2d(&tmB, wd, (uint64_t)k * k * c->cout, c->cin, (uint64_t)k * k * c->cout * 2, p.kc, p.block_n,
-                     p.kc * 2))
-    return fail(VTB_ECUDA, "vtb_conv_dgrad: tensor map for weights failed");
 
   if (c->stride == 1) {
     if (ho != c->h + 2 * pad - k + 1) return fail(VTB_EINVAL, "vtb_conv_dgrad: internal shape error");
     const int lo = -(k - 1 - pad);
     const int up = -pad;  // positions = ho + up - lo = ho + k - 1 - 2*pad = h
     p.M = c->n * c->h * c->w;
+    const ConvTiling tl = plan_conv_tiling(p.M, c->cin, k * k * c->cout / 16);
+    apply_tiling(p, tl);
+    if (!tmap_tiled_2d(&tmB, wd, (uint64_t)k * k * c->cout, c->cin, (uint64_t)k * k * c->cout * 2, p.kc, p.block_n,
+                       p.kc * 2))
+      return fail(VTB_ECUDA, "vtb_conv_dgrad: tensor map for weights failed");
+    p.a_tiled = (k == 1 && pad == 0) ? 1 : 0;
     p.Wq = c->w;
     p.Hp = c->h;
     p.stride = 1;
@@ -275,17 +328,21 @@ int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, v
         p.tap_kofs[t] = t * c->cout;
       }
     p.store_mode = accumulate ? kStoreTmaAdd : kStoreTma;
-    if (!tmap_im2col_nhwc(&tmA, dy, c->cout, wo, ho, c->n, lddy, lo, lo, up, up, p.kc, kBlockM, 1, p.kc * 2))
+    p.out = (__nv_bfloat16*)dx;
+    p.ldo = lddx;
+    if (p.a_tiled) {
+      if (!tmap_tiled_2d(&tmA, dy, c->cout, p.M, (uint64_t)lddy * 2, p.kc, p.block_m, p.kc * 2))
+        return fail(VTB_ECUDA, "vtb_conv_dgrad: tensor map for dy failed");
+    } else if (!tmap_im2col_nhwc(&tmA, dy, c->cout, wo, ho, c->n, lddy, lo, lo, up, up, p.kc, p.block_m, 1, p.kc * 2))
       return fail(VTB_ECUDA, "vtb_conv_dgrad: im2col tensor map for dy failed");
-    if (!tmap_tiled_2d(&tmD, dx, c->cin, p.M, (uint64_t)lddx * 2, p.panel_w, kBlockM, p.panel_w * 2))
+    if (!tmap_tiled_2d(&tmD, dx, c->cin, p.M, (uint64_t)lddx * 2, p.panel_w, 32, p.panel_w * 2))
       return fail(VTB_ECUDA, "vtb_conv_dgrad: tensor map for dx failed");
     count_launch(1);
-    return check_cuda(launch_conv_igemm(tmA, tmB, tmD, p, conv_grid(p.M, p.cout, p.block_n), (cudaStream_t)stream),
+    return check_cuda(launch_conv_igemm(tmA, tmB, tmD, p, tl.grid, (cudaStream_t)stream),
                       "conv_igemm_kernel(dgrad s1)");
   }
 
   // stride 2: one launch per output-parity phase (ph, pw); each is a dense stride-1 walk over dY.
-  tmD = tmB;  // unused in scatter mode, but must be a valid map
   for (int ph = 0; ph < 2; ++ph) {
     for (int pq = 0; pq < 2; ++pq) {
       const int Hph = (c->h - ph + 1) / 2, Wph = (c->w - pq + 1) / 2;
@@ -304,6 +361,12 @@ int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, v
         }
       ConvIgemmParams q = p;
       q.M = c->n * Hph * Wph;
+      const ConvTiling tl = plan_conv_tiling(q.M, c->cin, nr * ns * c->cout / 16);
+      apply_tiling(q, tl);
+      if (!tmap_tiled_2d(&tmB, wd, (uint64_t)k * k * c->cout, c->cin, (uint64_t)k * k * c->cout * 2, q.kc, q.block_n,
+                         q.kc * 2))
+        return fail(VTB_ECUDA, "vtb_conv_dgrad: tensor map for weights failed");
+      tmD = tmB;  // unused in scatter mode, but must be a valid map
       q.Wq = Wph;
       q.Hp = Hph;
       q.stride = 1;
@@ -333,10 +396,11 @@ int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, v
           q.tap_kofs[t] = (rs[i] * k + ss[j]) * c->cout;
         }
       const int up_h = Hph - ho + lo_h, up_w = Wph - wo + lo_w;
-      if (!tmap_im2col_nhwc(&tmA, dy, c->cout, wo, ho, c->n, lddy, lo_w, lo_h, up_w, up_h, q.kc, kBlockM, 1, q.kc * 2))
+      if (!tmap_im2col_nhwc(&tmA, dy, c->cout, wo, ho, c->n, lddy, lo_w, lo_h, up_w, up_h, q.kc, q.block_m, 1,
+                            q.kc * 2))
         return fail(VTB_ECUDA, "vtb_conv_dgrad: im2col tensor map for dy (phase %d,%d) failed", ph, pq);
       count_launch(1);
-      int e = launch_conv_igemm(tmA, tmB, tmD, q, conv_grid(q.M, q.cout, q.block_n), (cudaStream_t)stream);
+      int e = launch_conv_igemm(tmA, tmB, tmD, q, tl.grid, (cudaStream_t)stream);
       if (e) return check_cuda(e, "conv_igemm_kernel(dgrad s2)");
     }
   }

@@ -16,68 +16,197 @@ static __host__ __device__ inline int round_up_int(int a, int b) { return (a + b
 // ------------------------------------------------------------------------------------------------
 struct ConvSmem {
   uint32_t a_off, b_off, panel_off, bar_off, total;
-  uint32_t b_stage;
+  uint32_t a_stage, b_stage;
 };
-static __host__ __device__ inline ConvSmem conv_smem_layout(int block_n, int num_stages) {
+static __host__ __device__ inline ConvSmem conv_smem_layout(int block_m, int block_n, int num_stages, int panel_bufs) {
   ConvSmem s;
+  s.a_stage = block_m * kStageK * 2;
   s.b_stage = round_up_int(block_n * kStageK * 2, 1024);
   s.a_off = 0;
-  s.b_off = num_stages * (kBlockM * kStageK * 2);
+  s.b_off = num_stages * s.a_stage;
   s.panel_off = s.b_off + num_stages * s.b_stage;
-  s.bar_off = s.panel_off + 2 * (kBlockM * 128);
+  s.bar_off = s.panel_off + kEpiWarps * 2048;  // one 32-row x 64 B staging buffer per epilogue warp
   s.total = s.bar_off + 256;
   return s;
 }
-size_t conv_igemm_smem_bytes(int block_n, int num_stages) {
-  return conv_smem_layout(block_n, num_stages).total + 1024;  // + slack for manual 1024B alignment
+size_t conv_igemm_smem_bytes(int block_m, int block_n, int num_stages, int panel_bufs) {
+  return conv_smem_layout(block_m, block_n, num_stages, panel_bufs).total + 1024;  // + slack for 1024B alignment
 }
 
 __device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ (((off >> 7) & mask) << 4); }
 
+
+// Per-warp drain of a staged bf16 panel of 32 rows x (8*CH) columns (row pitch 16*CH bytes, XOR-swizzled 16-byte
+// chunks): lane = rg * CH + chunk reads chunk `chunk` of the rows of row group rg with 16-byte loads, writes them
+// to global memory (a warp instruction covers whole 16*CH-byte row segments -> coalesced; ADD = read-modify-write
+// for gradient fan-in, rounding like two bf16 tensors being added) and, if STATS, sums its 8 columns; a
+// recursive-halving butterfly across the row groups then leaves the 32-row (sum, sumsq) totals of
+//   CH == 8: columns chunk*8 + (rg&1)*4 + (rg>>1)*2, +1                        -> (o0,o1) and (o2,o3)
+//   CH == 4: column  chunk*8 + (rg&1)*4 + ((rg>>1)&1)*2 + (rg>>2)               -> (o0,o1)
+//   CH == 2: same column formula on rg bits 0..2; lanes with rg bit 3 clear hold the result -> (o0,o1)
+template <int CH, bool ADD, bool STATS>
+__device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloat16* gdst, int ld, int rows_valid,
+                                            float& o0, float& o1, float& o2, float& o3) {
+  constexpr int RG = 32 / CH;          // row groups
+  constexpr int ROWS = 32 / RG;        // rows per group
+  constexpr uint32_t PITCH = 16 * CH;
+  constexpr uint32_t SMASK = (CH == 8) ? 7u : (CH == 4 ? 3u : 1u);
+  const int chunk = lane % CH, rg = lane / CH;
+  float S[8], Q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) S[j] = Q[j] = 0.f;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int rr = rg * ROWS + r;
+    uint32_t w[4];
+    const uint32_t off = swz((uint32_t)rr * PITCH + chunk * 16, SMASK);
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(panel + off));
+    if (rr < rows_valid) {
+      uint4* gp = reinterpret_cast<uint4*>(gdst + (size_t)rr * ld + chunk * 8);
+      if (ADD) {
+        const uint4 ov = *gp;
+        const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(bf16lo(w[j]) + bf16lo(oo[j]), bf16hi(w[j]) + bf16hi(oo[j]));
+      }
+      *gp = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16lo(w[j]), b = bf16hi(w[j]);
+        S[2 * j] += a;
+        Q[2 * j] = fmaf(a, a, Q[2 * j]);
+        S[2 * j + 1] += b;
+        Q[2 * j + 1] = fmaf(b, b, Q[2 * j + 1]);
+      }
+    }
+  }
+  if (STATS) {
+    // butterfly over the row-group bits of the lane index
+    int n = 8;
+#pragma unroll
+    for (int step = 0; (1 << step) < RG; ++step) {
+      const int partner_bit = CH << step;
+      const bool upper = (lane & partner_bit) != 0;
+      if (n > 1) {
+        const int hn = n / 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < hn) {
+            // send the half I do not keep, receive the partner's copy of the half I keep
+            const float sendS = upper ? S[j] : S[j + hn], sendQ = upper ? Q[j] : Q[j + hn];
+            const float keepS = upper ? S[j + hn] : S[j], keepQ = upper ? Q[j + hn] : Q[j];
+            S[j] = keepS + __shfl_xor_sync(0xffffffffu, sendS, partner_bit);
+            Q[j] = keepQ + __shfl_xor_sync(0xffffffffu, sendQ, partner_bit);
+          }
+        }
+        n = hn;
+      } else {
+        S[0] += __shfl_xor_sync(0xffffffffu, S[0], partner_bit);
+        Q[0] += __shfl_xor_sync(0xffffffffu, Q[0], partner_bit);
+      }
+    }
+  }
+  o0 = S[0];
+  o1 = Q[0];
+  o2 = (CH == 8) ? S[1] : 0.f;
+  o3 = (CH == 8) ? Q[1] : 0.f;
+}
+template <bool ADD, bool STATS>
+__device__ __forceinline__ void panel_drain_pw(int pw, uint32_t panel, int lane, __nv_bfloat16* gdst, int ld,
+                                               int rows_valid, float& o0, float& o1, float& o2, float& o3) {
+  if (pw == 32) panel_drain<4, ADD, STATS>(panel, lane, gdst, ld, rows_valid, o0, o1, o2, o3);
+  else panel_drain<2, ADD, STATS>(panel, lane, gdst, ld, rows_valid, o0, o1, o2, o3);
+}
+
+// mbarrier wait that optionally accounts the stalled cycles (development counters, ConvIgemmParams::dbg)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool timed, long long& acc) {
+  if (!timed) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // conv_igemm_kernel
+//
+// Persistent, warp-specialised. One tile = block_m (128 | 256) output pixels x block_n channels; a CTA keeps ONE
+// n-block for its whole life (tile = m_blk * n_blocks + n_blk with n_blk = blockIdx.x % n_blocks), so the weight
+// tile stays hot in L2 and the per-channel statistics can be accumulated in registers across tiles.
+//
+// TMA issue rate, not bandwidth, bounds the operand feed on B200 (profiles/r01_tma_bw.txt: one im2col request
+// stream moves a <=256-row box per ~625 cycles whatever its size), hence: 256-row A boxes, and THREE independent
+// producer threads (A even stages / A odd stages / B).
+//   warp 0, 3 : A producers (im2col or tiled TMA), alternating pipeline stages
+//   warp 2    : B (weight) producer
+//   warp 1    : TMEM owner + MMA issuer (two M=128 UMMAs per K step when block_m == 256, same B descriptor)
+//   warps 4-7 / 8-11 : two epilogue groups, each draining its own 128-row accumulator
+// TMEM: back-to-back MMAs into ONE accumulator serialise on a ~170-cycle dependency (profiles/r01_mma_rate.txt), so
+// every 128-row half owns `ksplit` accumulators fed round-robin with successive K slices (summed in the epilogue):
+// chains = halves * ksplit independent accumulation chains of block_n columns form one "set"; 512 / set columns
+// (max 2) sets give double buffering against the epilogue when the tile is narrow.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNumThreads, 1)
+// EPI selects the epilogue flavour at compile time (each instantiation only carries the registers it needs):
+//   kEpiStats   dense store + BatchNorm statistics (training fprop)
+//   kEpiAffine  dense store of [relu](acc*scale+shift)[+residual] (eval-mode fused fprop)
+//   kEpiPlain   dense store or read-modify-write accumulate (stride-1 dgrad, fprop without statistics)
+//   kEpiScatter strided per-row store / accumulate (stride-2 dgrad phases)
+enum EpiKind : int { kEpiStats = 0, kEpiAffine = 1, kEpiPlain = 2, kEpiScatter = 3 };
+
+template <bool TIMED, int EPI>
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ ConvIgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const ConvSmem L = conv_smem_layout(p.block_n, p.num_stages);
   const int S = p.num_stages;
-
-  const uint32_t a_base = base + L.a_off;
-  const uint32_t b_base = base + L.b_off;
-  const uint32_t panel_base = base + L.panel_off;
-  const uint32_t bar_base = base + L.bar_off;
+  // everything below is either a kernel parameter (constant bank, costs no register) or one add away from one
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + p.b_off;
+  const uint32_t panel_base = base + p.panel_off;
+  const uint32_t bar_base = base + p.bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
-  uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to aligned base
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 4 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool timed = TIMED;   // development counters (ConvIgemmParams::dbg); compiled out of the production kernel
+  const long long t_start = timed ? clock64() : 0;
 
-  const int num_m_blocks = (p.M + kBlockM - 1) / kBlockM;
-  const int n_blocks = p.cout / p.block_n;
-  const int num_tiles = num_m_blocks * n_blocks;
-  const int kc = p.kc;
-  const int chunks_per_tap = p.cin / kc;
-  const int total_chunks = p.ntaps * chunks_per_tap;
-  const int subs_per_stage = kStageK / kc;
-  const int num_k_stages = (total_chunks + subs_per_stage - 1) / subs_per_stage;
-  const uint32_t a_sub_bytes = kBlockM * kc * 2;
-  const uint32_t b_sub_bytes = p.block_n * kc * 2;
+#define halves p.halves
+#define ksplit p.ksplit
+#define acc_stride p.acc_stride
+#define set_cols p.set_cols
+#define nsets p.nsets
+#define num_m_blocks p.num_m_blocks
+#define n_blocks p.n_blocks
+#define m_step p.m_step
+#define kc p.kc
+#define chunks_per_tap p.chunks_per_tap
+#define total_chunks p.total_chunks
+#define subs_per_stage p.subs_per_stage
+#define num_k_stages p.num_k_stages
+#define a_sub_bytes p.a_sub_bytes
+#define a_half_bytes p.a_half_bytes
+#define b_sub_bytes p.b_sub_bytes
+  const int n_blk = blockIdx.x % n_blocks;
+  const int m_first = blockIdx.x / n_blocks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 2);   // one arrive.expect_tx from the A producer of the stage, one from the B producer
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads);
+      mbar_init(tempty_bar(a), kEpiWarps);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -88,106 +217,165 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0) {
-    // ======================= TMA producer =======================
-    if (lane == 0) {
+  if (warp == 0 || warp == 3) {
+    // ======================= A producers =======================
+    // elect.sync (not `lane == 0`): ptxas then knows a single thread is active and emits straight-line
+    // UTMALDG / UTCHMMA with uniform-register operands instead of a per-instruction divergence ("waterfall") loop
+    if (elect_one()) {
+      const uint32_t who = (warp == 0) ? 0u : 1u;
       tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_blocks;
-        const int n_blk = tile - m_blk * n_blocks;
-        const int m0 = m_blk * kBlockM;
+      uint32_t stage = 0, phase = 0, g = 0;
+      long long waited = 0;
+      for (int m_blk = m_first; m_blk < num_m_blocks; m_blk += m_step) {
+        const int m0 = m_blk * p.block_m;
         const int q0 = m0 % p.Wq;
         const int t = m0 / p.Wq;
         const int p0 = t % p.Hp;
         const int img = t / p.Hp;
         const int bw = p.lower_w + q0 * p.stride;
         const int bh = p.lower_h + p0 * p.stride;
+        for (int ks = 0; ks < num_k_stages; ++ks, ++g) {
+          if ((g & 1u) == who) {
+            mbar_wait_t(empty_bar(stage), phase ^ 1u, timed, waited);
+            const int j0 = ks * subs_per_stage;
+            const int nsub = min(subs_per_stage, total_chunks - j0);
+            mbar_expect_tx(full_bar(stage), nsub * a_sub_bytes);
+            const uint32_t a_st = a_base + stage * p.a_stage;
+            for (int sub = 0; sub < nsub; ++sub) {
+              const int j = j0 + sub;
+              const int tap = j / chunks_per_tap;
+              const int c0 = (j - tap * chunks_per_tap) * kc;
+              if (p.a_tiled)
+                tma_load_2d(a_st + sub * a_sub_bytes, &tmA, full_bar(stage), c0, m0);
+              else
+                tma_load_im2col_4d(a_st + sub * a_sub_bytes, &tmA, full_bar(stage), c0, bw, bh, img, p.tap_ow[tap],
+                                   p.tap_oh[tap]);
+            }
+          }
+          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (timed) p.dbg[blockIdx.x * 16 + who] = waited;
+    }
+  } else if (warp == 2) {
+    // ======================= B producer =======================
+    if (elect_one()) {
+      tma_prefetch_desc(&tmB);
+      uint32_t stage = 0, phase = 0;
+      long long waited = 0;
+      for (int m_blk = m_first; m_blk < num_m_blocks; m_blk += m_step) {
         for (int ks = 0; ks < num_k_stages; ++ks) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_wait_t(empty_bar(stage), phase ^ 1u, timed, waited);
           const int j0 = ks * subs_per_stage;
           const int nsub = min(subs_per_stage, total_chunks - j0);
-          mbar_expect_tx(full_bar(stage), nsub * (a_sub_bytes + b_sub_bytes));
-          const uint32_t a_st = a_base + stage * (kBlockM * kStageK * 2);
-          const uint32_t b_st = b_base + stage * L.b_stage;
+          mbar_expect_tx(full_bar(stage), nsub * b_sub_bytes);
+          const uint32_t b_st = b_base + stage * p.b_stage;
           for (int sub = 0; sub < nsub; ++sub) {
             const int j = j0 + sub;
             const int tap = j / chunks_per_tap;
             const int c0 = (j - tap * chunks_per_tap) * kc;
-            tma_load_im2col_4d(a_st + sub * a_sub_bytes, &tmA, full_bar(stage), c0, bw, bh, img, p.tap_ow[tap],
-                               p.tap_oh[tap]);
             tma_load_2d(b_st + sub * b_sub_bytes, &tmB, full_bar(stage), p.tap_kofs[tap] + c0, n_blk * p.block_n);
           }
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
         }
       }
+      if (timed) p.dbg[blockIdx.x * 16 + 2] = waited;
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
+    if (elect_one()) {
+      // The issuing thread is on the critical path (one tcgen05.mma every ~64-150 cycles): keep the per-MMA
+      // instruction count minimal - descriptors are a constant high word OR-ed with (smem address >> 4).
       const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
       const uint32_t ltype = (kc == 64) ? 2u : (kc == 32 ? 4u : 6u);
-      const uint32_t sbo = 8u * kc * 2u;
+      const uint64_t desc_hi = make_smem_desc(0, 16, 8u * kc * 2u, ltype);
+      const uint32_t ks_mask = (uint32_t)ksplit - 1u;          // ksplit is a power of two
+      const uint32_t half_cols = (uint32_t)ksplit * acc_stride;  // TMEM column distance between the two halves
+      const uint32_t a_sub16 = a_sub_bytes >> 4, b_sub16 = b_sub_bytes >> 4, a_half16 = a_half_bytes >> 4;
+      const int k16_per_sub = kc / 16;
       uint32_t stage = 0, phase = 0;
-      int lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const int acc = lt & 1;
-        const uint32_t use = (uint32_t)(lt >> 1);
-        mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);
+      uint32_t lt = 0;  // local tile counter
+      long long w_full = 0, w_tempty = 0;
+      for (int m_blk = m_first; m_blk < num_m_blocks; m_blk += m_step, ++lt) {
+        const uint32_t set = (nsets == 2u) ? (lt & 1u) : 0u;
+        const uint32_t use = (nsets == 2u) ? (lt >> 1) : lt;
+        mbar_wait_t(tempty_bar(set), (use & 1u) ^ 1u, timed, w_tempty);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        uint32_t accumulate = 0;
+        const uint32_t d_set = tmem_base + set * set_cols;
+        uint32_t kk = 0;  // running K-slice (16 elements) counter of this tile
         for (int ks = 0; ks < num_k_stages; ++ks) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait_t(full_bar(stage), phase, timed, w_full);
           tc_fence_after();
-          const int j0 = ks * subs_per_stage;
-          const int nsub = min(subs_per_stage, total_chunks - j0);
-          const uint32_t a_st = a_base + stage * (kBlockM * kStageK * 2);
-          const uint32_t b_st = b_base + stage * L.b_stage;
-          for (int sub = 0; sub < nsub; ++sub) {
-            for (int k16 = 0; k16 < kc / 16; ++k16) {
-              const uint64_t adesc = make_smem_desc(a_st + sub * a_sub_bytes + k16 * 32, 16, sbo, ltype);
-              const uint64_t bdesc = make_smem_desc(b_st + sub * b_sub_bytes + k16 * 32, 16, sbo, ltype);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-              accumulate = 1;
+          const int nsub = min(subs_per_stage, total_chunks - ks * subs_per_stage);
+          uint32_t a16 = (a_base + stage * p.a_stage) >> 4;
+          uint32_t b16 = (b_base + stage * p.b_stage) >> 4;
+          for (int sub = 0; sub < nsub; ++sub, a16 += a_sub16, b16 += b_sub16) {
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+              if (k16 < k16_per_sub) {
+                const uint64_t bdesc = desc_hi | (uint64_t)(b16 + 2u * k16);
+                const uint32_t d0 = d_set + (kk & ks_mask) * acc_stride;
+                const uint32_t accumulate = (kk > ks_mask) ? 1u : 0u;
+                umma_bf16(d0, desc_hi | (uint64_t)(a16 + 2u * k16), bdesc, idesc, accumulate);
+                if (halves == 2)
+                  umma_bf16(d0 + half_cols, desc_hi | (uint64_t)(a16 + a_half16 + 2u * k16), bdesc, idesc, accumulate);
+                ++kk;
+              }
             }
           }
           umma_commit(empty_bar(stage));
           if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        umma_commit(tfull_bar(set));
+      }
+      if (timed) {
+        p.dbg[blockIdx.x * 16 + 3] = w_full;
+        p.dbg[blockIdx.x * 16 + 4] = w_tempty;
       }
     }
   } else {
-    // ======================= epilogue (4 warps) =======================
-    const int et = threadIdx.x - 64;            // 0..127
+    // ======================= epilogue (4 groups x 4 warps, every warp independent) =======================
+    // The drain is latency-bound per warp (dependent TMEM -> cvt -> smem -> global chains), so it is spread over 16
+    // warps: group g owns (half g>>1, panels g&1, g&1 + 2, ...) of a 256-row tile or panels g, g+4, .. of a 128-row one.
+    // A warp owns 32 accumulator rows (its TMEM lane quarter): TMEM -> registers -> its own swizzled 32-row smem
+    // panel -> its own TMA store.  No block-level barriers: only __syncwarp and per-thread bulk-group waits.
+    const int grp = (warp - 4) >> 2;            // epilogue group 0..3
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;        // tile row == TMEM lane
+    const int row = quarter * 32 + lane;        // row inside the 128-row half == TMEM lane
     const int pw = p.panel_w;
-    const int nchunk = pw / 16;
     const uint32_t pitch = pw * 2;
     const uint32_t smask = (pw == 64) ? 7u : (pw == 32 ? 3u : 1u);
-    const bool tma_mode = (p.store_mode == kStoreTma || p.store_mode == kStoreTmaAdd);
-    const bool do_stats = (p.stats_partial != nullptr) && tma_mode;
-    const int pairs = pw / 2;
-    const int groups = kEpiThreads / pairs;
-    const int rows_per_group = kBlockM / groups;
-    const int my_pair = et % pairs;
-    const int my_grp = et / pairs;
-    uint32_t pcount = 0;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int acc = lt & 1;
-      const uint32_t use = (uint32_t)(lt >> 1);
-      const int m_blk = tile / n_blocks;
-      const int n_blk = tile - m_blk * n_blocks;
-      const int m0 = m_blk * kBlockM;
-      const int n0 = n_blk * p.block_n;
-      mbar_wait(tfull_bar(acc), use & 1u);
+    constexpr bool tma_mode = (EPI != kEpiScatter);   // dense (staged, coalesced) store
+    constexpr bool do_stats = (EPI == kEpiStats);
+    const int npanels = p.block_n / pw;         // host guarantees npanels <= kMaxPanels
+    const int n0 = n_blk * p.block_n;
+    // this warp's staging buffer: 32 rows x 64 B (panels are at most 32 columns wide)
+    const uint32_t my_panels = panel_base + (uint32_t)(warp - 4) * 2048u;
+    // running (sum, sumsq) totals of this lane's column(s) for the whole CTA lifetime, 16 registers:
+    // pw == 64: up to 4 panels x 4 values (two columns); pw < 64: up to 8 panels x 2 values (one column)
+    // (scalars, not an array: a runtime-indexed array would be demoted to local memory = L2 round trips here)
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;   // <= 4 local panels x (sum, sumsq) of one column
+    uint32_t lt = 0;
+    long long w_tfull = 0, t_ld = 0, t_cvt = 0, t_drain = 0;
+    // work split: with two halves each group drains its own half; with one half the groups take alternate panels
+    const int my_half = (halves == 2) ? (grp >> 1) : 0;
+    const int pi_first = (halves == 2) ? (grp & 1) : grp;
+    const int pi_step = (halves == 2) ? 2 : 4;
+    for (int m_blk = m_first; m_blk < num_m_blocks; m_blk += m_step, ++lt) {
+      const int h = my_half;
+      const uint32_t set = (nsets == 2u) ? (lt & 1u) : 0u;
+      const uint32_t use = (nsets == 2u) ? (lt >> 1) : lt;
+      const int m0 = m_blk * p.block_m + h * kBlockM;
+      mbar_wait_t(tfull_bar(set), use & 1u, timed, w_tfull);
       tc_fence_after();
+      if (pi_first >= npanels) {  // nothing to drain for this group: release the set straight away
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(tempty_bar(set));
+      }
+      const uint32_t acc0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * set_cols + (h * ksplit) * acc_stride;
 
       // scatter-mode addressing for this thread's pixel
       __nv_bfloat16* out_row = nullptr;
@@ -200,127 +388,158 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         out_row = p.out + ((size_t)((size_t)img * p.OH + (size_t)pp * p.os + p.oph) * p.OW + (size_t)q * p.os + p.opw) *
                               (size_t)p.ldo;
       }
-      const int npanels = p.block_n / pw;
-      for (int pi = 0; pi < npanels; ++pi) {
-        const uint32_t buf = pcount & 1u;
-        ++pcount;
-        const uint32_t panel = panel_base + buf * (kBlockM * 128);
-        if (tma_mode) {
-          if (et == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, kEpiThreads);
-        }
-        uint32_t v[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + pi * pw;
+      for (int pi = pi_first; pi < npanels; pi += pi_step) {
+        const uint32_t panel = my_panels;
+        const uint32_t taddr = acc0 + pi * pw;
+        long long tp_ld = 0, tp_cvt = 0;
+        // the panel is drained in pieces of 16 columns to keep the register footprint small: this kernel runs with
+        // ~no L1 (all of it is shared memory), so a spilled register costs an L2 round trip
+        const int npieces = pw / 16;
+        for (int pc = 0; pc < npieces; ++pc) {
+          const long long tq0 = timed ? clock64() : 0;
+          uint32_t v[16];
+          const uint32_t ta = taddr + pc * 16;
+          tmem_ld16(ta, v);
+          tmem_ld_wait();
+          for (int ksel = 1; ksel < ksplit; ++ksel) {  // sum the K-interleaved partial accumulators
+            uint32_t v2[16];
+            tmem_ld16(ta + ksel * acc_stride, v2);
+            tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-          if (ch < nchunk) tmem_ld16(taddr + ch * 16, v + ch * 16);
-        tmem_ld_wait();
-        if (pi == npanels - 1) {
-          tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
-        }
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+          }
+          if (pi + pi_step >= npanels && pc == npieces - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(set));
+          }
+          const long long tq1 = timed ? clock64() : 0;
+          {
+            {
+              const int ch = pc;   // 16-column chunk inside the panel
+              float f[16];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch < nchunk) {
-            float f[16];
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+              const int col0 = n0 + pi * pw + ch * 16;
+              if (EPI == kEpiAffine && p.scale != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[ch * 16 + i]);
-            const int col0 = n0 + pi * pw + ch * 16;
-            if (p.scale != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], __ldg(p.scale + col0 + i), __ldg(p.shift + col0 + i));
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-            if (p.residual != nullptr && m < p.M) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.ldr + col0);
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint4 rv = __ldg(r4 + h);
-                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  // the reference adds two bf16 tensors: round first, then add
-                  f[h * 8 + 2 * i] = __bfloat162float(__float2bfloat16_rn(f[h * 8 + 2 * i])) + bf16lo(rr[i]);
-                  f[h * 8 + 2 * i + 1] = __bfloat162float(__float2bfloat16_rn(f[h * 8 + 2 * i + 1])) + bf16hi(rr[i]);
-                }
+                for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], __ldg(p.scale + col0 + i), __ldg(p.shift + col0 + i));
               }
-            }
-            if (tma_mode) {
-              uint32_t pk[8];
+              if (EPI == kEpiAffine && p.relu) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint32_t off = swz(row * pitch + (ch * 2 + h) * 16, smask);
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(panel + off), "r"(pk[4 * h]),
-                             "r"(pk[4 * h + 1]), "r"(pk[4 * h + 2]), "r"(pk[4 * h + 3])
-                             : "memory");
+                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
               }
-            } else if (out_row != nullptr) {
-              uint4* o4 = reinterpret_cast<uint4*>(out_row + col0);
+              if (EPI == kEpiAffine && p.residual != nullptr && m < p.M) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.ldr + col0);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (p.store_mode == kStoreScatterAdd) {
-                  const uint4 ov = o4[h];
-                  const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w};
+                for (int hh = 0; hh < 2; ++hh) {
+                  const uint4 rv = __ldg(r4 + hh);
+                  const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
-                    f[h * 8 + 2 * i] = __bfloat162float(__float2bfloat16_rn(f[h * 8 + 2 * i])) + bf16lo(oo[i]);
-                    f[h * 8 + 2 * i + 1] = __bfloat162float(__float2bfloat16_rn(f[h * 8 + 2 * i + 1])) + bf16hi(oo[i]);
+                    // the reference adds two bf16 tensors: round first, then add
+                    f[hh * 8 + 2 * i] = __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i])) + bf16lo(rr[i]);
+                    f[hh * 8 + 2 * i + 1] =
+                        __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i + 1])) + bf16hi(rr[i]);
                   }
                 }
-                uint4 sv;
-                sv.x = pack_bf16x2(f[h * 8 + 0], f[h * 8 + 1]);
-                sv.y = pack_bf16x2(f[h * 8 + 2], f[h * 8 + 3]);
-                sv.z = pack_bf16x2(f[h * 8 + 4], f[h * 8 + 5]);
-                sv.w = pack_bf16x2(f[h * 8 + 6], f[h * 8 + 7]);
-                o4[h] = sv;
+              }
+              if (tma_mode) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const uint32_t off = swz(lane * pitch + (ch * 2 + hh) * 16, smask);
+                  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(panel + off), "r"(pk[4 * hh]),
+                               "r"(pk[4 * hh + 1]), "r"(pk[4 * hh + 2]), "r"(pk[4 * hh + 3])
+                               : "memory");
+                }
+              } else if (out_row != nullptr) {
+                uint4* o4 = reinterpret_cast<uint4*>(out_row + col0);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  if (p.store_mode == kStoreScatterAdd) {
+                    const uint4 ov = o4[hh];
+                    const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      f[hh * 8 + 2 * i] = __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i])) + bf16lo(oo[i]);
+                      f[hh * 8 + 2 * i + 1] =
+                          __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i + 1])) + bf16hi(oo[i]);
+                    }
+                  }
+                  uint4 sv;
+                  sv.x = pack_bf16x2(f[hh * 8 + 0], f[hh * 8 + 1]);
+                  sv.y = pack_bf16x2(f[hh * 8 + 2], f[hh * 8 + 3]);
+                  sv.z = pack_bf16x2(f[hh * 8 + 4], f[hh * 8 + 5]);
+                  sv.w = pack_bf16x2(f[hh * 8 + 6], f[hh * 8 + 7]);
+                  o4[hh] = sv;
+                }
               }
             }
           }
+          if (timed) {
+            tp_ld += tq1 - tq0;
+            tp_cvt += clock64() - tq1;
+          }
         }
+        const long long tp2 = timed ? clock64() : 0;
         if (tma_mode) {
-          fence_proxy_async_smem();
-          named_bar_sync(2, kEpiThreads);
-          if (et == 0) {
-            if (p.store_mode == kStoreTma)
-              tma_store_2d(&tmD, panel, n0 + pi * pw, m0);
-            else
-              tma_reduce_add_2d(&tmD, panel, n0 + pi * pw, m0);
-            tma_store_commit();
-          }
+          __syncwarp();
+          float o0, o1, o2, o3;
+          const int rows_valid = p.M - (m0 + quarter * 32);   // rows of this warp inside the tensor (may be <= 0)
+          __nv_bfloat16* gdst = p.out + (size_t)(m0 + quarter * 32) * p.ldo + n0 + pi * pw;
+          if (do_stats) panel_drain_pw<false, true>(pw, panel, lane, gdst, p.ldo, rows_valid, o0, o1, o2, o3);
+          else if (EPI == kEpiPlain && p.store_mode == kStoreTmaAdd)
+            panel_drain_pw<true, false>(pw, panel, lane, gdst, p.ldo, rows_valid, o0, o1, o2, o3);
+          else panel_drain_pw<false, false>(pw, panel, lane, gdst, p.ldo, rows_valid, o0, o1, o2, o3);
           if (do_stats) {
-            // column sums over this thread's row group, read back from the staged bf16 panel
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-            const int r0 = my_grp * rows_per_group;
-            const uint32_t cofs = (my_pair >> 2) * 16 + (my_pair & 3) * 4;
-#pragma unroll 8
-            for (int r = 0; r < rows_per_group; ++r) {
-              uint32_t w;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(panel + swz((r0 + r) * pitch + cofs, smask)));
-              const float a = bf16lo(w), b = bf16hi(w);
-              s0 += a;
-              q0 = fmaf(a, a, q0);
-              s1 += b;
-              q1 = fmaf(b, b, q1);
-            }
-            float4* dst = reinterpret_cast<float4*>(
-                p.stats_partial + (((size_t)blockIdx.x * groups + my_grp) * p.cout + n0 + pi * pw + 2 * my_pair) * 2);
-            float4 cur = *dst;
-            cur.x += s0;
-            cur.y += q0;
-            cur.z += s1;
-            cur.w += q1;
-            *dst = cur;
+            const int lpi = (pi - pi_first) / pi_step;   // local panel index of this group, < 4
+            if (lpi == 0) { a0.x += o0; a0.y += o1; }
+            else if (lpi == 1) { a0.z += o0; a0.w += o1; }
+            else if (lpi == 2) { a1.x += o0; a1.y += o1; }
+            else { a1.z += o0; a1.w += o1; }
           }
+          __syncwarp();   // the staging buffer is rewritten by the next panel
+        }
+        if (timed) {
+          t_ld += tp_ld; t_cvt += tp_cvt; t_drain += clock64() - tp2;
         }
       }
     }
-    if (tma_mode && et == 0) tma_store_wait_all<0>();
+    if (do_stats) {
+      // one statistics row per 32-row slice of the tile; this warp fills the columns of the panels it drained
+      float* rowp = p.stats_partial + (size_t)((m_first * halves + my_half) * 4 + quarter) * p.cout * 2;
+      for (int pi = pi_first; pi < npanels; pi += pi_step) {
+        const int lpi = (pi - pi_first) / pi_step;
+        float4 o = (lpi < 2) ? a0 : a1;
+        if (lpi & 1) o = make_float4(o.z, o.w, 0.f, 0.f);
+        const int cbase = n0 + pi * pw;
+        // column owned by this lane after the butterfly (see panel_col_stats): row-group bit k selects half 4>>k
+        if (pw == 64) {
+          const int rg = lane >> 3;
+          const int col = (lane & 7) * 8 + (rg & 1) * 4 + (rg >> 1) * 2;
+          *reinterpret_cast<float4*>(rowp + (size_t)(cbase + col) * 2) = o;
+        } else if (pw == 32) {
+          const int rg = lane >> 2;
+          const int col = (lane & 3) * 8 + (rg & 1) * 4 + ((rg >> 1) & 1) * 2 + (rg >> 2);
+          *reinterpret_cast<float2*>(rowp + (size_t)(cbase + col) * 2) = make_float2(o.x, o.y);
+        } else if ((lane >> 4) == 0) {
+          const int rg = lane >> 1;
+          const int col = (lane & 1) * 8 + (rg & 1) * 4 + ((rg >> 1) & 1) * 2 + ((rg >> 2) & 1);
+          *reinterpret_cast<float2*>(rowp + (size_t)(cbase + col) * 2) = make_float2(o.x, o.y);
+        }
+      }
+    }
+    if (timed && quarter == 0 && lane == 0 && grp < 2) p.dbg[blockIdx.x * 16 + 5 + grp] = w_tfull;
+    if (timed && warp == 4 && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 8] = t_ld;
+      p.dbg[blockIdx.x * 16 + 9] = t_cvt;
+      p.dbg[blockIdx.x * 16 + 10] = t_drain;
+    }
   }
+  if (timed && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 7] = clock64() - t_start;
 
   tc_fence_before();
   __syncthreads();
@@ -328,6 +547,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+#undef halves
+#undef ksplit
+#undef acc_stride
+#undef set_cols
+#undef nsets
+#undef num_m_blocks
+#undef n_blocks
+#undef m_step
+#undef kc
+#undef chunks_per_tap
+#undef total_chunks
+#undef subs_per_stage
+#undef num_k_stages
+#undef a_sub_bytes
+#undef a_half_bytes
+#undef b_sub_bytes
+
+void fill_derived(ConvIgemmParams& p, int grid) {
+  const ConvSmem L = conv_smem_layout(p.block_m, p.block_n, p.num_stages, p.panel_bufs);
+  p.halves = p.block_m / kBlockM;
+  p.n_blocks = p.cout / p.block_n;
+  p.num_m_blocks = (p.M + p.block_m - 1) / p.block_m;
+  p.m_step = grid / p.n_blocks;
+  p.chunks_per_tap = p.cin / p.kc;
+  p.total_chunks = p.ntaps * p.chunks_per_tap;
+  p.subs_per_stage = kStageK / p.kc;
+  p.num_k_stages = (p.total_chunks + p.subs_per_stage - 1) / p.subs_per_stage;
+  p.acc_stride = (uint32_t)((p.block_n + 31) & ~31);
+  p.set_cols = (uint32_t)(p.halves * p.ksplit) * p.acc_stride;
+  p.nsets = (2u * p.set_cols <= 512u) ? 2u : 1u;
+  p.a_stage = L.a_stage;
+  p.b_stage = L.b_stage;
+  p.b_off = L.b_off;
+  p.panel_off = L.panel_off;
+  p.bar_off = L.bar_off;
+  p.a_sub_bytes = (uint32_t)p.block_m * p.kc * 2;
+  p.a_half_bytes = (uint32_t)kBlockM * p.kc * 2;
+  p.b_sub_bytes = (uint32_t)p.block_n * p.kc * 2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -406,7 +665,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tmDY);
       tma_prefetch_desc(&tmX);
       uint32_t stage = 0, phase = 0;
@@ -436,7 +695,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, p.sub_n, 1, 1);
       const uint32_t lta = (p.ca == 64) ? 2u : (p.ca == 32 ? 4u : 6u);
       const uint32_t ltb = (p.cc == 64) ? 2u : (p.cc == 32 ? 4u : 6u);
@@ -504,17 +763,43 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-int launch_conv_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-                      const ConvIgemmParams& p, int grid, cudaStream_t stream) {
+template <bool TIMED, int EPI>
+static int launch_conv_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                               const ConvIgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<TIMED, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBudget);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const size_t smem = conv_igemm_smem_bytes(p.block_n, p.num_stages);
-  conv_igemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, tmD, p);
+  conv_igemm_kernel<TIMED, EPI><<<grid, kConvThreads, smem, stream>>>(tmA, tmB, tmD, p);
   return (int)cudaGetLastError();
+}
+
+int launch_conv_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                      const ConvIgemmParams& p_in, int grid, cudaStream_t stream) {
+  ConvIgemmParams p = p_in;
+  fill_derived(p, grid);
+  const size_t smem = conv_igemm_smem_bytes(p.block_m, p.block_n, p.num_stages, p.panel_bufs);
+  const bool dense = (p.store_mode == kStoreTma || p.store_mode == kStoreTmaAdd);
+  const int epi = !dense ? kEpiScatter
+                         : (p.stats_partial != nullptr ? kEpiStats
+                                                       : ((p.scale != nullptr || p.relu || p.residual != nullptr) ? kEpiAffine : kEpiPlain));
+  if (p.dbg != nullptr) {
+    switch (epi) {
+      case kEpiStats: return launch_conv_variant<true, kEpiStats>(tmA, tmB, tmD, p, grid, smem, stream);
+      case kEpiAffine: return launch_conv_variant<true, kEpiAffine>(tmA, tmB, tmD, p, grid, smem, stream);
+      case kEpiPlain: return launch_conv_variant<true, kEpiPlain>(tmA, tmB, tmD, p, grid, smem, stream);
+      default: return launch_conv_variant<true, kEpiScatter>(tmA, tmB, tmD, p, grid, smem, stream);
+    }
+  }
+  switch (epi) {
+    case kEpiStats: return launch_conv_variant<false, kEpiStats>(tmA, tmB, tmD, p, grid, smem, stream);
+    case kEpiAffine: return launch_conv_variant<false, kEpiAffine>(tmA, tmB, tmD, p, grid, smem, stream);
+    case kEpiPlain: return launch_conv_variant<false, kEpiPlain>(tmA, tmB, tmD, p, grid, smem, stream);
+    default: return launch_conv_variant<false, kEpiScatter>(tmA, tmB, tmD, p, grid, smem, stream);
+  }
 }
 
 int launch_wgrad_igemm(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradIgemmParams& p, int grid_x,

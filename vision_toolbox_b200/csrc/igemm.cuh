@@ -13,12 +13,16 @@
 
 namespace vtb {
 
-constexpr int kBlockM = 128;       // output pixels per tile (UMMA M)
+constexpr int kBlockM = 128;       // rows per UMMA (M); a conv tile is 1 or 2 such halves (block_m 128 / 256)
 constexpr int kStageK = 64;        // K elements (bf16) per pipeline stage
 constexpr int kMaxTaps = 36;       // 6x6 filter
-constexpr int kNumThreads = 192;   // warp0 TMA, warp1 MMA, warps2-5 epilogue
-constexpr int kEpiThreads = 128;
+constexpr int kNumThreads = 192;   // wgrad kernel: warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kConvThreads = 640;  // conv kernel: warp0/3 A producers, warp1 MMA, warp2 B producer, warps 4-19 epilogue (4 groups)
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = 128;   // threads per epilogue group
 constexpr int kTmemCols = 512;
+constexpr int kSmemBudget = 232448;
+constexpr int kMaxPanels = 8;      // staged output panels per accumulator (block_n / panel_w)
 
 enum StoreMode : int {
   kStoreTma = 0,        // bf16 tile via TMA store
@@ -30,6 +34,15 @@ enum StoreMode : int {
 struct ConvIgemmParams {
   // GEMM / pixel space of the output of this launch
   int M;            // number of output pixels handled by this launch (Nimg*Hp*Wq)
+  int block_m;      // 128 or 256 output pixels per tile (256 = two UMMA halves sharing one B tile)
+  int a_tiled;      // 1: A operand is a plain [pixels][cin] matrix loaded in tiled mode (1x1 stride-1), 0: im2col
+  int panel_bufs;   // staged-output buffers per epilogue group (1 or 2)
+  int ksplit;       // accumulators per 128-row half, fed round-robin with successive K slices (1, 2 or 4)
+  // values derived on the host (fill_derived) so that no kernel role has to keep division results in registers
+  int halves, n_blocks, num_m_blocks, m_step, chunks_per_tap, total_chunks, subs_per_stage, num_k_stages;
+  uint32_t acc_stride, set_cols, nsets;                          // TMEM layout
+  uint32_t a_stage, b_stage, b_off, panel_off, bar_off;          // shared-memory layout (bytes from the aligned base)
+  uint32_t a_sub_bytes, a_half_bytes, b_sub_bytes;
   int Wq, Hp;       // output-pixel lattice (q fastest, then p, then image)
   int stride;       // traversal stride of the im2col walk
   int lower_w, lower_h;  // coordinate of the base pixel for q=0 / p=0 (== pixelBoxLowerCorner)
@@ -48,7 +61,9 @@ struct ConvIgemmParams {
   // scatter mode: pixel (img,p,q) -> out + ((img*OH + p*os + oph)*OW + q*os + opw)*ldo
   __nv_bfloat16* out;
   int OH, OW, os, oph, opw, ldo;
-  // per-channel batch statistics of the bf16-rounded result: [gridDim.x][groups][cout][2] (sum, sumsq)
+  // per-channel batch statistics of the bf16-rounded result: [rows][cout][2] (sum, sumsq),
+  // rows = (gridDim.x / n_blocks) * 4 * (block_m / 128): one per 32-row slice of the tile; every (row, channel) is
+  // written exactly once
   float* stats_partial;
   // optional fused per-channel affine + ReLU (+ residual) epilogue (eval-mode folded BN)
   const float* scale;
@@ -56,6 +71,8 @@ struct ConvIgemmParams {
   int relu;
   const __nv_bfloat16* residual;
   int ldr;
+  // development aid (tools/bench_conv): per-CTA [8] cycle counters of the time each role spent waiting; usually null
+  unsigned long long* dbg;
 };
 
 struct WgradIgemmParams {
@@ -78,8 +95,11 @@ struct WgradIgemmParams {
   float* ws;         // [splits][cout][ntaps*cin] fp32 partials
 };
 
-size_t conv_igemm_smem_bytes(int block_n, int num_stages);
+size_t conv_igemm_smem_bytes(int block_m, int block_n, int num_stages, int panel_bufs);
 size_t wgrad_igemm_smem_bytes(int subs_per_tile, int sub_n, int num_stages);
+
+// completes the derived fields of ConvIgemmParams from block_m/block_n/num_stages/ksplit/kc/cin/ntaps/M/cout and grid
+void fill_derived(ConvIgemmParams& p, int grid);
 
 // host launchers (igemm.cu); return cudaError_t as int
 int launch_conv_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
