@@ -119,7 +119,7 @@ class ProfilingLib:
             e0.record()
             rc = fn(*args)
             e1.record()
-            self.records.append((name, args[0] if name.startswith("vtb_conv_") else None, e0, e1))
+            self.records.append((name, args[0] if name.startswith("vtb_conv_") else None, e0, e1, args))
             return rc
 
         return wrapped
@@ -348,15 +348,16 @@ def main() -> None:
         for r in runners:
             r.L = _lib.lib()
         agg = {}
-        for name, geom, a, b in prof.records:
+        for name, geom, a, b, _ in prof.records:
             t = a.elapsed_time(b)
-            fl = conv_flops(geom) if geom is not None and name in ("vtb_conv_fprop", "vtb_conv_dgrad", "vtb_conv_wgrad") else 0.0
+            fl = conv_flops(geom) if geom is not None and name in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_wgrad") else 0.0
             d = agg.setdefault(name, [0.0, 0.0, 0])
             d[0] += t; d[1] += fl; d[2] += 1
         pk = peaks()
-        igemm_ms = agg.get("vtb_conv_fprop", [0, 0, 0])[0] + agg.get("vtb_conv_dgrad", [0, 0, 0])[0]
-        igemm_fl = agg.get("vtb_conv_fprop", [0, 0, 0])[1] + agg.get("vtb_conv_dgrad", [0, 0, 0])[1]
-        igemm_n = agg.get("vtb_conv_fprop", [0, 0, 0])[2] + agg.get("vtb_conv_dgrad", [0, 0, 0])[2]
+        conv_calls = [agg.get(k, [0, 0, 0]) for k in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad")]
+        igemm_ms = sum(v[0] for v in conv_calls)
+        igemm_fl = sum(v[1] for v in conv_calls)
+        igemm_n = sum(v[2] for v in conv_calls)
         achieved = igemm_fl / (igemm_ms / 1e3) / 1e12 if igemm_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (fprop + dgrad launches)", "achieved": achieved,
                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,

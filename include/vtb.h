@@ -49,7 +49,7 @@ long long vtb_launch_count(void);
 
 /* ---- shape / workspace queries (host only, no GPU needed) ---- */
 int vtb_conv_out_hw(const VtbConv* c, int* ho, int* wo);
-/* rows of the per-CTA statistics scratch written by vtb_conv_fprop: floats = rows * cout * 2 */
+/* rows of the per-CTA statistics scratch written by vtb_conv_fprop (one per thread block): floats = rows * cout * 2 */
 int vtb_conv_stats_rows(const VtbConv* c);
 size_t vtb_conv_wgrad_workspace_bytes(const VtbConv* c);
 
@@ -68,6 +68,28 @@ int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* w
  *   then + residual (bf16 NHWC, pitch ldr) if residual != NULL (darknet.py:28, vovnet.py:60-61). */
 int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
                    const float* scale, const float* shift, int relu, const void* residual, int ldr, void* stream);
+
+/* Training-mode fusion of the two library calls at components.py:26-36: the convolution above (with statistics)
+ * PLUS vtb_bn_finalize below, executed by the last thread block of the convolution kernel to finish - BatchNorm2d's
+ * statistics finalisation then costs no kernel launch.  `tickets`: >= 64 zero-initialised uint32 owned by the caller
+ * (the kernel leaves them zero; one array can serve every layer launched on the same stream).  Single-GPU statistics
+ * only: under SyncBN use vtb_conv_fprop + vtb_bn_stats_reduce + (exchange) + vtb_bn_finalize. */
+typedef struct VtbBnTrain {
+  double count;                    /* elements per channel: N*Ho*Wo */
+  const float* gamma;              /* norm.weight */
+  const float* beta;               /* norm.bias */
+  float eps, momentum;
+  float* running_mean;             /* may be NULL (track_running_stats=False) */
+  float* running_var;
+  long long* num_batches_tracked;  /* may be NULL */
+  float* mean;                     /* out [cout] */
+  float* invstd;                   /* out [cout] */
+  float* scale;                    /* out [cout]: gamma*invstd */
+  float* shift;                    /* out [cout]: beta - mean*scale */
+  unsigned int* tickets;
+} VtbBnTrain;
+int vtb_conv_fprop_bn(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
+                      const VtbBnTrain* bn, void* stream);
 
 /* ---- convolution backward: replaces aten::convolution_backward (autograd of components.py:26-35) ----
  * dgrad: dx = conv_transpose(dy, w); accumulate != 0 adds into dx (gradient fan-in of residual / CSP /

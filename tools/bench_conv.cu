@@ -87,6 +87,19 @@ int main(int argc, char** argv) {
     const double avg = total / iters;
     printf("%-6s %4d->%4d k%ds%d %3dx%-3d n%-3d | avg %8.1f us  best %8.1f us | %7.1f TF/s %7.1f GB/s\n", names[which], c.cin, c.cout,
            c.k, c.stride, c.h, c.w, c.n, avg * 1e3, best * 1e3, flops / (avg * 1e-3) / 1e12, bytes / (avg * 1e-3) / 1e9);
+    if (which == 2) {
+      CK(cudaMemset(dbg, 0, 1024 * 128));
+      vtb_debug_counters(dbg);
+      run();
+      CK(cudaDeviceSynchronize());
+      vtb_debug_counters(nullptr);
+      std::vector<unsigned long long> h(1024 * 16);
+      CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+      double s[16] = {0}; int n = 0;
+      for (int b = 0; b < 1024; ++b) if (h[b * 16 + 2]) { ++n; for (int j = 0; j < 16; ++j) s[j] += (double)h[b * 16 + j]; }
+      if (n) printf("       ctas %d | cycles/CTA %.0f | setup %.0f | first-full %.0f | producer0 on empty %.0f | MMA on full %.0f | epi on tmem-full %.0f, drain %.0f\n",
+                    n, s[2] / n, s[6] / n, s[5] / n, s[0] / n, s[1] / n, s[3] / n, s[4] / n);
+    }
     if (which < 2 && !(which == 1 && c.stride == 2)) {
       CK(cudaMemset(dbg, 0, 1024 * 128));
       vtb_debug_counters(dbg);

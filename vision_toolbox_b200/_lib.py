@@ -21,6 +21,15 @@ class VtbConv(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("n", "h", "w", "cin", "cout", "k", "stride", "pad")]
 
 
+class VtbBnTrain(C.Structure):
+    """struct VtbBnTrain of include/vtb.h (BatchNorm2d training tensors for the fused conv + finalize call)."""
+
+    _fields_ = [("count", C.c_double), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+                ("momentum", C.c_float), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("num_batches_tracked", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("tickets", C.c_void_p)]
+
+
 _p = C.c_void_p
 _i = C.c_int
 _ll = C.c_longlong
@@ -39,6 +48,7 @@ SIGNATURES = {
     "vtb_conv_wgrad_workspace_bytes": (C.c_size_t, [_cp]),
     "vtb_pack_weight": (_i, [_cp, _p, _i, _p, _p, _p]),
     "vtb_conv_fprop": (_i, [_cp, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _p]),
+    "vtb_conv_fprop_bn": (_i, [_cp, _p, _i, _p, _p, _i, _p, C.POINTER(VtbBnTrain), _p]),
     "vtb_conv_dgrad": (_i, [_cp, _p, _i, _p, _p, _i, _i, _p]),
     "vtb_conv_wgrad": (_i, [_cp, _p, _i, _p, _i, _p, _p, _i, _i, _p]),
     "vtb_bn_stats_reduce": (_i, [_p, _i, _i, _p, _p]),

@@ -112,7 +112,7 @@ static ConvTiling plan_conv_tiling(long long M, int ncols, int total_k16) {
   }
   static const int o_stages = env_int("VTB_STAGES");
   if (o_stages > 0) t.stages = std::min(t.stages, o_stages);
-  t.stat_rows = (t.grid / t.n_blocks) * 4 * (t.block_m / kBlockM);  // one row per 32-row slice of a tile
+  t.stat_rows = t.grid / t.n_blocks;  // one row per CTA
   return t;
 }
 static void apply_tiling(ConvIgemmParams& p, const ConvTiling& t) {
@@ -142,49 +142,102 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
-// dw[co][ci][t] (+)= sum_split ws[split][co][t*cin + ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, int cin_real, int kk,
-                                    float* __restrict__ dw, int accumulate) {
-  const long long total = (long long)cout * cin_real * kk;
-  const long long split_stride = (long long)cout * kk * cin;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i % kk);
-    const int ci = (int)((i / kk) % cin_real);
-    const int co = (int)(i / ((long long)kk * cin_real));
-    const float* src = ws + ((long long)co * kk + t) * cin + ci;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += src[s * split_stride];
-    dw[i] = accumulate ? dw[i] + acc : acc;
+// dw[co][ci][t] (+)= sum_split ws[split][co][t*cin + ci].  One block per (output channel, slice of EW <= 64 input
+// channels).  The 256 threads are EW channel lanes x SG split groups: every group sums its share of the splits with
+// coalesced reads (many independent loads in flight: the split count, not the tile, carries the parallelism for small
+// layers), the groups are combined through shared memory in a fixed order (deterministic), and the slice is written out
+// in OIHW order, which is contiguous for the block ((ci, t) fastest).
+template <int EW>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, int cin_real, int kk,
+                    float* __restrict__ dw, int accumulate) {
+  constexpr int SG = 256 / EW;
+  extern __shared__ float red_sm[];   // [SG][kk][EW + 1]
+  const int co = blockIdx.x;
+  const int c0 = blockIdx.y * EW;
+  const int cw = min(EW, cin - c0);              // channels of the (padded) workspace row handled here
+  const int cr = min(cw, cin_real - c0);         // of which real (the image stem pads 3 -> 16)
+  if (cr <= 0) return;
+  const int e = threadIdx.x % EW, sg = threadIdx.x / EW;
+  constexpr int pitch = EW + 1;
+  const size_t split_stride = (size_t)cout * kk * cin;
+  if (e < cw) {
+    const float* src = ws + (size_t)co * kk * cin + c0 + e;
+    for (int t = 0; t < kk; ++t) {
+      float acc = 0.f;
+#pragma unroll 4
+      for (int s = sg; s < splits; s += SG) acc += __ldg(src + (size_t)s * split_stride + (size_t)t * cin);
+      red_sm[(sg * kk + t) * pitch + e] = acc;
+    }
+  }
+  __syncthreads();
+  float* dst = dw + ((size_t)co * cin_real + c0) * kk;
+  const int ngroups = min(SG, splits);
+  for (int j = threadIdx.x; j < cr * kk; j += 256) {
+    const int c = j / kk, t = j - c * kk;
+    float v = 0.f;
+    for (int g = 0; g < ngroups; ++g) v += red_sm[(g * kk + t) * pitch + c];
+    dst[j] = accumulate ? dst[j] + v : v;
   }
 }
 
 struct WgradPlan {
-  int ca, cc, sub_n, subs_per_tile, total_subs, n_tiles, m_tiles, splits, kblocks, stages;
+  int ca, cc, ma, kpix, boxes_per_tap, total_boxes, boxes_per_tile, n_cols, n_tiles, m_tiles, ksplit, acc_stride, splits,
+      kblocks, stages;
   long long mpix;
 };
 static WgradPlan plan_wgrad(const VtbConv* c) {
   WgradPlan w;
   int ho, wo;
   out_hw(c, &ho, &wo);
+  const int sms = std::max(1, num_sms() > 0 ? num_sms() : 148);
   w.mpix = (long long)c->n * ho * wo;
   w.ca = chunk_of(c->cout);
-  w.sub_n = block_of(c->cin);
-  w.cc = chunk_of(w.sub_n);
+  w.cc = chunk_of(c->cin);
+  w.ma = std::min(128, c->cout);
   const int taps = c->k * c->k;
-  w.total_subs = taps * (c->cin / w.sub_n);
-  w.subs_per_tile = std::max(1, 256 / w.sub_n);
-  w.subs_per_tile = std::min(w.subs_per_tile, w.total_subs);
-  w.n_tiles = (w.total_subs + w.subs_per_tile - 1) / w.subs_per_tile;
+  w.boxes_per_tap = c->cin / w.cc;
+  w.total_boxes = taps * w.boxes_per_tap;
+  // column tiling of the flattened tap*cin axis: tiles of <= 256 columns, as even as the box width allows
+  const int max_boxes = 256 / w.cc;
+  int best_tiles = (w.total_boxes + max_boxes - 1) / max_boxes, best_bpt = 0, best_waste = 1 << 30;
+  for (int nt = best_tiles; nt <= best_tiles + 2; ++nt) {
+    const int bpt = (w.total_boxes + nt - 1) / nt;
+    const int tiles = (w.total_boxes + bpt - 1) / bpt;
+    const int waste = tiles * bpt - w.total_boxes;
+    if (waste < best_waste) { best_waste = waste; best_bpt = bpt; best_tiles = tiles; }
+  }
+  static const int o_bpt = env_int("VTB_WG_BOXES");
+  if (o_bpt > 0 && o_bpt <= max_boxes) { best_bpt = std::min(o_bpt, w.total_boxes); best_tiles = (w.total_boxes + best_bpt - 1) / best_bpt; }
+  w.boxes_per_tile = best_bpt;
+  w.n_tiles = best_tiles;
+  w.n_cols = best_bpt * w.cc;
   w.m_tiles = (c->cout + 127) / 128;
-  w.kblocks = (int)((w.mpix + kStageK - 1) / kStageK);
+  // independent accumulation chains: as many as TMEM holds (an MMA chain into one accumulator has ~170 cycles latency)
+  w.acc_stride = (w.n_cols + 31) & ~31;
+  int ks = 8;
+  while (ks > 1 && ks * w.acc_stride > 512) ks >>= 1;
+  static const int o_ks = env_int("VTB_WG_KSPLIT");
+  if (o_ks > 0 && o_ks * w.acc_stride <= 512) ks = o_ks;
+  w.ksplit = ks;
+  // pixels per stage: the largest box that still leaves >= 2 stages (fewer, larger TMA requests: the per-SM TMA
+  // ingest rate grows with the box height, profiles/r01_tma_bw.txt)
+  const int budget = kSmemBudget - 256 - 1024;
+  auto stage_bytes = [&](int kp) { return ((kp * w.ma * 2 + 1023) / 1024 + (kp * w.n_cols * 2 + 1023) / 1024) * 1024; };
+  int kpix = 256;
+  while (kpix > 64 && budget / stage_bytes(kpix) < 2) kpix >>= 1;
+  static const int o_kp = env_int("VTB_WG_KPIX");
+  if ((o_kp == 64 || o_kp == 128 || o_kp == 256) && budget / stage_bytes(o_kp) >= 1) kpix = o_kp;
+  while (kpix > 64 && w.mpix < (long long)kpix * 2) kpix >>= 1;
+  w.kpix = kpix;
+  w.stages = std::max(1, std::min(8, budget / stage_bytes(kpix)));
+  static const int o_st = env_int("VTB_WG_STAGES");
+  if (o_st > 0) w.stages = std::min(w.stages, o_st);
+  w.kblocks = (int)((w.mpix + kpix - 1) / kpix);
   const int ctas = w.n_tiles * w.m_tiles;
-  const int sms = std::max(1, num_sms() > 0 ? num_sms() : 148);
   int splits = std::max(1, sms / ctas);
-  splits = std::min(splits, std::max(1, w.kblocks / 4));
+  splits = std::min(splits, std::max(1, w.kblocks / 2));
   w.splits = splits;
-  const int b_stage = ((w.subs_per_tile * w.sub_n * kStageK * 2 + 1023) / 1024) * 1024;
-  const int per_stage = kStageK * 128 * 2 + b_stage;
-  w.stages = std::max(2, std::min(8, (232448 - 256 - 1024) / per_stage));
   return w;
 }
 
@@ -231,9 +284,13 @@ int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* w
   return check_cuda((int)cudaGetLastError(), "pack_weight_kernel");
 }
 
-int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
-                   const float* scale, const float* shift, int relu, const void* residual, int ldr, void* stream) {
+static int fprop_impl(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
+                      const float* scale, const float* shift, int relu, const void* residual, int ldr,
+                      const VtbBnTrain* bn, void* stream) {
   if (!conv_ok(c) || !x || !wf || !y) return fail(VTB_EINVAL, "vtb_conv_fprop: bad arguments");
+  if (bn && (!stats_partial || !bn->tickets || !bn->gamma || !bn->beta || !bn->mean || !bn->invstd || !bn->scale ||
+             !bn->shift || bn->count <= 0 || ((bn->running_mean == nullptr) != (bn->running_var == nullptr))))
+    return fail(VTB_EINVAL, "vtb_conv_fprop_bn: bad BatchNorm arguments");
   if (ldx < c->cin || ldy < c->cout || ldx % 8 || ldy % 8) return fail(VTB_EINVAL, "vtb_conv_fprop: bad pitch");
   if ((scale == nullptr) != (shift == nullptr)) return fail(VTB_EINVAL, "vtb_conv_fprop: scale/shift must pair");
   if (residual && (ldr < c->cout || ldr % 8)) return fail(VTB_EINVAL, "vtb_conv_fprop: bad residual pitch");
@@ -266,6 +323,21 @@ int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, voi
   p.out = (__nv_bfloat16*)y;
   p.ldo = ldy;
   p.stats_partial = stats_partial;
+  if (bn) {
+    p.tickets = bn->tickets;
+    p.bn_count = bn->count;
+    p.bn_gamma = bn->gamma;
+    p.bn_beta = bn->beta;
+    p.bn_eps = bn->eps;
+    p.bn_momentum = bn->momentum;
+    p.bn_running_mean = bn->running_mean;
+    p.bn_running_var = bn->running_var;
+    p.bn_nbt = bn->num_batches_tracked;
+    p.bn_mean = bn->mean;
+    p.bn_invstd = bn->invstd;
+    p.bn_scale = bn->scale;
+    p.bn_shift = bn->shift;
+  }
   p.scale = scale;
   p.shift = shift;
   p.relu = relu;
@@ -286,6 +358,17 @@ int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, voi
     return fail(VTB_ECUDA, "vtb_conv_fprop: tensor map for y failed");
   count_launch(1);
   return check_cuda(launch_conv_igemm(tmA, tmB, tmD, p, tl.grid, (cudaStream_t)stream), "conv_igemm_kernel(fprop)");
+}
+
+int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
+                   const float* scale, const float* shift, int relu, const void* residual, int ldr, void* stream) {
+  return fprop_impl(c, x, ldx, wf, y, ldy, stats_partial, scale, shift, relu, residual, ldr, nullptr, stream);
+}
+
+int vtb_conv_fprop_bn(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
+                      const VtbBnTrain* bn, void* stream) {
+  if (!bn) return fail(VTB_EINVAL, "vtb_conv_fprop_bn: bn must not be NULL");
+  return fprop_impl(c, x, ldx, wf, y, ldy, stats_partial, nullptr, nullptr, 0, nullptr, 0, bn, stream);
 }
 
 int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
@@ -428,10 +511,15 @@ int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, in
   p.ntaps = c->k * c->k;
   p.cc = w.cc;
   p.ca = w.ca;
-  p.sub_n = w.sub_n;
-  p.subs_per_tile = w.subs_per_tile;
+  p.ma = w.ma;
+  p.kpix = w.kpix;
+  p.boxes_per_tap = w.boxes_per_tap;
+  p.total_boxes = w.total_boxes;
+  p.boxes_per_tile = w.boxes_per_tile;
+  p.n_cols = w.n_cols;
   p.n_tiles = w.n_tiles;
-  p.total_subs = w.total_subs;
+  p.ksplit = w.ksplit;
+  p.acc_stride = (uint32_t)w.acc_stride;
   p.splits = w.splits;
   p.kblocks = w.kblocks;
   p.num_stages = w.stages;
@@ -441,20 +529,30 @@ int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, in
       p.tap_oh[r * c->k + s] = (uint16_t)r;
     }
   p.ws = (float*)workspace;
+  p.dbg = g_dbg;
   const int upper = c->pad - (c->k - 1);
   CUtensorMap tmDY, tmX;
-  if (!tmap_tiled_2d(&tmDY, dy, c->cout, (uint64_t)w.mpix, (uint64_t)lddy * 2, w.ca, kStageK, w.ca * 2))
+  if (!tmap_tiled_2d(&tmDY, dy, c->cout, (uint64_t)w.mpix, (uint64_t)lddy * 2, w.ca, w.kpix, w.ca * 2))
     return fail(VTB_ECUDA, "vtb_conv_wgrad: tensor map for dy failed");
-  if (!tmap_im2col_nhwc(&tmX, x, c->cin, c->w, c->h, c->n, ldx, -c->pad, -c->pad, upper, upper, w.cc, kStageK,
+  if (!tmap_im2col_nhwc(&tmX, x, c->cin, c->w, c->h, c->n, ldx, -c->pad, -c->pad, upper, upper, w.cc, w.kpix,
                         c->stride, w.cc * 2))
     return fail(VTB_ECUDA, "vtb_conv_wgrad: im2col tensor map for x failed");
   count_launch(2);
   int e = launch_wgrad_igemm(tmDY, tmX, p, w.m_tiles * w.n_tiles, (cudaStream_t)stream);
   if (e) return check_cuda(e, "wgrad_igemm_kernel");
-  const long long total = (long long)c->cout * cin_real * p.ntaps;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 2048);
-  wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, w.splits, c->cout, c->cin,
-                                                                cin_real, p.ntaps, dw_oihw, accumulate);
+  static const int no_reduce = env_int("VTB_WG_NOREDUCE");   // development: time the GEMM alone
+  if (no_reduce) return VTB_OK;
+  const int ew = c->cin <= 16 ? 16 : (c->cin <= 32 ? 32 : 64);
+  const dim3 rgrid(c->cout, (c->cin + ew - 1) / ew);
+  const size_t rsmem = (size_t)(256 / ew) * p.ntaps * (ew + 1) * sizeof(float);
+  const float* wsf = (const float*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ew == 16)
+    wgrad_reduce_kernel<16><<<rgrid, 256, rsmem, st>>>(wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
+  else if (ew == 32)
+    wgrad_reduce_kernel<32><<<rgrid, 256, rsmem, st>>>(wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
+  else
+    wgrad_reduce_kernel<64><<<rgrid, 256, rsmem, st>>>(wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
   return check_cuda((int)cudaGetLastError(), "wgrad_reduce_kernel");
 }
 

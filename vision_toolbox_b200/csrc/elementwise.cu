@@ -76,8 +76,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
     s = sums_in[ch * 2];
     q = sums_in[ch * 2 + 1];
   } else {
+#pragma unroll 4
     for (int r = lane; r < rows; r += 32) {
-      const float2 v = *reinterpret_cast<const float2*>(partial + ((size_t)r * c + ch) * 2);
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)r * c + ch) * 2));
       s += v.x;
       q += v.y;
     }
@@ -116,90 +117,147 @@ __global__ void bn_eval_affine_kernel(int c, const float* gamma, const float* be
 }
 
 // ---------------------------------------------------------------------------------------------
+// Thread geometry of the per-pixel passes: a block is `ppi` pixel lanes x `cv` channel vectors (8 channels = 16 bytes
+// each), so a thread's channels - and with them its per-channel parameters - are loop invariant: they are loaded once
+// into registers and the pixel loop contains no division and no parameter loads.  The pixel loop is unrolled kEwUnroll
+// times with all loads issued before the first use (memory-level parallelism is what reaches HBM bandwidth here).
+// ---------------------------------------------------------------------------------------------
+constexpr int kEwUnroll = 4;
+struct EwGeom {
+  int cv;      // channel vectors per block (<= 64); blockDim.x = ppi * cv
+  int ppi;     // pixel lanes per block
+  int chunks;  // blocks along the channel axis (gridDim.y)
+  int rows;    // blocks along the pixel axis (gridDim.x)
+};
+static EwGeom ew_geom(long long pixels, int c8, int max_threads, int blocks_per_sm) {
+  EwGeom g;
+  g.cv = std::min(c8, 64);
+  g.chunks = (c8 + g.cv - 1) / g.cv;
+  g.cv = (c8 + g.chunks - 1) / g.chunks;            // even split (c8 = 20/24/28 for VoVNet's 160/192/224 channels)
+  g.ppi = std::max(1, max_threads / g.cv);
+  const int sms = std::max(1, num_sms());
+  const long long want = (pixels + (long long)g.ppi * kEwUnroll - 1) / ((long long)g.ppi * kEwUnroll);
+  g.rows = (int)std::max<long long>(1, std::min<long long>(want, std::max(1, sms * blocks_per_sm / g.chunks)));
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------
 // out = [relu](y*scale + shift) [+ residual]     (bf16 rounding after the affine+relu, then after the add:
 // the reference adds two bf16 tensors, darknet.py:28 / vovnet.py:61)
 // ---------------------------------------------------------------------------------------------
 template <bool RELU, bool RES>
-__global__ void bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int c8,
-                              const float* __restrict__ scale, const float* __restrict__ shift,
-                              const __nv_bfloat16* __restrict__ res, int ldr, __nv_bfloat16* __restrict__ out,
-                              int ldo) {
-  const long long total = pixels * c8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / c8;
-    const int ch = (int)(i - pix * c8) * 8;
-    float f[8], sc[8], sh[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(y + pix * ldy + ch)), f);
-    load8f(scale + ch, sc);
-    load8f(shift + ch, sh);
+__global__ void __launch_bounds__(512)
+bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int c8, int cv,
+              const float* __restrict__ scale, const float* __restrict__ shift,
+              const __nv_bfloat16* __restrict__ res, int ldr, __nv_bfloat16* __restrict__ out, int ldo) {
+  const int vl = threadIdx.x % cv, pl = threadIdx.x / cv, ppi = blockDim.x / cv;
+  const int v = blockIdx.y * cv + vl;
+  if (v >= c8) return;
+  const int ch = v * 8;
+  float sc[8], sh[8];
+  load8f(scale + ch, sc);
+  load8f(shift + ch, sh);
+  const long long step = (long long)gridDim.x * ppi;
+  for (long long pix = (long long)blockIdx.x * ppi + pl; pix < pixels; pix += step * kEwUnroll) {
+    uint4 yv[kEwUnroll], rv[kEwUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      f[j] = fmaf(f[j], sc[j], sh[j]);
-      if (RELU) f[j] = fmaxf(f[j], 0.f);
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long q = pix + u * step;
+      if (q < pixels) {
+        yv[u] = __ldg(reinterpret_cast<const uint4*>(y + q * ldy + ch));
+        if (RES) rv[u] = __ldg(reinterpret_cast<const uint4*>(res + q * ldr + ch));
+      }
     }
-    if (RES) {
-      float r[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(res + pix * ldr + ch)), r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = rbf(f[j]) + r[j];
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long q = pix + u * step;
+      if (q < pixels) {
+        float f[8];
+        unpack8(yv[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaf(f[j], sc[j], sh[j]);
+          if (RELU) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (RES) {
+          float r[8];
+          unpack8(rv[u], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = rbf(f[j]) + r[j];
+        }
+        *reinterpret_cast<uint4*>(out + q * ldo + ch) = pack8(f);
+      }
     }
-    *reinterpret_cast<uint4*>(out + pix * ldo + ch) = pack8(f);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // BatchNorm(+ReLU) backward, stage 1: per-channel sums of dz and dz*xhat
 //   z = y*scale+shift, dz = dout * (z > 0) (ReLU mask recomputed from the saved conv output), xhat = (y-mean)*invstd
-// block = 256 threads handling ppi = 256/cvec pixels x cvec channel-vectors per iteration
+// one partial row per block along the pixel axis; the pixel lanes of a block are combined in a fixed order
 // ---------------------------------------------------------------------------------------------
 template <bool RELU>
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo,
-                                     const __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int c8, int cvec,
-                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                     float* __restrict__ partial, int c) {
-  __shared__ float red[256][17];
-  const int ppi = 256 / cvec;
+__global__ void __launch_bounds__(512)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ y, int ldy,
+                     long long pixels, int c8, int cv, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, float* __restrict__ partial, int c) {
+  extern __shared__ float red[];   // [blockDim.x][17]
   const int t = threadIdx.x;
-  const int v_local = t % cvec;
-  const int pl = t / cvec;
-  const int v = blockIdx.y * cvec + v_local;
+  const int vl = t % cv, pl = t / cv, ppi = blockDim.x / cv;
+  const int v = blockIdx.y * cv + vl;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  if (pl < ppi && v < c8) {
+  if (v < c8) {
     const int ch = v * 8;
     float sc[8], sh[8], mu[8], is[8];
     load8f(scale + ch, sc);
     load8f(shift + ch, sh);
     load8f(mean + ch, mu);
     load8f(invstd + ch, is);
-    for (long long pix = (long long)blockIdx.x * ppi + pl; pix < pixels; pix += (long long)gridDim.x * ppi) {
-      float g[8], yy[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dout + pix * lddo + ch)), g);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(y + pix * ldy + ch)), yy);
+    const long long step = (long long)gridDim.x * ppi;
+    for (long long pix = (long long)blockIdx.x * ppi + pl; pix < pixels; pix += step * kEwUnroll) {
+      uint4 gv[kEwUnroll], yv[kEwUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(yy[j], sc[j], sh[j]);
-        const float dz = (!RELU || z > 0.f) ? g[j] : 0.f;
-        s1[j] += dz;
-        s2[j] = fmaf(dz, (yy[j] - mu[j]) * is[j], s2[j]);
+      for (int u = 0; u < kEwUnroll; ++u) {
+        const long long q = pix + u * step;
+        if (q < pixels) {
+          gv[u] = __ldg(reinterpret_cast<const uint4*>(dout + q * lddo + ch));
+          yv[u] = __ldg(reinterpret_cast<const uint4*>(y + q * ldy + ch));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) {
+        const long long q = pix + u * step;
+        if (q < pixels) {
+          float g[8], yy[8];
+          unpack8(gv[u], g);
+          unpack8(yv[u], yy);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(yy[j], sc[j], sh[j]);
+            const float dz = (!RELU || z > 0.f) ? g[j] : 0.f;
+            s1[j] += dz;
+            s2[j] = fmaf(dz, (yy[j] - mu[j]) * is[j], s2[j]);
+          }
+        }
       }
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    red[t][j] = s1[j];
-    red[t][8 + j] = s2[j];
+    red[t * 17 + j] = s1[j];
+    red[t * 17 + 8 + j] = s2[j];
   }
   __syncthreads();
-  // outputs: cvec vectors x 16 values; sum over pl in fixed order (deterministic)
-  for (int o = t; o < cvec * 16; o += 256) {
-    const int vl = o / 16, j = o % 16;
-    const int vg = blockIdx.y * cvec + vl;
+  // outputs: cv vectors x 16 values; sum over the pixel lanes in fixed order (deterministic)
+  for (int o = t; o < cv * 16; o += blockDim.x) {
+    const int vl2 = o / 16, j = o % 16;
+    const int vg = blockIdx.y * cv + vl2;
     if (vg >= c8) continue;
     float acc = 0.f;
-    for (int q = 0; q < ppi; ++q) acc += red[q * cvec + vl][j];
+    for (int q = 0; q < ppi; ++q) acc += red[(q * cv + vl2) * 17 + j];
     const int ch = vg * 8 + (j & 7);
     partial[((size_t)blockIdx.x * c + ch) * 2 + (j >> 3)] = acc;
   }
@@ -218,8 +276,9 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ro
     s = sums_in[ch * 2];
     q = sums_in[ch * 2 + 1];
   } else {
+#pragma unroll 4
     for (int r = lane; r < rows; r += 32) {
-      const float2 v = *reinterpret_cast<const float2*>(partial + ((size_t)r * c + ch) * 2);
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)r * c + ch) * 2));
       s += v.x;
       q += v.y;
     }
@@ -246,33 +305,59 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ro
 
 // stage 3: dy = scale * (dz - mean_dz - xhat * mean_dzxhat)
 template <bool RELU>
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo,
-                                    const __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int c8,
-                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy, int lddy) {
-  const long long total = pixels * c8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / c8;
-    const int ch = (int)(i - pix * c8) * 8;
-    float g[8], yy[8], sc[8], sh[8], mu[8], is[8], cf[16];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dout + pix * lddo + ch)), g);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(y + pix * ldy + ch)), yy);
+__global__ void __launch_bounds__(512)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ y, int ldy,
+                    long long pixels, int c8, int cv, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ coef,
+                    __nv_bfloat16* __restrict__ dy, int lddy) {
+  const int vl = threadIdx.x % cv, pl = threadIdx.x / cv, ppi = blockDim.x / cv;
+  const int v = blockIdx.y * cv + vl;
+  if (v >= c8) return;
+  const int ch = v * 8;
+  // per-channel constants: dy = sc*dz - k0 - k1*(y - mu)   with k0 = sc*coef0, k1 = sc*invstd*coef1
+  float sc[8], sh[8], mu[8], k0[8], k1[8];
+  {
+    float is[8], cf[16];
     load8f(scale + ch, sc);
     load8f(shift + ch, sh);
     load8f(mean + ch, mu);
     load8f(invstd + ch, is);
     load8f(coef + ch * 2, cf);
     load8f(coef + ch * 2 + 8, cf + 8);
-    float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(yy[j], sc[j], sh[j]);
-      const float dz = (!RELU || z > 0.f) ? g[j] : 0.f;
-      const float xh = (yy[j] - mu[j]) * is[j];
-      o[j] = sc[j] * (dz - cf[2 * j] - xh * cf[2 * j + 1]);
+      k0[j] = sc[j] * cf[2 * j];
+      k1[j] = sc[j] * is[j] * cf[2 * j + 1];
     }
-    *reinterpret_cast<uint4*>(dy + pix * lddy + ch) = pack8(o);
+  }
+  const long long step = (long long)gridDim.x * ppi;
+  for (long long pix = (long long)blockIdx.x * ppi + pl; pix < pixels; pix += step * kEwUnroll) {
+    uint4 gv[kEwUnroll], yv[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long q = pix + u * step;
+      if (q < pixels) {
+        gv[u] = __ldg(reinterpret_cast<const uint4*>(dout + q * lddo + ch));
+        yv[u] = __ldg(reinterpret_cast<const uint4*>(y + q * ldy + ch));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long q = pix + u * step;
+      if (q < pixels) {
+        float g[8], yy[8], o[8];
+        unpack8(gv[u], g);
+        unpack8(yv[u], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(yy[j], sc[j], sh[j]);
+          const float dz = (!RELU || z > 0.f) ? g[j] : 0.f;
+          o[j] = fmaf(sc[j], dz, -k0[j]) - k1[j] * (yy[j] - mu[j]);
+        }
+        *reinterpret_cast<uint4*>(dy + q * lddy + ch) = pack8(o);
+      }
+    }
   }
 }
 
@@ -326,11 +411,7 @@ extern "C" {
 
 int vtb_bn_bwd_rows(long long pixels, int c) {
   if (pixels <= 0 || c <= 0 || c % 8) return fail(VTB_EINVAL, "vtb_bn_bwd_rows: bad arguments");
-  const int c8 = c / 8, cvec = std::min(c8, 256), ppi = 256 / cvec;
-  const int chunks = (c8 + cvec - 1) / cvec;
-  const int sms = num_sms() > 0 ? num_sms() : 148;
-  const long long want = (pixels + (long long)ppi * 8 - 1) / ((long long)ppi * 8);  // >= 8 pixels per thread
-  return (int)std::max<long long>(1, std::min<long long>(want, std::max(1, sms * 4 / chunks)));
+  return ew_geom(pixels, c / 8, 512, 2).rows;
 }
 
 int vtb_bn_stats_reduce(const float* partial, int rows, int c, double* sums, void* stream) {
@@ -370,15 +451,17 @@ int vtb_bn_act(const void* y, int ldy, long long pixels, int c, const float* sca
       (residual && !VIEW_OK(residual, ldr, c)))
     return fail(VTB_EINVAL, "vtb_bn_act: bad arguments");
   const int c8 = c / 8;
-  const int grid = ew_grid(pixels * c8, 256);
+  const EwGeom g = ew_geom(pixels, c8, 512, 4);
+  const dim3 grid(g.rows, g.chunks);
+  const int bs = g.ppi * g.cv;
   const __nv_bfloat16* yy = (const __nv_bfloat16*)y;
   const __nv_bfloat16* rr = (const __nv_bfloat16*)residual;
   __nv_bfloat16* oo = (__nv_bfloat16*)out;
   cudaStream_t st = (cudaStream_t)stream;
-  if (relu && rr) bn_act_kernel<true, true><<<grid, 256, 0, st>>>(yy, ldy, pixels, c8, scale, shift, rr, ldr, oo, ldo);
-  else if (relu) bn_act_kernel<true, false><<<grid, 256, 0, st>>>(yy, ldy, pixels, c8, scale, shift, rr, ldr, oo, ldo);
-  else if (rr) bn_act_kernel<false, true><<<grid, 256, 0, st>>>(yy, ldy, pixels, c8, scale, shift, rr, ldr, oo, ldo);
-  else bn_act_kernel<false, false><<<grid, 256, 0, st>>>(yy, ldy, pixels, c8, scale, shift, rr, ldr, oo, ldo);
+  if (relu && rr) bn_act_kernel<true, true><<<grid, bs, 0, st>>>(yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
+  else if (relu) bn_act_kernel<true, false><<<grid, bs, 0, st>>>(yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
+  else if (rr) bn_act_kernel<false, true><<<grid, bs, 0, st>>>(yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
+  else bn_act_kernel<false, false><<<grid, bs, 0, st>>>(yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "bn_act_kernel");
 }
@@ -389,17 +472,18 @@ int vtb_bn_bwd_reduce(const void* dout, int lddo, const void* y, int ldy, long l
   if (pixels <= 0 || c <= 0 || c % 8 || !VIEW_OK(dout, lddo, c) || !VIEW_OK(y, ldy, c) || !scale || !shift || !mean ||
       !invstd || !partial)
     return fail(VTB_EINVAL, "vtb_bn_bwd_reduce: bad arguments");
-  const int c8 = c / 8, cvec = std::min(c8, 256);
-  const int chunks = (c8 + cvec - 1) / cvec;
-  const int rows = vtb_bn_bwd_rows(pixels, c);
-  dim3 grid(rows, chunks);
+  const int c8 = c / 8;
+  const EwGeom g = ew_geom(pixels, c8, 512, 2);
+  const dim3 grid(g.rows, g.chunks);
+  const int bs = g.ppi * g.cv;
+  const size_t sm = (size_t)bs * 17 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (relu)
-    bn_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
-                                                     pixels, c8, cvec, scale, shift, mean, invstd, partial, c);
+    bn_bwd_reduce_kernel<true><<<grid, bs, sm, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+                                                     pixels, c8, g.cv, scale, shift, mean, invstd, partial, c);
   else
-    bn_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
-                                                      pixels, c8, cvec, scale, shift, mean, invstd, partial, c);
+    bn_bwd_reduce_kernel<false><<<grid, bs, sm, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+                                                      pixels, c8, g.cv, scale, shift, mean, invstd, partial, c);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "bn_bwd_reduce_kernel");
 }
@@ -423,16 +507,18 @@ int vtb_bn_bwd_apply(const void* dout, int lddo, const void* y, int ldy, long lo
       !scale || !shift || !mean || !invstd || !coef)
     return fail(VTB_EINVAL, "vtb_bn_bwd_apply: bad arguments");
   const int c8 = c / 8;
-  const int grid = ew_grid(pixels * c8, 256);
+  const EwGeom g = ew_geom(pixels, c8, 512, 4);
+  const dim3 grid(g.rows, g.chunks);
+  const int bs = g.ppi * g.cv;
   cudaStream_t st = (cudaStream_t)stream;
   if (relu)
-    bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
-                                                    pixels, c8, scale, shift, mean, invstd, coef, (__nv_bfloat16*)dy,
-                                                    lddy);
+    bn_bwd_apply_kernel<true><<<grid, bs, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+                                                   pixels, c8, g.cv, scale, shift, mean, invstd, coef,
+                                                   (__nv_bfloat16*)dy, lddy);
   else
-    bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
-                                                     pixels, c8, scale, shift, mean, invstd, coef, (__nv_bfloat16*)dy,
-                                                     lddy);
+    bn_bwd_apply_kernel<false><<<grid, bs, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+                                                    pixels, c8, g.cv, scale, shift, mean, invstd, coef,
+                                                    (__nv_bfloat16*)dy, lddy);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "bn_bwd_apply_kernel");
 }

@@ -509,26 +509,93 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     if (do_stats) {
-      // one statistics row per 32-row slice of the tile; this warp fills the columns of the panels it drained
-      float* rowp = p.stats_partial + (size_t)((m_first * halves + my_half) * 4 + quarter) * p.cout * 2;
+      // Combine the 4 (x2 halves) lane-quarter slices of the CTA in shared memory (fixed order), so that the CTA
+      // contributes ONE statistics row; then, if the caller asked for it (p.tickets), the last CTA of this n-block
+      // to finish turns the rows into mean / invstd / scale / shift and the running-statistics update - BatchNorm's
+      // finalisation costs no extra launch.
+      const int et = threadIdx.x - 128;             // 0..511 over the 16 epilogue warps
+      const int nslices = halves * 4;
+      float2* slots = reinterpret_cast<float2*>(smem_raw + (panel_base - smem_u32(smem_raw)));   // [8][block_n]
+      named_bar_sync(1, kEpiWarps * 32);            // every warp is done with its staging buffer
+      const int q8 = my_half * 4 + quarter;
       for (int pi = pi_first; pi < npanels; pi += pi_step) {
         const int lpi = (pi - pi_first) / pi_step;
-        float4 o = (lpi < 2) ? a0 : a1;
-        if (lpi & 1) o = make_float4(o.z, o.w, 0.f, 0.f);
-        const int cbase = n0 + pi * pw;
-        // column owned by this lane after the butterfly (see panel_col_stats): row-group bit k selects half 4>>k
-        if (pw == 64) {
-          const int rg = lane >> 3;
-          const int col = (lane & 7) * 8 + (rg & 1) * 4 + (rg >> 1) * 2;
-          *reinterpret_cast<float4*>(rowp + (size_t)(cbase + col) * 2) = o;
-        } else if (pw == 32) {
+        const float4 o4 = (lpi < 2) ? a0 : a1;
+        const float2 o = (lpi & 1) ? make_float2(o4.z, o4.w) : make_float2(o4.x, o4.y);
+        // column owned by this lane after the butterfly (see panel_drain): row-group bit k selects half 4>>k
+        int col = -1;
+        if (pw == 32) {
           const int rg = lane >> 2;
-          const int col = (lane & 3) * 8 + (rg & 1) * 4 + ((rg >> 1) & 1) * 2 + (rg >> 2);
-          *reinterpret_cast<float2*>(rowp + (size_t)(cbase + col) * 2) = make_float2(o.x, o.y);
+          col = (lane & 3) * 8 + (rg & 1) * 4 + ((rg >> 1) & 1) * 2 + (rg >> 2);
         } else if ((lane >> 4) == 0) {
           const int rg = lane >> 1;
-          const int col = (lane & 1) * 8 + (rg & 1) * 4 + ((rg >> 1) & 1) * 2 + ((rg >> 2) & 1);
-          *reinterpret_cast<float2*>(rowp + (size_t)(cbase + col) * 2) = make_float2(o.x, o.y);
+          col = (lane & 1) * 8 + (rg & 1) * 4 + ((rg >> 1) & 1) * 2 + ((rg >> 2) & 1);
+        }
+        if (col >= 0) slots[q8 * p.block_n + pi * pw + col] = o;
+      }
+      named_bar_sync(1, kEpiWarps * 32);
+      float* rowp = p.stats_partial + (size_t)m_first * p.cout * 2;
+      if (et < p.block_n) {
+        float sx = 0.f, sq = 0.f;
+        for (int q = 0; q < nslices; ++q) {
+          const float2 v = slots[q * p.block_n + et];
+          sx += v.x;
+          sq += v.y;
+        }
+        *reinterpret_cast<float2*>(rowp + (size_t)(n0 + et) * 2) = make_float2(sx, sq);
+      }
+      if (p.tickets != nullptr) {
+        __threadfence();
+        named_bar_sync(1, kEpiWarps * 32);
+        uint32_t* flag = reinterpret_cast<uint32_t*>(slots);
+        if (et == 0) {
+          const unsigned int t = atomicAdd(p.tickets + n_blk, 1u);
+          *flag = (t == (unsigned int)(m_step - 1)) ? 1u : 0u;
+        }
+        named_bar_sync(1, kEpiWarps * 32);
+        const bool last = (*flag != 0u);
+        named_bar_sync(1, kEpiWarps * 32);          // everyone has read the flag before the slots are reused
+        if (last) {
+          __threadfence();
+          // G row groups x block_n columns; each thread sums rows g, g+G, .. of its column in double
+          const int G = (kEpiWarps * 32) / p.block_n;
+          const int g = et / p.block_n, col = et - g * p.block_n;
+          double* dsl = reinterpret_cast<double*>(slots);   // [G][block_n][2]
+          if (g < G) {
+            double sx = 0.0, sq = 0.0;
+            for (int r = g; r < m_step; r += G) {
+              const float2 v = __ldcg(reinterpret_cast<const float2*>(p.stats_partial + ((size_t)r * p.cout + n0 + col) * 2));
+              sx += (double)v.x;
+              sq += (double)v.y;
+            }
+            dsl[(g * p.block_n + col) * 2] = sx;
+            dsl[(g * p.block_n + col) * 2 + 1] = sq;
+          }
+          named_bar_sync(1, kEpiWarps * 32);
+          if (et < p.block_n) {
+            double sx = 0.0, sq = 0.0;
+            for (int gg = 0; gg < G; ++gg) {
+              sx += dsl[(gg * p.block_n + et) * 2];
+              sq += dsl[(gg * p.block_n + et) * 2 + 1];
+            }
+            const int ch = n0 + et;
+            const double mean = sx / p.bn_count;
+            double var = sq / p.bn_count - mean * mean;
+            if (var < 0) var = 0;
+            const float invstd = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+            p.bn_mean[ch] = (float)mean;
+            p.bn_invstd[ch] = invstd;
+            const float sc = p.bn_gamma[ch] * invstd;
+            p.bn_scale[ch] = sc;
+            p.bn_shift[ch] = p.bn_beta[ch] - (float)mean * sc;
+            if (p.bn_running_mean != nullptr) {
+              const double unbiased = p.bn_count > 1 ? var * (p.bn_count / (p.bn_count - 1.0)) : var;
+              p.bn_running_mean[ch] = (1.f - p.bn_momentum) * p.bn_running_mean[ch] + p.bn_momentum * (float)mean;
+              p.bn_running_var[ch] = (1.f - p.bn_momentum) * p.bn_running_var[ch] + p.bn_momentum * (float)unbiased;
+            }
+            if (ch == 0 && p.bn_nbt != nullptr) *p.bn_nbt += 1;
+          }
+          if (et == 0) p.tickets[n_blk] = 0u;       // self-cleaning: ready for the next launch
         }
       }
     }
@@ -591,32 +658,43 @@ void fill_derived(ConvIgemmParams& p, int grid) {
 
 // ------------------------------------------------------------------------------------------------
 // wgrad_igemm_kernel
+//
+// dW[Cout][tap*Cin] = sum over pixels dY[pix][Cout]^T * im2col(X)[pix][tap*Cin]: both operands MN-major (the GEMM-K
+// axis = pixels is the strided one), split over the pixel axis, fp32 partials per split (deterministic).
+// One CTA owns a 128 (Cout) x n_cols (<= 256 flattened tap*Cin columns) tile and ONE UMMA N = n_cols; successive
+// 16-pixel K slices go round-robin to `ksplit` TMEM accumulators (independent dependency chains, summed in the epilogue).
+// Operand feed: per stage `kpix` pixels = a_boxes dY boxes [kpix][ca] + b_boxes im2col X boxes [kpix][cc].  A single
+// thread sustains only one TMA request per ~300 (tiled) / ~600 (im2col) cycles (profiles/r01_tma_bw.txt), so the requests
+// of a stage are dealt round-robin to kWgProducers producer warps; every producer arrives on the stage's full barrier
+// with the byte count of the boxes it issued.
+//   warps 0..NP-1 : TMA producers     warp NP : TMEM owner + MMA issuer     warps NP+1..NP+4 : epilogue
 // ------------------------------------------------------------------------------------------------
 struct WgradSmem {
   uint32_t a_stage, b_stage, a_off, b_off, bar_off, total;
 };
-static __host__ __device__ inline WgradSmem wgrad_smem_layout(int subs_per_tile, int sub_n, int kpix, int num_stages) {
+static __host__ __device__ inline WgradSmem wgrad_smem_layout(int ma, int n_cols, int kpix, int num_stages) {
   WgradSmem s;
-  s.a_stage = kpix * 128 * 2;
-  s.b_stage = round_up_int(subs_per_tile * sub_n * kpix * 2, 1024);
+  s.a_stage = round_up_int(kpix * ma * 2, 1024);
+  s.b_stage = round_up_int(kpix * n_cols * 2, 1024);
   s.a_off = 0;
   s.b_off = num_stages * s.a_stage;
   s.bar_off = s.b_off + num_stages * s.b_stage;
   s.total = s.bar_off + 256;
   return s;
 }
-size_t wgrad_igemm_smem_bytes(int subs_per_tile, int sub_n, int num_stages) {
-  return wgrad_smem_layout(subs_per_tile, sub_n, kStageK, num_stages).total + 1024;
+size_t wgrad_igemm_smem_bytes(int ma, int n_cols, int kpix, int num_stages) {
+  return wgrad_smem_layout(ma, n_cols, kpix, num_stages).total + 1024;
 }
 
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <bool TIMED>
+__global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                    const __grid_constant__ WgradIgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr int kpix = kStageK;
   const int S = p.num_stages;
-  const WgradSmem L = wgrad_smem_layout(p.subs_per_tile, p.sub_n, kpix, S);
+  const int kpix = p.kpix;
+  const WgradSmem L = wgrad_smem_layout(p.ma, p.n_cols, kpix, S);
   const uint32_t a_base = base + L.a_off;
   const uint32_t b_base = base + L.b_off;
   const uint32_t bar_base = base + L.bar_off;
@@ -624,125 +702,159 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * S);
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 1);
-  uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool timed = TIMED;   // development counters (WgradIgemmParams::dbg), compiled out of the production kernel
+  const long long t_start = timed ? clock64() : 0;
+  unsigned long long* dbg = timed ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 
-  // tile decode: blockIdx.x = (m_tile * n_tiles + n_tile), blockIdx.y = split
+  // tile decode: blockIdx.x = m_tile * n_tiles + n_tile, blockIdx.y = split
   const int n_tile = blockIdx.x % p.n_tiles;
   const int m_tile = blockIdx.x / p.n_tiles;
   const int split = blockIdx.y;
-  const int sub0 = n_tile * p.subs_per_tile;
-  const int nsubs = min(p.subs_per_tile, p.total_subs - sub0);
+  const int box0 = n_tile * p.boxes_per_tile;                       // first (tap, c0) box of this tile
+  const int b_boxes = min(p.boxes_per_tile, p.total_boxes - box0);  // real X boxes of this tile
   const int kb_per = (p.kblocks + p.splits - 1) / p.splits;
   const int kb0 = split * kb_per;
   const int kb1 = min(p.kblocks, kb0 + kb_per);
   const int nkb = max(0, kb1 - kb0);
-  const int subs_per_tap = p.cin / p.sub_n;
   const int co0 = m_tile * 128;
-  const int a_boxes = min(128, p.cout - co0) / p.ca;     // real dY boxes along Cout
-  const int b_boxes = p.sub_n / p.cc;                     // boxes per sub-tile along Cin
+  const int a_boxes = min(128, p.cout - co0) / p.ca;                // real dY boxes along Cout
   const uint32_t a_box_bytes = kpix * p.ca * 2;
   const uint32_t b_box_bytes = kpix * p.cc * 2;
-  const uint32_t b_sub_bytes = kpix * p.sub_n * 2;
+  const int reqs = a_boxes + b_boxes;                               // TMA requests per stage
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), kWgProducers);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kWgProducers) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0) {
+  if (warp < kWgProducers) {
+    // ======================= TMA producers =======================
     if (elect_one()) {
       tma_prefetch_desc(&tmDY);
       tma_prefetch_desc(&tmX);
       uint32_t stage = 0, phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const int pix0 = kb * kpix;
-        const int q0 = pix0 % p.Wq;
-        const int t = pix0 / p.Wq;
-        const int p0 = t % p.Hp;
-        const int img = t / p.Hp;
-        const int bw = p.lower_w + q0 * p.stride;
-        const int bh = p.lower_h + p0 * p.stride;
-        mbar_expect_tx(full_bar(stage), a_boxes * a_box_bytes + nsubs * b_sub_bytes);
-        const uint32_t a_st = a_base + stage * L.a_stage;
-        const uint32_t b_st = b_base + stage * L.b_stage;
-        for (int b = 0; b < a_boxes; ++b)
-          tma_load_2d(a_st + b * a_box_bytes, &tmDY, full_bar(stage), co0 + b * p.ca, pix0);
-        for (int s = 0; s < nsubs; ++s) {
-          const int sub = sub0 + s;
-          const int tap = sub / subs_per_tap;
-          const int c0 = (sub - tap * subs_per_tap) * p.sub_n;
-          for (int b = 0; b < b_boxes; ++b)
-            tma_load_im2col_4d(b_st + s * b_sub_bytes + b * b_box_bytes, &tmX, full_bar(stage), c0 + b * p.cc, bw, bh,
-                               img, p.tap_ow[tap], p.tap_oh[tap]);
+      uint32_t g = 0;  // running request counter at the start of the stage (same value in every producer)
+      long long waited = 0;
+      for (int kb = kb0; kb < kb1; ++kb, g += reqs) {
+        mbar_wait_t(empty_bar(stage), phase ^ 1u, timed, waited);
+        // requests r of this stage with (g + r) % NP == warp are mine
+        int r = (int)((warp + kWgProducers - (g % kWgProducers)) % kWgProducers);
+        int mine_a = 0, mine_b = 0;
+        for (int q = r; q < reqs; q += kWgProducers) (q < a_boxes) ? ++mine_a : ++mine_b;
+        const uint32_t bytes = mine_a * a_box_bytes + mine_b * b_box_bytes;
+        if (bytes) mbar_expect_tx(full_bar(stage), bytes);
+        else mbar_arrive(full_bar(stage));
+        if (bytes) {
+          const int pix0 = kb * kpix;
+          const int q0 = pix0 % p.Wq;
+          const int t = pix0 / p.Wq;
+          const int p0 = t % p.Hp;
+          const int img = t / p.Hp;
+          const int bw = p.lower_w + q0 * p.stride;
+          const int bh = p.lower_h + p0 * p.stride;
+          const uint32_t a_st = a_base + stage * L.a_stage;
+          const uint32_t b_st = b_base + stage * L.b_stage;
+          for (; r < reqs; r += kWgProducers) {
+            if (r < a_boxes) {
+              tma_load_2d(a_st + r * a_box_bytes, &tmDY, full_bar(stage), co0 + r * p.ca, pix0);
+            } else {
+              const int b = r - a_boxes;
+              const int box = box0 + b;
+              const int tap = box / p.boxes_per_tap;
+              const int c0 = (box - tap * p.boxes_per_tap) * p.cc;
+              tma_load_im2col_4d(b_st + b * b_box_bytes, &tmX, full_bar(stage), c0, bw, bh, img, p.tap_ow[tap],
+                                 p.tap_oh[tap]);
+            }
+          }
         }
         if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
       }
+      if (timed && warp == 0) dbg[0] = waited;
     }
-  } else if (warp == 1) {
+  } else if (warp == kWgProducers) {
+    // ======================= MMA issuer =======================
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, p.sub_n, 1, 1);
+      const uint32_t n_mma = (uint32_t)b_boxes * p.cc;   // UMMA N of this tile (multiple of 16, <= 256)
+      const uint32_t idesc = make_idesc_bf16(128, n_mma, 1, 1);
       const uint32_t lta = (p.ca == 64) ? 2u : (p.ca == 32 ? 4u : 6u);
       const uint32_t ltb = (p.cc == 64) ? 2u : (p.cc == 32 ? 4u : 6u);
       const uint32_t sbo_a = 8u * p.ca * 2u, sbo_b = 8u * p.cc * 2u;
-      uint32_t stage = 0, phase = 0;
+      // MN-major operands: LBO = distance between the channel boxes, SBO = distance between 8-pixel groups
+      const uint64_t adesc_hi = make_smem_desc(0, a_box_bytes, sbo_a, lta);
+      const uint64_t bdesc_hi = make_smem_desc(0, b_box_bytes, sbo_b, ltb);
+      const uint32_t a_k16 = (2u * sbo_a) >> 4, b_k16 = (2u * sbo_b) >> 4;
+      const uint32_t ks_mask = (uint32_t)p.ksplit - 1u;
+      const int k16s = kpix / 16;
+      uint32_t stage = 0, phase = 0, kk = 0;
+      long long w_full = 0;
+      if (timed) dbg[6] = clock64() - t_start;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait_t(full_bar(stage), phase, timed, w_full);
+        if (timed && kb == kb0) dbg[5] = w_full;
         tc_fence_after();
-        const uint32_t a_st = a_base + stage * L.a_stage;
-        const uint32_t b_st = b_base + stage * L.b_stage;
-        for (int s = 0; s < nsubs; ++s) {
-          for (int k16 = 0; k16 < kpix / 16; ++k16) {
-            const uint64_t adesc = make_smem_desc(a_st + k16 * 2 * sbo_a, a_box_bytes, sbo_a, lta);
-            const uint64_t bdesc = make_smem_desc(b_st + s * b_sub_bytes + k16 * 2 * sbo_b, b_box_bytes, sbo_b, ltb);
-            umma_bf16(tmem_base + s * p.sub_n, adesc, bdesc, idesc, (kb > kb0 || k16 > 0) ? 1u : 0u);
-          }
-        }
+        uint32_t a16 = (a_base + stage * L.a_stage) >> 4;
+        uint32_t b16 = (b_base + stage * L.b_stage) >> 4;
+        for (int k16 = 0; k16 < k16s; ++k16, ++kk, a16 += a_k16, b16 += b_k16)
+          umma_bf16(tmem_base + (kk & ks_mask) * p.acc_stride, adesc_hi | (uint64_t)a16, bdesc_hi | (uint64_t)b16, idesc,
+                    (kk > ks_mask) ? 1u : 0u);
         umma_commit(empty_bar(stage));
         if (++stage == (uint32_t)S) { stage = 0; phase ^= 1u; }
       }
       umma_commit(tfull_bar);
+      if (timed) dbg[1] = w_full;
     }
   } else {
+    // ======================= epilogue: TMEM -> fp32 partial tile of this split =======================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int co = co0 + row;
     const int ktot = p.ntaps * p.cin;
+    const int n_mma = b_boxes * p.cc;
+    const int ks_used = min(p.ksplit, nkb * (kpix / 16));   // accumulators that received at least one MMA
+    long long w_tf = 0;
     if (nkb > 0) {
-      mbar_wait(tfull_bar, 0);
+      mbar_wait_t(tfull_bar, 0, timed, w_tf);
       tc_fence_after();
     }
-    float* wrow = p.ws + ((size_t)split * p.cout + co) * ktot;
-    for (int s = 0; s < nsubs; ++s) {
-      const int sub = sub0 + s;
-      const int tap = sub / subs_per_tap;
-      const int c0 = (sub - tap * subs_per_tap) * p.sub_n;
-      for (int ch = 0; ch < p.sub_n / 16; ++ch) {
+    const long long t_epi = timed ? clock64() : 0;
+    if (timed && quarter == 0 && lane == 0) dbg[3] = w_tf;
+    if (co0 + quarter * 32 < p.cout) {   // warp-uniform: skip lane quarters that hold no real output channel
+      float* wrow = p.ws + ((size_t)split * p.cout + min(co, p.cout - 1)) * ktot + (size_t)box0 * p.cc;
+      for (int ch = 0; ch < n_mma / 16; ++ch) {
         uint32_t v[16];
         if (nkb > 0) {
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + s * p.sub_n + ch * 16, v);
+          const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 16;
+          tmem_ld16(ta, v);
           tmem_ld_wait();
+          for (int s = 1; s < ks_used; ++s) {
+            uint32_t v2[16];
+            tmem_ld16(ta + s * p.acc_stride, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0u;
         }
         if (co < p.cout) {
-          float4* dst = reinterpret_cast<float4*>(wrow + tap * p.cin + c0 + ch * 16);
+          float4* dst = reinterpret_cast<float4*>(wrow + ch * 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
@@ -750,10 +862,12 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         }
       }
     }
+    if (timed && quarter == 0 && lane == 0) dbg[4] = clock64() - t_epi;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (timed && threadIdx.x == 0) dbg[2] = clock64() - t_start;
+  if (warp == kWgProducers) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -806,12 +920,15 @@ int launch_wgrad_igemm(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wg
                        cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wgrad_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const size_t smem = wgrad_igemm_smem_bytes(p.subs_per_tile, p.sub_n, p.num_stages);
-  wgrad_igemm_kernel<<<dim3(grid_x, p.splits), kNumThreads, smem, stream>>>(tmDY, tmX, p);
+  const size_t smem = wgrad_igemm_smem_bytes(p.ma, p.n_cols, p.kpix, p.num_stages);
+  if (p.dbg != nullptr) wgrad_igemm_kernel<true><<<dim3(grid_x, p.splits), kWgThreads, smem, stream>>>(tmDY, tmX, p);
+  else wgrad_igemm_kernel<false><<<dim3(grid_x, p.splits), kWgThreads, smem, stream>>>(tmDY, tmX, p);
   return (int)cudaGetLastError();
 }
 

@@ -16,7 +16,8 @@ namespace vtb {
 constexpr int kBlockM = 128;       // rows per UMMA (M); a conv tile is 1 or 2 such halves (block_m 128 / 256)
 constexpr int kStageK = 64;        // K elements (bf16) per pipeline stage
 constexpr int kMaxTaps = 36;       // 6x6 filter
-constexpr int kNumThreads = 192;   // wgrad kernel: warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kWgProducers = 8;    // wgrad kernel: TMA producer warps
+constexpr int kWgThreads = (kWgProducers + 1 + 4) * 32;  // + MMA warp + 4 epilogue warps
 constexpr int kConvThreads = 640;  // conv kernel: warp0/3 A producers, warp1 MMA, warp2 B producer, warps 4-19 epilogue (4 groups)
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = 128;   // threads per epilogue group
@@ -62,9 +63,22 @@ struct ConvIgemmParams {
   __nv_bfloat16* out;
   int OH, OW, os, oph, opw, ldo;
   // per-channel batch statistics of the bf16-rounded result: [rows][cout][2] (sum, sumsq),
-  // rows = (gridDim.x / n_blocks) * 4 * (block_m / 128): one per 32-row slice of the tile; every (row, channel) is
-  // written exactly once
+  // rows = gridDim.x / n_blocks: one per CTA; every (row, channel) is written exactly once
   float* stats_partial;
+  // optional in-kernel BatchNorm finalisation by the last CTA of every n-block (tickets != nullptr): [n_blocks]
+  // zero-initialised counters (left zero again), the per-channel element count and the BatchNorm tensors
+  unsigned int* tickets;
+  double bn_count;
+  const float* bn_gamma;
+  const float* bn_beta;
+  float bn_eps, bn_momentum;
+  float* bn_running_mean;
+  float* bn_running_var;
+  long long* bn_nbt;
+  float* bn_mean;
+  float* bn_invstd;
+  float* bn_scale;
+  float* bn_shift;
   // optional fused per-channel affine + ReLU (+ residual) epilogue (eval-mode folded BN)
   const float* scale;
   const float* shift;
@@ -80,23 +94,29 @@ struct WgradIgemmParams {
   int Wq, Hp;        // dY pixel lattice
   int stride, lower_w, lower_h;
   int cout, cin;
-  int ntaps;         // taps handled per n-tile group table below
-  int cc;            // channels per B sub-tile box (16/32/64)
-  int ca;            // channels per A (dY) box (16/32/64)
-  int sub_n;         // UMMA N per MMA (= min(cin, 256) slice width)
-  int subs_per_tile; // number of (tap, c0) sub-tiles per CTA n-tile; subs_per_tile*sub_n <= 512
-  int n_tiles;       // CTA n-tiles
-  int total_subs;    // ntaps * (cin / sub_n)
+  int ntaps;
+  int ca;            // channels per dY box (16/32/64)
+  int cc;            // channels per X box (16/32/64); the flattened tap*cin column axis is tiled in boxes of cc
+  int ma;            // dY channels staged per stage: min(128, cout)
+  int kpix;          // pixels (GEMM K) per pipeline stage = TMA box rows (64/128/256)
+  int boxes_per_tap; // cin / cc
+  int total_boxes;   // ntaps * boxes_per_tap
+  int boxes_per_tile;// X boxes per CTA tile: n_cols = boxes_per_tile * cc <= 256
+  int n_cols;
+  int n_tiles;       // CTA tiles along the column axis
+  int ksplit;        // TMEM accumulators fed round-robin (power of two, ksplit * acc_stride <= 512)
+  uint32_t acc_stride;
   int splits;        // split-K factor over pixel blocks
-  int kblocks;       // ceil(Mpix / 64)
+  int kblocks;       // ceil(Mpix / kpix)
   int num_stages;
   uint16_t tap_ow[kMaxTaps];
   uint16_t tap_oh[kMaxTaps];
   float* ws;         // [splits][cout][ntaps*cin] fp32 partials
+  unsigned long long* dbg;   // development aid (tools/bench_conv): per-CTA [16] cycle counters; usually null
 };
 
 size_t conv_igemm_smem_bytes(int block_m, int block_n, int num_stages, int panel_bufs);
-size_t wgrad_igemm_smem_bytes(int subs_per_tile, int sub_n, int num_stages);
+size_t wgrad_igemm_smem_bytes(int ma, int n_cols, int kpix, int num_stages);
 
 // completes the derived fields of ConvIgemmParams from block_m/block_n/num_stages/ksplit/kc/cin/ntaps/M/cout and grid
 void fill_derived(ConvIgemmParams& p, int grid);

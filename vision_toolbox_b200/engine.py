@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import VtbConv, check
+from ._lib import VtbBnTrain, VtbConv, check
 
 BF16 = 2
 
@@ -302,6 +302,8 @@ class Runner:
         self.L = _lib.lib()
         self.dist: Optional[DistConfig] = None
         self.grad_sink = False
+        # ticket counters of the fused conv + BatchNorm-finalize kernels (self-cleaning, shared by all layers)
+        self.tickets = torch.zeros(256, dtype=torch.int32, device=device)
 
     # -- helpers
     def _stream(self) -> int:
@@ -391,8 +393,6 @@ class Runner:
             return
         y = op.y
         use_batch_stats = g.training
-        check(L.vtb_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(), abase + y.byte_offset(),
-                               y.ld, f("partial_f") if use_batch_stats else 0, 0, 0, 0, 0, 0, st), "vtb_conv_fprop")
         if use_batch_stats:
             mom = norm.momentum if norm.momentum is not None else 0.1
             track = norm.track_running_stats and norm.running_mean is not None
@@ -400,18 +400,26 @@ class Runner:
             rv = norm.running_var.data_ptr() if track else 0
             nbt = norm.num_batches_tracked.data_ptr() if track else 0
             count = float(out.pixels)
-            if world > 1:
-                check(L.vtb_bn_stats_reduce(f("partial_f"), op.rows_f, cout, f("sums"), st), "vtb_bn_stats_reduce")
-                sums = run.stat_view_f64(op.st["sums"], cout * 2, sbase)
-                self.dist.all_reduce_(sums)
-                check(L.vtb_bn_finalize(0, 0, f("sums"), count * world, cout, norm.weight.data_ptr(),
-                                        norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt, f("mean"), f("invstd"),
-                                        f("scale"), f("shift"), st), "vtb_bn_finalize")
-            else:
-                check(L.vtb_bn_finalize(f("partial_f"), op.rows_f, 0, count, cout, norm.weight.data_ptr(),
-                                        norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt, f("mean"), f("invstd"),
-                                        f("scale"), f("shift"), st), "vtb_bn_finalize")
+        if use_batch_stats and world == 1:
+            # conv + statistics + BatchNorm finalisation in ONE launch (last CTA finalises)
+            bn = VtbBnTrain(count, norm.weight.data_ptr(), norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt,
+                            f("mean"), f("invstd"), f("scale"), f("shift"), self.tickets.data_ptr())
+            check(L.vtb_conv_fprop_bn(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(),
+                                      abase + y.byte_offset(), y.ld, f("partial_f"), C.byref(bn), st),
+                  "vtb_conv_fprop_bn")
         else:
+            check(L.vtb_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(),
+                                   abase + y.byte_offset(), y.ld, f("partial_f") if use_batch_stats else 0, 0, 0, 0, 0,
+                                   0, st), "vtb_conv_fprop")
+        if use_batch_stats and world > 1:
+            # SyncBN: local sums -> cross-rank sum -> finalise with the GLOBAL element count
+            check(L.vtb_bn_stats_reduce(f("partial_f"), op.rows_f, cout, f("sums"), st), "vtb_bn_stats_reduce")
+            sums = run.stat_view_f64(op.st["sums"], cout * 2, sbase)
+            self.dist.all_reduce_(sums)
+            check(L.vtb_bn_finalize(0, 0, f("sums"), count * world, cout, norm.weight.data_ptr(),
+                                    norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt, f("mean"), f("invstd"),
+                                    f("scale"), f("shift"), st), "vtb_bn_finalize")
+        elif not use_batch_stats:
             # frozen statistics but autograd requested: affine from running stats, mean/invstd kept for backward
             check(L.vtb_bn_eval_affine(cout, norm.weight.data_ptr(), norm.bias.data_ptr(), norm.running_mean.data_ptr(),
                                        norm.running_var.data_ptr(), norm.eps, f("scale"), f("shift"), st),
