@@ -143,6 +143,15 @@ int vtb_bn_bwd_apply(const void* dout, int lddo, const void* y, int ldy, long lo
                      const float* shift, const float* mean, const float* invstd, int relu, const float* coef,
                      void* dy, int lddy, void* stream);
 
+/* The three calls above in ONE cooperative launch (single-GPU statistics): reduce -> grid barrier -> finalize -> apply.
+ * partial: vtb_bn_bwd_fused_rows(pixels, c) * c * 2 floats of scratch; sync: >= 128 zero-initialised uint32 owned by the
+ * caller (left zero); dgamma / dbeta may be NULL.  c % 16 == 0. */
+int vtb_bn_bwd_fused_rows(long long pixels, int c);
+int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long long pixels, int c, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, int relu, double count,
+                     float* partial, float* dgamma, float* dbeta, int accumulate, unsigned int* sync, void* dy,
+                     int lddy, void* stream);
+
 /* dst (+)= src on bf16 NHWC views: gradient fan-out of the residual add (darknet.py:28) when it cannot be
  * aliased, and injection of incoming feature-map gradients. */
 int vtb_grad_add(void* dst, int ldd, const void* src, int lds, long long pixels, int c, int accumulate, void* stream);

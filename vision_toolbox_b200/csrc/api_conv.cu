@@ -29,6 +29,14 @@ int check_cuda(int e, const char* what) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("VTB_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
 int num_sms() {
   static int sms = [] {
     int dev = 0, n = 0;
@@ -131,6 +139,8 @@ static void apply_tiling(ConvIgemmParams& p, const ConvTiling& t) {
 __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin_real, int cin, int kk,
                                    __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
   const long long total = (long long)cout * kk * cin;
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(i % cin);
     const int t = (int)((i / cin) % kk);
@@ -157,6 +167,8 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin,
   const int c0 = blockIdx.y * EW;
   const int cw = min(EW, cin - c0);              // channels of the (padded) workspace row handled here
   const int cr = min(cw, cin_real - c0);         // of which real (the image stem pads 3 -> 16)
+  pdl_wait();
+  pdl_trigger();
   if (cr <= 0) return;
   const int e = threadIdx.x % EW, sg = threadIdx.x / EW;
   constexpr int pitch = EW + 1;
@@ -278,10 +290,10 @@ int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* w
     return fail(VTB_EINVAL, "vtb_pack_weight: bad arguments");
   const long long total = (long long)c->cout * c->k * c->k * c->cin;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
-  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, c->cout, cin_real, c->cin, c->k * c->k,
-                                                               (__nv_bfloat16*)wf, (__nv_bfloat16*)wd);
   count_launch(1);
-  return check_cuda((int)cudaGetLastError(), "pack_weight_kernel");
+  return check_cuda((int)launch_pdl(pack_weight_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, w_oihw, c->cout,
+                                    cin_real, c->cin, c->k * c->k, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd),
+                    "pack_weight_kernel");
 }
 
 static int fprop_impl(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
@@ -547,13 +559,14 @@ int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, in
   const size_t rsmem = (size_t)(256 / ew) * p.ntaps * (ew + 1) * sizeof(float);
   const float* wsf = (const float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t re;
   if (ew == 16)
-    wgrad_reduce_kernel<16><<<rgrid, 256, rsmem, st>>>(wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
+    re = launch_pdl(wgrad_reduce_kernel<16>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
   else if (ew == 32)
-    wgrad_reduce_kernel<32><<<rgrid, 256, rsmem, st>>>(wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
+    re = launch_pdl(wgrad_reduce_kernel<32>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
   else
-    wgrad_reduce_kernel<64><<<rgrid, 256, rsmem, st>>>(wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
-  return check_cuda((int)cudaGetLastError(), "wgrad_reduce_kernel");
+    re = launch_pdl(wgrad_reduce_kernel<64>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
+  return check_cuda((int)re, "wgrad_reduce_kernel");
 }
 
 }  // extern "C"

@@ -44,6 +44,8 @@ static int ew_grid(long long vecs, int block) {
 // ---------------------------------------------------------------------------------------------
 // one warp per channel
 __global__ void bn_stats_reduce_kernel(const float* __restrict__ partial, int rows, int c, double* __restrict__ sums) {
+  pdl_wait();
+  pdl_trigger();
   const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (ch >= c) return;
@@ -68,6 +70,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
                                    const float* __restrict__ beta, float eps, float momentum, float* running_mean,
                                    float* running_var, long long* nbt, float* mean_out, float* invstd_out,
                                    float* scale, float* shift) {
+  pdl_wait();
+  pdl_trigger();
   const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (ch >= c) return;
@@ -109,6 +113,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
 
 __global__ void bn_eval_affine_kernel(int c, const float* gamma, const float* beta, const float* rm, const float* rv,
                                       float eps, float* scale, float* shift) {
+  pdl_wait();
+  pdl_trigger();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const float sc = gamma[ch] / sqrtf(rv[ch] + eps);
@@ -150,6 +156,8 @@ __global__ void __launch_bounds__(512)
 bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ldy, long long pixels, int c8, int cv,
               const float* __restrict__ scale, const float* __restrict__ shift,
               const __nv_bfloat16* __restrict__ res, int ldr, __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_wait();
+  pdl_trigger();
   const int vl = threadIdx.x % cv, pl = threadIdx.x / cv, ppi = blockDim.x / cv;
   const int v = blockIdx.y * cv + vl;
   if (v >= c8) return;
@@ -202,6 +210,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __n
                      long long pixels, int c8, int cv, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ mean,
                      const float* __restrict__ invstd, float* __restrict__ partial, int c) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float red[];   // [blockDim.x][17]
   const int t = threadIdx.x;
   const int vl = t % cv, pl = t / cv, ppi = blockDim.x / cv;
@@ -268,6 +278,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ro
                                        double count, int c, float* dgamma, float* dbeta, int accumulate,
                                        const double* __restrict__ local_sums, float* __restrict__ coef,
                                        double* __restrict__ sums_out) {
+  pdl_wait();
+  pdl_trigger();
   const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (ch >= c) return;
@@ -311,6 +323,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv
                     const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ coef,
                     __nv_bfloat16* __restrict__ dy, int lddy) {
+  pdl_wait();
+  pdl_trigger();
   const int vl = threadIdx.x % cv, pl = threadIdx.x / cv, ppi = blockDim.x / cv;
   const int v = blockIdx.y * cv + vl;
   if (v >= c8) return;
@@ -361,10 +375,192 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BatchNorm(+ReLU) backward in ONE cooperative launch: stage 1 (partial sums) -> grid barrier over the blocks of a
+// channel chunk -> every block finalises its chunk's (mean dz, mean dz*xhat) from the partial rows (fp64, fixed order)
+// -> stage 3 (apply).  Saves two launches per layer and the second pass finds dout / y in L2 for mid-sized layers.
+// sync[2 * chunk + {0,1}]: zero-initialised arrive / depart counters, left zero again (self-cleaning).
+// ---------------------------------------------------------------------------------------------
+template <bool RELU>
+__global__ void __launch_bounds__(512)
+bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ y, int ldy,
+                    long long pixels, int c8, int cv, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, float* __restrict__ partial, int c, double count,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                    unsigned int* __restrict__ sync, __nv_bfloat16* __restrict__ dy, int lddy) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float red[];   // stage 1: [blockDim.x][17] floats; stage 2: doubles [G][pairs][4] then coef [cv*8][2]
+  const int t = threadIdx.x;
+  const int vl = t % cv, pl = t / cv, ppi = blockDim.x / cv;
+  const int v = blockIdx.y * cv + vl;
+  const bool active = v < c8;
+  const int ch = v * 8;
+  const long long step = (long long)gridDim.x * ppi;
+  float sc[8], sh[8], mu[8], is[8];
+  if (active) {
+    load8f(scale + ch, sc);
+    load8f(shift + ch, sh);
+    load8f(mean + ch, mu);
+    load8f(invstd + ch, is);
+  }
+  // ---------------- stage 1
+  {
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (active) {
+      for (long long pix = (long long)blockIdx.x * ppi + pl; pix < pixels; pix += step * kEwUnroll) {
+        uint4 gv[kEwUnroll], yv[kEwUnroll];
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+          const long long q = pix + u * step;
+          if (q < pixels) {
+            gv[u] = __ldg(reinterpret_cast<const uint4*>(dout + q * lddo + ch));
+            yv[u] = __ldg(reinterpret_cast<const uint4*>(y + q * ldy + ch));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+          const long long q = pix + u * step;
+          if (q < pixels) {
+            float g[8], yy[8];
+            unpack8(gv[u], g);
+            unpack8(yv[u], yy);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float z = fmaf(yy[j], sc[j], sh[j]);
+              const float dz = (!RELU || z > 0.f) ? g[j] : 0.f;
+              s1[j] += dz;
+              s2[j] = fmaf(dz, (yy[j] - mu[j]) * is[j], s2[j]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[t * 17 + j] = s1[j];
+      red[t * 17 + 8 + j] = s2[j];
+    }
+    __syncthreads();
+    for (int o = t; o < cv * 16; o += blockDim.x) {
+      const int vl2 = o / 16, j = o % 16;
+      const int vg = blockIdx.y * cv + vl2;
+      if (vg >= c8) continue;
+      float acc = 0.f;
+      for (int q = 0; q < ppi; ++q) acc += red[(q * cv + vl2) * 17 + j];
+      partial[((size_t)blockIdx.x * c + vg * 8 + (j & 7)) * 2 + (j >> 3)] = acc;
+    }
+  }
+  // ---------------- barrier over the gridDim.x blocks of this channel chunk
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    unsigned int* arrive = sync + 2 * blockIdx.y;
+    atomicAdd(arrive, 1u);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned int*>(arrive) < gridDim.x) {
+      if (clock64() - t0 > 4000000000LL) __trap();   // co-residency is guaranteed by the cooperative launch
+    }
+    __threadfence();
+    if (atomicAdd(arrive + 1, 1u) == gridDim.x - 1) {   // last block out: nobody spins any more
+      arrive[0] = 0u;
+      arrive[1] = 0u;
+    }
+  }
+  __syncthreads();
+  // ---------------- stage 2: this chunk's sums, every block redundantly (thread = channel pair x row group)
+  {
+    const int chans = min(cv * 8, c - blockIdx.y * cv * 8);
+    const int pairs = chans / 2;
+    const int G = max(1, (int)blockDim.x / pairs);
+    const int pr = t % pairs, g = t / pairs;
+    double* dsum = reinterpret_cast<double*>(red);     // [G][pairs][4]
+    float* cf = reinterpret_cast<float*>(dsum + (size_t)G * pairs * 4);   // [chans][2]
+    if (g < G) {
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const float* src = partial + ((size_t)blockIdx.y * cv * 8 + pr * 2) * 2;
+      const int R = (int)gridDim.x;
+      for (int r = g; r < R; r += 8 * G) {   // 8 independent loads in flight per thread
+        float4 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rr = r + u * G;
+          q[u] = (rr < R) ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)rr * c * 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a0 += q[u].x; a1 += q[u].y; a2 += q[u].z; a3 += q[u].w; }
+      }
+      double* d = dsum + ((size_t)g * pairs + pr) * 4;
+      d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
+    }
+    __syncthreads();
+    if (t < pairs) {
+      double a[4] = {0, 0, 0, 0};
+      for (int gg = 0; gg < G; ++gg) {
+        const double* d = dsum + ((size_t)gg * pairs + t) * 4;
+        a[0] += d[0]; a[1] += d[1]; a[2] += d[2]; a[3] += d[3];
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int lc = t * 2 + h;
+        const int gc = blockIdx.y * cv * 8 + lc;
+        const double s = a[2 * h], q = a[2 * h + 1];
+        cf[lc * 2] = (float)(s / count);
+        cf[lc * 2 + 1] = (float)(q / count);
+        if (blockIdx.x == 0) {
+          if (dgamma) dgamma[gc] = accumulate ? dgamma[gc] + (float)q : (float)q;
+          if (dbeta) dbeta[gc] = accumulate ? dbeta[gc] + (float)s : (float)s;
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- stage 3: dy = sc*dz - k0 - k1*(y - mu)
+    if (!active) return;
+    float k0[8], k1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      k0[j] = sc[j] * cf[(vl * 8 + j) * 2];
+      k1[j] = sc[j] * is[j] * cf[(vl * 8 + j) * 2 + 1];
+    }
+    for (long long pix = (long long)blockIdx.x * ppi + pl; pix < pixels; pix += step * kEwUnroll) {
+      uint4 gv[kEwUnroll], yv[kEwUnroll];
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) {
+        const long long q = pix + u * step;
+        if (q < pixels) {
+          gv[u] = __ldg(reinterpret_cast<const uint4*>(dout + q * lddo + ch));
+          yv[u] = __ldg(reinterpret_cast<const uint4*>(y + q * ldy + ch));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) {
+        const long long q = pix + u * step;
+        if (q < pixels) {
+          float g[8], yy[8], o[8];
+          unpack8(gv[u], g);
+          unpack8(yv[u], yy);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(yy[j], sc[j], sh[j]);
+            const float dz = (!RELU || z > 0.f) ? g[j] : 0.f;
+            o[j] = fmaf(sc[j], dz, -k0[j]) - k1[j] * (yy[j] - mu[j]);
+          }
+          *reinterpret_cast<uint4*>(dy + q * lddy + ch) = pack8(o);
+        }
+      }
+    }
+  }
+}
+
 // dst (+)= src   (bf16 views; fan-out copies / fan-in adds of activation gradients)
 template <bool ADD>
 __global__ void grad_add_kernel(__nv_bfloat16* __restrict__ dst, int ldd, const __nv_bfloat16* __restrict__ src,
                                 int lds, long long pixels, int c8) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = pixels * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / c8;
@@ -385,6 +581,8 @@ __global__ void grad_add_kernel(__nv_bfloat16* __restrict__ dst, int ldd, const 
 // NCHW fp32 image -> NHWC bf16 with channels zero-padded to cpad (multiple of 8)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, long long hw,
                                     __nv_bfloat16* __restrict__ out, int cpad) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)n * hw;
   const int v8 = cpad / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -416,7 +614,7 @@ int vtb_bn_bwd_rows(long long pixels, int c) {
 
 int vtb_bn_stats_reduce(const float* partial, int rows, int c, double* sums, void* stream) {
   if (!partial || !sums || rows <= 0 || c <= 0) return fail(VTB_EINVAL, "vtb_bn_stats_reduce: bad arguments");
-  bn_stats_reduce_kernel<<<(c * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, rows, c, sums);
+  launch_pdl(bn_stats_reduce_kernel, dim3((c * 32 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, partial, rows, c, sums);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "bn_stats_reduce_kernel");
 }
@@ -428,7 +626,7 @@ int vtb_bn_finalize(const float* partial, int rows, const double* sums, double c
   if ((partial == nullptr) == (sums == nullptr) || c <= 0 || count <= 0 || !gamma || !beta || !mean || !invstd ||
       !scale || !shift || (partial && rows <= 0) || ((running_mean == nullptr) != (running_var == nullptr)))
     return fail(VTB_EINVAL, "vtb_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(c * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(bn_finalize_kernel, dim3((c * 32 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, 
       partial, rows, sums, count, c, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, mean,
       invstd, scale, shift);
   count_launch(1);
@@ -439,7 +637,7 @@ int vtb_bn_eval_affine(int c, const float* gamma, const float* beta, const float
                        const float* running_var, float eps, float* scale, float* shift, void* stream) {
   if (c <= 0 || !gamma || !beta || !running_mean || !running_var || !scale || !shift)
     return fail(VTB_EINVAL, "vtb_bn_eval_affine: bad arguments");
-  bn_eval_affine_kernel<<<(c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c, gamma, beta, running_mean, running_var,
+  launch_pdl(bn_eval_affine_kernel, dim3((c + 255) / 256), dim3(256), 0, (cudaStream_t)stream, c, gamma, beta, running_mean, running_var,
                                                                            eps, scale, shift);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "bn_eval_affine_kernel");
@@ -458,10 +656,10 @@ int vtb_bn_act(const void* y, int ldy, long long pixels, int c, const float* sca
   const __nv_bfloat16* rr = (const __nv_bfloat16*)residual;
   __nv_bfloat16* oo = (__nv_bfloat16*)out;
   cudaStream_t st = (cudaStream_t)stream;
-  if (relu && rr) bn_act_kernel<true, true><<<grid, bs, 0, st>>>(yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
-  else if (relu) bn_act_kernel<true, false><<<grid, bs, 0, st>>>(yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
-  else if (rr) bn_act_kernel<false, true><<<grid, bs, 0, st>>>(yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
-  else bn_act_kernel<false, false><<<grid, bs, 0, st>>>(yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
+  if (relu && rr) launch_pdl(bn_act_kernel<true, true>, dim3(grid), dim3(bs), 0, st, yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
+  else if (relu) launch_pdl(bn_act_kernel<true, false>, dim3(grid), dim3(bs), 0, st, yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
+  else if (rr) launch_pdl(bn_act_kernel<false, true>, dim3(grid), dim3(bs), 0, st, yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
+  else launch_pdl(bn_act_kernel<false, false>, dim3(grid), dim3(bs), 0, st, yy, ldy, pixels, c8, g.cv, scale, shift, rr, ldr, oo, ldo);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "bn_act_kernel");
 }
@@ -479,10 +677,10 @@ int vtb_bn_bwd_reduce(const void* dout, int lddo, const void* y, int ldy, long l
   const size_t sm = (size_t)bs * 17 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (relu)
-    bn_bwd_reduce_kernel<true><<<grid, bs, sm, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+    launch_pdl(bn_bwd_reduce_kernel<true>, dim3(grid), dim3(bs), sm, st, (const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
                                                      pixels, c8, g.cv, scale, shift, mean, invstd, partial, c);
   else
-    bn_bwd_reduce_kernel<false><<<grid, bs, sm, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+    launch_pdl(bn_bwd_reduce_kernel<false>, dim3(grid), dim3(bs), sm, st, (const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
                                                       pixels, c8, g.cv, scale, shift, mean, invstd, partial, c);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "bn_bwd_reduce_kernel");
@@ -494,7 +692,7 @@ int vtb_bn_bwd_finalize(const float* partial, int rows, const double* sums, cons
   if ((partial == nullptr) == (sums == nullptr) || c <= 0 || count <= 0 || (!coef && !sums_out) ||
       (partial && rows <= 0))
     return fail(VTB_EINVAL, "vtb_bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<(c * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(bn_bwd_finalize_kernel, dim3((c * 32 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, 
       partial, rows, sums, count, c, dgamma, dbeta, accumulate, local_sums, coef, sums_out);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "bn_bwd_finalize_kernel");
@@ -512,15 +710,64 @@ int vtb_bn_bwd_apply(const void* dout, int lddo, const void* y, int ldy, long lo
   const int bs = g.ppi * g.cv;
   cudaStream_t st = (cudaStream_t)stream;
   if (relu)
-    bn_bwd_apply_kernel<true><<<grid, bs, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+    launch_pdl(bn_bwd_apply_kernel<true>, dim3(grid), dim3(bs), 0, st, (const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
                                                    pixels, c8, g.cv, scale, shift, mean, invstd, coef,
                                                    (__nv_bfloat16*)dy, lddy);
   else
-    bn_bwd_apply_kernel<false><<<grid, bs, 0, st>>>((const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
+    launch_pdl(bn_bwd_apply_kernel<false>, dim3(grid), dim3(bs), 0, st, (const __nv_bfloat16*)dout, lddo, (const __nv_bfloat16*)y, ldy,
                                                     pixels, c8, g.cv, scale, shift, mean, invstd, coef,
                                                     (__nv_bfloat16*)dy, lddy);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "bn_bwd_apply_kernel");
+}
+
+// geometry of the fused backward: all blocks must be co-resident (cooperative launch), one 512-thread block per SM
+static EwGeom bwd_fused_geom(long long pixels, int c8) {
+  EwGeom g = ew_geom(pixels, c8, 512, 1);
+  // stage 2 reads gridDim.x rows per channel pair with blockDim / pairs row groups: keep that <= ~40 loads per thread
+  const int pairs = g.cv * 4;
+  const int G = std::max(1, (g.ppi * g.cv) / pairs);
+  g.rows = std::max(1, std::min(g.rows, 40 * G));
+  return g;
+}
+
+int vtb_bn_bwd_fused_rows(long long pixels, int c) {
+  if (pixels <= 0 || c <= 0 || c % 16) return fail(VTB_EINVAL, "vtb_bn_bwd_fused_rows: bad arguments");
+  return bwd_fused_geom(pixels, c / 8).rows;
+}
+
+int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long long pixels, int c, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, int relu, double count,
+                     float* partial, float* dgamma, float* dbeta, int accumulate, unsigned int* sync, void* dy,
+                     int lddy, void* stream) {
+  if (pixels <= 0 || c <= 0 || c % 16 || !VIEW_OK(dout, lddo, c) || !VIEW_OK(y, ldy, c) || !VIEW_OK(dy, lddy, c) ||
+      !scale || !shift || !mean || !invstd || !partial || !sync || count <= 0)
+    return fail(VTB_EINVAL, "vtb_bn_bwd_fused: bad arguments");
+  int c8 = c / 8;
+  const EwGeom g = bwd_fused_geom(pixels, c8);
+  if (g.chunks > 64) return fail(VTB_EINVAL, "vtb_bn_bwd_fused: too many channels");
+  int cv = g.cv;
+  const dim3 grid(g.rows, g.chunks);
+  const dim3 block(g.ppi * g.cv);
+  const int chans = g.cv * 8, pairs = chans / 2, G = std::max(1, (int)block.x / pairs);
+  const size_t sm = std::max<size_t>((size_t)block.x * 17 * sizeof(float),
+                                     (size_t)G * pairs * 4 * sizeof(double) + (size_t)chans * 2 * sizeof(float));
+  const void* fn = relu ? (const void*)bn_bwd_fused_kernel<true> : (const void*)bn_bwd_fused_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[relu ? 1 : 0]) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return check_cuda((int)e, "bn_bwd_fused_kernel attribute");
+    attr_set[relu ? 1 : 0] = true;
+  }
+  if (sm > 96 * 1024) return fail(VTB_EINVAL, "vtb_bn_bwd_fused: shared memory");
+  const __nv_bfloat16* dout_p = (const __nv_bfloat16*)dout;
+  const __nv_bfloat16* y_p = (const __nv_bfloat16*)y;
+  __nv_bfloat16* dy_p = (__nv_bfloat16*)dy;
+  void* args[] = {&dout_p, &lddo, &y_p, &ldy, &pixels, &c8, &cv, &scale, &shift, &mean, &invstd, &partial, &c, &count,
+                  &dgamma, &dbeta, &accumulate, &sync, &dy_p, &lddy};
+  count_launch(1);
+  return check_cuda((int)cudaLaunchCooperativeKernel(fn, grid, block, args, sm, (cudaStream_t)stream),
+                    "bn_bwd_fused_kernel");
 }
 
 int vtb_grad_add(void* dst, int ldd, const void* src, int lds, long long pixels, int c, int accumulate, void* stream) {
@@ -529,10 +776,10 @@ int vtb_grad_add(void* dst, int ldd, const void* src, int lds, long long pixels,
   const int c8 = c / 8;
   const int grid = ew_grid(pixels * c8, 256);
   if (accumulate)
-    grad_add_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dst, ldd, (const __nv_bfloat16*)src,
+    launch_pdl(grad_add_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (__nv_bfloat16*)dst, ldd, (const __nv_bfloat16*)src,
                                                                   lds, pixels, c8);
   else
-    grad_add_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dst, ldd, (const __nv_bfloat16*)src,
+    launch_pdl(grad_add_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (__nv_bfloat16*)dst, ldd, (const __nv_bfloat16*)src,
                                                                    lds, pixels, c8);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "grad_add_kernel");
@@ -542,7 +789,7 @@ int vtb_nchw_to_nhwc(const float* x, int n, int c, int h, int w, void* out, int 
   if (!x || !out || n <= 0 || c <= 0 || h <= 0 || w <= 0 || cpad < c || cpad % 8)
     return fail(VTB_EINVAL, "vtb_nchw_to_nhwc: bad arguments");
   const long long total = (long long)n * h * w;
-  nchw_to_nhwc_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(x, n, c, (long long)h * w,
+  launch_pdl(nchw_to_nhwc_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, n, c, (long long)h * w,
                                                                              (__nv_bfloat16*)out, cpad);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "nchw_to_nhwc_kernel");

@@ -4,6 +4,7 @@
 // (one lane), warps 2..5 = epilogue (TMEM -> registers -> smem/global).  Operands are staged in shared
 // memory by TMA (im2col mode for the activation operand, so a tile of 128 consecutive output pixels may
 // cross row and image boundaries and padding is zero-filled by hardware), accumulators live in TMEM.
+#include "common.cuh"
 #include "igemm.cuh"
 #include "ptx.cuh"
 
@@ -209,6 +210,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(tempty_bar(a), kEpiWarps);   // one arrival per epilogue warp
     }
     fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemCols);
@@ -219,6 +222,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_trigger();
 
   if (warp == 0 || warp == 3) {
     // ======================= A producers =======================
@@ -226,7 +231,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // UTMALDG / UTCHMMA with uniform-register operands instead of a per-instruction divergence ("waterfall") loop
     if (elect_one()) {
       const uint32_t who = (warp == 0) ? 0u : 1u;
-      tma_prefetch_desc(&tmA);
       uint32_t stage = 0, phase = 0, g = 0;
       long long waited = 0;
       for (int m_blk = m_first; m_blk < num_m_blocks; m_blk += m_step) {
@@ -263,7 +267,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 2) {
     // ======================= B producer =======================
     if (elect_one()) {
-      tma_prefetch_desc(&tmB);
       uint32_t stage = 0, phase = 0;
       long long waited = 0;
       for (int m_blk = m_first; m_blk < num_m_blocks; m_blk += m_step) {
@@ -545,7 +548,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         *reinterpret_cast<float2*>(rowp + (size_t)(n0 + et) * 2) = make_float2(sx, sq);
       }
       if (p.tickets != nullptr) {
-        __threadfence();
+        if (et < p.block_n) __threadfence();
         named_bar_sync(1, kEpiWarps * 32);
         uint32_t* flag = reinterpret_cast<uint32_t*>(slots);
         if (et == 0) {
@@ -563,10 +566,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           double* dsl = reinterpret_cast<double*>(slots);   // [G][block_n][2]
           if (g < G) {
             double sx = 0.0, sq = 0.0;
-            for (int r = g; r < m_step; r += G) {
-              const float2 v = __ldcg(reinterpret_cast<const float2*>(p.stats_partial + ((size_t)r * p.cout + n0 + col) * 2));
-              sx += (double)v.x;
-              sq += (double)v.y;
+            const float* src = p.stats_partial + (size_t)(n0 + col) * 2;
+            const size_t rstride = (size_t)p.cout * 2;
+            // 8 independent loads in flight per thread (a dependent add right behind each load would serialise them)
+            for (int r = g; r < m_step; r += 8 * G) {
+              float2 v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int rr = r + u * G;
+                v[u] = (rr < m_step) ? __ldcg(reinterpret_cast<const float2*>(src + (size_t)rr * rstride)) : make_float2(0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                sx += (double)v[u].x;
+                sq += (double)v[u].y;
+              }
             }
             dsl[(g * p.block_n + col) * 2] = sx;
             dsl[(g * p.block_n + col) * 2 + 1] = sq;
@@ -732,6 +746,8 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
   }
   if (warp == kWgProducers) {
     tmem_alloc(tmem_slot, kTmemCols);
@@ -742,12 +758,12 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
+  pdl_trigger();
 
   if (warp < kWgProducers) {
     // ======================= TMA producers =======================
     if (elect_one()) {
-      tma_prefetch_desc(&tmDY);
-      tma_prefetch_desc(&tmX);
       uint32_t stage = 0, phase = 0;
       uint32_t g = 0;  // running request counter at the start of the stage (same value in every producer)
       long long waited = 0;
@@ -887,8 +903,7 @@ static int launch_conv_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, c
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  conv_igemm_kernel<TIMED, EPI><<<grid, kConvThreads, smem, stream>>>(tmA, tmB, tmD, p);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(conv_igemm_kernel<TIMED, EPI>, dim3(grid), dim3(kConvThreads), smem, stream, tmA, tmB, tmD, p);
 }
 
 int launch_conv_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
@@ -927,9 +942,9 @@ int launch_wgrad_igemm(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wg
     attr_set = true;
   }
   const size_t smem = wgrad_igemm_smem_bytes(p.ma, p.n_cols, p.kpix, p.num_stages);
-  if (p.dbg != nullptr) wgrad_igemm_kernel<true><<<dim3(grid_x, p.splits), kWgThreads, smem, stream>>>(tmDY, tmX, p);
-  else wgrad_igemm_kernel<false><<<dim3(grid_x, p.splits), kWgThreads, smem, stream>>>(tmDY, tmX, p);
-  return (int)cudaGetLastError();
+  if (p.dbg != nullptr)
+    return (int)launch_pdl(wgrad_igemm_kernel<true>, dim3(grid_x, p.splits), dim3(kWgThreads), smem, stream, tmDY, tmX, p);
+  return (int)launch_pdl(wgrad_igemm_kernel<false>, dim3(grid_x, p.splits), dim3(kWgThreads), smem, stream, tmDY, tmX, p);
 }
 
 }  // namespace vtb

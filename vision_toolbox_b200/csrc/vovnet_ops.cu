@@ -36,6 +36,8 @@ static int vgrid(long long work, int block) {
 // ------------------------------------------------------------------ MaxPool2d(k=3, s=2, p=1)
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int c8, int ho,
                                    int wo, __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)n * ho * wo * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % c8);
@@ -69,6 +71,8 @@ template <bool ADD>
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int c8, int ho,
                                    int wo, const __nv_bfloat16* __restrict__ dout, int lddo,
                                    __nv_bfloat16* __restrict__ dx, int lddx) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)n * h * w * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % c8);
@@ -127,6 +131,8 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
 template <bool PRODUCT>
 __global__ void hw_reduce_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b,
                                  int ldb, int hw, int c8, float* __restrict__ out, int c, float mul) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8][32][9];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int v = blockIdx.x * 32 + tx;
@@ -167,6 +173,8 @@ __global__ void hw_reduce_kernel(const __nv_bfloat16* __restrict__ a, int lda, c
 __global__ void ese_fc_fwd_kernel(const float* __restrict__ pool, const float* __restrict__ W,
                                   const float* __restrict__ bias, int n, int c, float* __restrict__ z,
                                   float* __restrict__ gate) {
+  pdl_wait();
+  pdl_trigger();
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= (long long)n * c) return;
@@ -186,6 +194,8 @@ template <bool RES>
 __global__ void ese_scale_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gate, int hw,
                                  long long pixels, int c8, const __nv_bfloat16* __restrict__ res, int ldr,
                                  __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = pixels * c8;
   const int c = c8 * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -212,6 +222,8 @@ __global__ void ese_scale_kernel(const __nv_bfloat16* __restrict__ x, int ldx, c
 // dz[n][co] = dgate * hardsigmoid'(z)
 __global__ void ese_dz_kernel(const float* __restrict__ dgate, const float* __restrict__ z, long long total,
                               float* __restrict__ dz) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
   const float t = z[i] * (1.f / 6.f) + 0.5f;
@@ -220,6 +232,8 @@ __global__ void ese_dz_kernel(const float* __restrict__ dgate, const float* __re
 // dpool[n][ci] = sum_co dz[n][co] * bf16(W[co][ci]) ; scaled by 1/hw for the mean
 __global__ void ese_dpool_kernel(const float* __restrict__ dz, const float* __restrict__ W, int n, int c, float inv_hw,
                                  float* __restrict__ dpool) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)n * c) return;
   const int img = (int)(i / c), ci = (int)(i % c);
@@ -230,6 +244,8 @@ __global__ void ese_dpool_kernel(const float* __restrict__ dz, const float* __re
 // dW[co][ci] (+)= sum_n dz[n][co]*bf16(pool[n][ci]); db[co] (+)= sum_n dz[n][co]
 __global__ void ese_dw_kernel(const float* __restrict__ dz, const float* __restrict__ pool, int n, int c,
                               float* __restrict__ dW, float* __restrict__ db, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)c * c) return;
   const int co = (int)(i / c), ci = (int)(i % c);
@@ -247,6 +263,8 @@ template <bool ADD>
 __global__ void ese_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const float* __restrict__ gate,
                                   const float* __restrict__ dpool, int hw, long long pixels, int c8,
                                   __nv_bfloat16* __restrict__ dx, int lddx) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = pixels * c8;
   const int c = c8 * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -280,7 +298,7 @@ int vtb_maxpool3s2_fwd(const void* x, int ldx, int n, int h, int w, int c, void*
     return fail(VTB_EINVAL, "vtb_maxpool3s2_fwd: bad arguments");
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
-  maxpool_fwd_kernel<<<vgrid(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, n, h, w, c / 8,
+  launch_pdl(maxpool_fwd_kernel, dim3(vgrid(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8,
                                                                           ho, wo, (__nv_bfloat16*)out, ldo);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "maxpool_fwd_kernel");
@@ -294,10 +312,10 @@ int vtb_maxpool3s2_bwd(const void* x, int ldx, int n, int h, int w, int c, const
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   const long long total = (long long)n * h * w * (c / 8);
   if (accumulate)
-    maxpool_bwd_kernel<true><<<vgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(maxpool_bwd_kernel<true>, dim3(vgrid(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, ho, wo, (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx);
   else
-    maxpool_bwd_kernel<false><<<vgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(maxpool_bwd_kernel<false>, dim3(vgrid(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, ho, wo, (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "maxpool_bwd_kernel");
@@ -310,17 +328,17 @@ int vtb_ese_fwd(const void* x, int ldx, int n, int hw, int c, const float* weigh
     return fail(VTB_EINVAL, "vtb_ese_fwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const int c8 = c / 8;
-  hw_reduce_kernel<false><<<dim3((c8 + 31) / 32, n), 256, 0, st>>>((const __nv_bfloat16*)x, ldx, nullptr, 0, hw, c8,
+  launch_pdl(hw_reduce_kernel<false>, dim3(dim3((c8 + 31) / 32, n)), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, nullptr, 0, hw, c8,
                                                                    pool, c, 1.f / hw);
   const long long warps = (long long)n * c;
-  ese_fc_fwd_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(pool, weight, bias, n, c, z, gate);
+  launch_pdl(ese_fc_fwd_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st, pool, weight, bias, n, c, z, gate);
   const long long pixels = (long long)n * hw;
   if (residual)
-    ese_scale_kernel<true><<<vgrid(pixels * c8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, ldx, gate, hw, pixels, c8,
+    launch_pdl(ese_scale_kernel<true>, dim3(vgrid(pixels * c8, 256)), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, gate, hw, pixels, c8,
                                                                     (const __nv_bfloat16*)residual, ldr,
                                                                     (__nv_bfloat16*)out, ldo);
   else
-    ese_scale_kernel<false><<<vgrid(pixels * c8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, ldx, gate, hw, pixels, c8,
+    launch_pdl(ese_scale_kernel<false>, dim3(vgrid(pixels * c8, 256)), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, gate, hw, pixels, c8,
                                                                      nullptr, 0, (__nv_bfloat16*)out, ldo);
   count_launch(3);
   return check_cuda((int)cudaGetLastError(), "ese forward kernels");
@@ -338,18 +356,18 @@ int vtb_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weigh
   float* dgate = scratch;          // [n][c]
   float* dz = scratch + nc;        // [n][c]
   float* dpool = scratch + 2 * nc; // [n][c]
-  hw_reduce_kernel<true><<<dim3((c8 + 31) / 32, n), 256, 0, st>>>((const __nv_bfloat16*)dout, lddo,
+  launch_pdl(hw_reduce_kernel<true>, dim3(dim3((c8 + 31) / 32, n)), dim3(256), 0, st, (const __nv_bfloat16*)dout, lddo,
                                                                   (const __nv_bfloat16*)x, ldx, hw, c8, dgate, c, 1.f);
-  ese_dz_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(dgate, z, nc, dz);
-  ese_dpool_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(dz, weight, n, c, 1.f / hw, dpool);
-  ese_dw_kernel<<<(unsigned)(((long long)c * c + 255) / 256), 256, 0, st>>>(dz, pool, n, c, dweight, dbias,
+  launch_pdl(ese_dz_kernel, dim3((unsigned)((nc + 255) / 256)), dim3(256), 0, st, dgate, z, nc, dz);
+  launch_pdl(ese_dpool_kernel, dim3((unsigned)((nc + 255) / 256)), dim3(256), 0, st, dz, weight, n, c, 1.f / hw, dpool);
+  launch_pdl(ese_dw_kernel, dim3((unsigned)(((long long)c * c + 255) / 256)), dim3(256), 0, st, dz, pool, n, c, dweight, dbias,
                                                                             accumulate_dw);
   const long long pixels = (long long)n * hw;
   if (accumulate_dx)
-    ese_bwd_dx_kernel<true><<<vgrid(pixels * c8, 256), 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, gate, dpool, hw,
+    launch_pdl(ese_bwd_dx_kernel<true>, dim3(vgrid(pixels * c8, 256)), dim3(256), 0, st, (const __nv_bfloat16*)dout, lddo, gate, dpool, hw,
                                                                      pixels, c8, (__nv_bfloat16*)dx, lddx);
   else
-    ese_bwd_dx_kernel<false><<<vgrid(pixels * c8, 256), 256, 0, st>>>((const __nv_bfloat16*)dout, lddo, gate, dpool, hw,
+    launch_pdl(ese_bwd_dx_kernel<false>, dim3(vgrid(pixels * c8, 256)), dim3(256), 0, st, (const __nv_bfloat16*)dout, lddo, gate, dpool, hw,
                                                                       pixels, c8, (__nv_bfloat16*)dx, lddx);
   count_launch(5);
   return check_cuda((int)cudaGetLastError(), "ese backward kernels");

@@ -195,7 +195,7 @@ class Graph:
         rows_f = L.vtb_conv_stats_rows(C.byref(geom))
         if rows_f <= 0:
             check(-1, "vtb_conv_stats_rows")
-        rows_b = L.vtb_bn_bwd_rows(out.pixels, cout)
+        rows_b = max(L.vtb_bn_bwd_rows(out.pixels, cout), L.vtb_bn_bwd_fused_rows(out.pixels, cout))
         for name in ("mean", "invstd", "scale", "shift"):
             self._stat(op, name, cout)
         self._stat(op, "partial_f", rows_f * cout * 2)
@@ -303,7 +303,7 @@ class Runner:
         self.dist: Optional[DistConfig] = None
         self.grad_sink = False
         # ticket counters of the fused conv + BatchNorm-finalize kernels (self-cleaning, shared by all layers)
-        self.tickets = torch.zeros(256, dtype=torch.int32, device=device)
+        self.tickets = torch.zeros(512, dtype=torch.int32, device=device)   # [0,256): conv tickets, [256,512): BN bwd
 
     # -- helpers
     def _stream(self) -> int:
@@ -555,6 +555,14 @@ class Runner:
         x, y, out, res = op.x, op.y, op.out, op.residual
         f = lambda name: sbase + 4 * op.st[name]
         dout_p, dout_ld = gp(out), gld(out)
+        if g.training and world == 1:
+            # reduce -> finalize -> apply in one cooperative launch
+            check(L.vtb_bn_bwd_fused(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
+                                     f("shift"), f("mean"), f("invstd"), int(op.relu), float(out.pixels),
+                                     f("partial_b"), pgrads[op.pidx + 1].data_ptr(), pgrads[op.pidx + 2].data_ptr(), 0,
+                                     self.tickets.data_ptr() + 1024, dybase, cout, st), "vtb_bn_bwd_fused")
+            self._conv_backward_gemms(op, abase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st)
+            return
         check(L.vtb_bn_bwd_reduce(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
                                   f("shift"), f("mean"), f("invstd"), int(op.relu), f("partial_b"), st),
               "vtb_bn_bwd_reduce")
@@ -577,6 +585,13 @@ class Runner:
         check(L.vtb_bn_bwd_apply(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
                                  f("shift"), f("mean"), f("invstd"), int(op.relu), f("coef"), dybase, cout, st),
               "vtb_bn_bwd_apply")
+        self._conv_backward_gemms(op, abase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st)
+
+    def _conv_backward_gemms(self, op: ConvOp, abase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st):
+        L = self.L
+        geom, cout = op.geom, op.geom.cout
+        x, out, res = op.x, op.out, op.residual
+        dout_p, dout_ld = gp(out), gld(out)
         _, wd = self._packed(op, L, st)
         if not (x.is_input and not run.x_requires_grad):
             check(L.vtb_conv_dgrad(C.byref(geom), dybase, cout, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
