@@ -119,6 +119,30 @@ int vtb_bn_finalize(const float* partial, int rows, const double* sums, double c
 int vtb_bn_eval_affine(int c, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, void* stream);
 
+/* ---- SyncBatchNorm (configs/base.yaml:22 `sync_batchnorm: true` -> torch.nn.SyncBatchNorm's per-layer
+ * all_gather / all_reduce, torch/nn/modules/_functions.py:39-170) as ONE kernel per exchange over NVLink peer memory.
+ * Every rank owns a zero-initialised buffer of vtb_bn_sync_buffer_bytes() that all peers have mapped
+ * (peer_buffers[r] = rank r's buffer as seen from THIS process, e.g. torch.distributed._symmetric_memory buffer_ptrs).
+ * The kernel reduces the local partial rows, pushes the fp64 sums to every peer, waits for all peers and finalises with
+ * the GLOBAL element count (`count` = sum over ranks of N*H*W).  All ranks must issue the same sequence of calls.
+ *  vtb_bn_sync_finalize     : forward, same outputs as vtb_bn_finalize.
+ *  vtb_bn_sync_bwd_finalize : backward, same outputs as vtb_bn_bwd_finalize (dgamma/dbeta from LOCAL sums, coef from
+ *                             global sums); local_scratch: 2*c doubles. */
+#define VTB_SYNC_MAX_RANKS 8
+#define VTB_SYNC_MAX_CHANNELS 2048
+typedef struct VtbSyncBn {
+  int rank, world;
+  void* peer_buffers[VTB_SYNC_MAX_RANKS];
+} VtbSyncBn;
+size_t vtb_bn_sync_buffer_bytes(void);
+int vtb_bn_sync_finalize(const float* partial, int rows, int c, const VtbSyncBn* sync, double count,
+                         const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                         float* running_var, long long* num_batches_tracked, float* mean, float* invstd, float* scale,
+                         float* shift, void* stream);
+int vtb_bn_sync_bwd_finalize(const float* partial, int rows, int c, const VtbSyncBn* sync, double count,
+                             float* dgamma, float* dbeta, int accumulate, float* coef, double* local_scratch,
+                             void* stream);
+
 /* out = [relu](y*scale + shift) [+ residual]: the BatchNorm normalise + nn.ReLU(inplace) of
  * components.py:36-39 and the post-activation residual add of darknet.py:28 / vovnet.py:60-61 in one pass.
  * `out` may be a channel slice of a concat buffer (replaces torch.cat, darknet.py:53 / vovnet.py:55). */

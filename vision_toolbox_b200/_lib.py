@@ -30,6 +30,12 @@ class VtbBnTrain(C.Structure):
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("tickets", C.c_void_p)]
 
 
+class VtbSyncBn(C.Structure):
+    """struct VtbSyncBn of include/vtb.h (peer-mapped SyncBN exchange buffers)."""
+
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("peer_buffers", C.c_void_p * 8)]
+
+
 _p = C.c_void_p
 _i = C.c_int
 _ll = C.c_longlong
@@ -54,6 +60,9 @@ SIGNATURES = {
     "vtb_bn_stats_reduce": (_i, [_p, _i, _i, _p, _p]),
     "vtb_bn_finalize": (_i, [_p, _i, _p, _d, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vtb_bn_eval_affine": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _p]),
+    "vtb_bn_sync_buffer_bytes": (C.c_size_t, []),
+    "vtb_bn_sync_finalize": (_i, [_p, _i, _i, C.POINTER(VtbSyncBn), _d, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vtb_bn_sync_bwd_finalize": (_i, [_p, _i, _i, C.POINTER(VtbSyncBn), _d, _p, _p, _i, _p, _p, _p]),
     "vtb_bn_act": (_i, [_p, _i, _ll, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
     "vtb_bn_bwd_rows": (_i, [_ll, _i]),
     "vtb_bn_bwd_reduce": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _p, _p]),

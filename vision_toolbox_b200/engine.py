@@ -195,13 +195,14 @@ class Graph:
         rows_f = L.vtb_conv_stats_rows(C.byref(geom))
         if rows_f <= 0:
             check(-1, "vtb_conv_stats_rows")
-        rows_b = max(L.vtb_bn_bwd_rows(out.pixels, cout), L.vtb_bn_bwd_fused_rows(out.pixels, cout))
+        rows_b = L.vtb_bn_bwd_rows(out.pixels, cout)            # rows written by vtb_bn_bwd_reduce
+        rows_b_alloc = max(rows_b, L.vtb_bn_bwd_fused_rows(out.pixels, cout))   # scratch also serves the fused kernel
         for name in ("mean", "invstd", "scale", "shift"):
             self._stat(op, name, cout)
         self._stat(op, "partial_f", rows_f * cout * 2)
         self._stat(op, "sums", cout * 4)  # double[c][2]
         if self.need_grad:
-            self._stat(op, "partial_b", rows_b * cout * 2)
+            self._stat(op, "partial_b", rows_b_alloc * cout * 2)
             self._stat(op, "coef", cout * 2)
             self._stat(op, "sums_b", cout * 4)
             self._stat(op, "lsums_b", cout * 4)
@@ -276,14 +277,59 @@ class Run:
 
 
 class DistConfig:
-    """Data-parallel hooks (vision_toolbox_b200.parallel fills this in)."""
+    """Data-parallel hooks (vision_toolbox_b200.parallel fills this in).
 
-    def __init__(self, group=None, sync_bn: bool = True):
+    SyncBN statistics travel either through the one-kernel NVLink peer-memory exchange (``vtb_bn_sync_*``; buffers from
+    ``torch.distributed._symmetric_memory``) or, when peer memory cannot be set up (``VTB_SYNCBN=nccl`` forces it),
+    through one NCCL all-reduce per exchange.
+    """
+
+    def __init__(self, group=None, sync_bn: bool = True, device: Optional[torch.device] = None):
+        import os
+
         import torch.distributed as dist
 
         self.group = group
         self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
         self.sync_bn = sync_bn and self.world > 1
+        self.sync = None          # _lib.VtbSyncBn when the peer-memory path is active
+        self.sync_error = None
+        self.on_grads_ready = None  # callable(list[Tensor]) : parameter gradients that are final (parallel.Trainer)
+        if (self.sync_bn and device is not None and device.type == "cuda"
+                and os.environ.get("VTB_SYNCBN", "p2p") == "p2p" and self.world <= 8):
+            try:
+                self._setup_peer_memory(device)
+            except Exception as e:  # noqa: BLE001 - any failure selects the NCCL exchange, loudly
+                self.sync_error = f"{type(e).__name__}: {e}"
+                if self.rank == 0:
+                    print(f"[vision_toolbox_b200] SyncBN peer-memory exchange unavailable ({self.sync_error}); "
+                          "using NCCL all-reduce per layer", flush=True)
+            # every rank must agree on the path
+            flag = torch.tensor([1 if self.sync is not None else 0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag) == 0:
+                self.sync = None
+
+    def _setup_peer_memory(self, device: torch.device) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        L = _lib.lib()
+        nbytes = int(L.vtb_bn_sync_buffer_bytes())
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)   # every buffer is zeroed before anyone pushes into it
+        sync = _lib.VtbSyncBn()
+        sync.rank, sync.world = int(hdl.rank), int(hdl.world_size)
+        ptrs = list(hdl.buffer_ptrs)
+        assert sync.world == self.world and len(ptrs) == self.world
+        for r, ptr in enumerate(ptrs):
+            sync.peer_buffers[r] = int(ptr)
+        self._symm_buf, self._symm_hdl = buf, hdl   # keep the mapping alive
+        self.sync = sync
 
     def all_reduce_(self, t: torch.Tensor) -> None:
         import torch.distributed as dist
@@ -411,8 +457,13 @@ class Runner:
             check(L.vtb_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(),
                                    abase + y.byte_offset(), y.ld, f("partial_f") if use_batch_stats else 0, 0, 0, 0, 0,
                                    0, st), "vtb_conv_fprop")
-        if use_batch_stats and world > 1:
-            # SyncBN: local sums -> cross-rank sum -> finalise with the GLOBAL element count
+        if use_batch_stats and world > 1 and self.dist.sync is not None:
+            # SyncBN: reduce + NVLink exchange + finalise (GLOBAL element count) in one kernel
+            check(L.vtb_bn_sync_finalize(f("partial_f"), op.rows_f, cout, C.byref(self.dist.sync), count * world,
+                                         norm.weight.data_ptr(), norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt,
+                                         f("mean"), f("invstd"), f("scale"), f("shift"), st), "vtb_bn_sync_finalize")
+        elif use_batch_stats and world > 1:
+            # SyncBN through NCCL: local sums -> cross-rank sum -> finalise with the GLOBAL element count
             check(L.vtb_bn_stats_reduce(f("partial_f"), op.rows_f, cout, f("sums"), st), "vtb_bn_stats_reduce")
             sums = run.stat_view_f64(op.st["sums"], cout * 2, sbase)
             self.dist.all_reduce_(sums)
@@ -492,6 +543,8 @@ class Runner:
             mark(t)
 
         pending: list[tuple[TView, TView]] = []
+        # gradient all-reduce overlap: only meaningful when gradients land directly in the caller's flat buffer
+        ready_cb = self.dist.on_grads_ready if (self.dist is not None and self.grad_sink and all(direct)) else None
 
         def flush_pending(force_for: Optional[TView]) -> None:
             for item in list(pending):
@@ -511,9 +564,13 @@ class Runner:
                     n_p = 3 if op.kind == "conv" else 2
                     for j in range(n_p):
                         pgrads[op.pidx + j].zero_()
+                    if ready_cb is not None:
+                        ready_cb(g.params[op.pidx : op.pidx + n_p])
                 continue
             if op.kind == "conv":
                 self._conv_backward(op, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world)
+                if ready_cb is not None:
+                    ready_cb(g.params[op.pidx : op.pidx + 3])
             elif op.kind == "pool":
                 xx, oo = op.x, op.out
                 if not (xx.is_input and not run.x_requires_grad):
@@ -529,6 +586,8 @@ class Runner:
                                     pgrads[op.pidx].data_ptr(), pgrads[op.pidx + 1].data_ptr(), 0,
                                     sbase + 4 * op.st["scratch"], st), "vtb_ese_bwd")
                 mark(xx)
+                if ready_cb is not None:
+                    ready_cb(g.params[op.pidx : op.pidx + 2])
                 if rr is not None and gview(rr) is not gview(oo):
                     # `rr` may be slice 0 of a concat buffer whose gradient is about to be (over)written as a whole
                     # by out_conv's dgrad: defer the identity contribution until that memory is initialised
@@ -568,7 +627,11 @@ class Runner:
               "vtb_bn_bwd_reduce")
         dgamma, dbeta = pgrads[op.pidx + 1].data_ptr(), pgrads[op.pidx + 2].data_ptr()
         count = float(out.pixels)
-        if g.training and world > 1:
+        if g.training and world > 1 and self.dist.sync is not None:
+            check(L.vtb_bn_sync_bwd_finalize(f("partial_b"), op.rows_b, cout,
+                                             C.byref(self.dist.sync), count * world, dgamma, dbeta, 0, f("coef"),
+                                             f("lsums_b"), st), "vtb_bn_sync_bwd_finalize")
+        elif g.training and world > 1:
             check(L.vtb_bn_bwd_finalize(f("partial_b"), op.rows_b, 0, 0, count, cout, 0, 0, 0, 0, f("lsums_b"), st),
                   "vtb_bn_bwd_finalize(local)")
             sums = run.stat_view_f64(op.st["sums_b"], cout * 2, sbase)

@@ -46,6 +46,14 @@ def bucket_ranges(sizes: list[int], bucket_elems: int) -> list[tuple[int, int]]:
 
 
 class Trainer:
+    """One data-parallel training step: forward, label-smoothed CE, backward, gradient mean, SGD.
+
+    Gradient exchange: every parameter ``.grad`` is a view of ONE flat fp32 buffer, cut into ~``bucket_mb`` buckets.
+    The native backward reports which parameter gradients are final (reverse layer order); as soon as a bucket is
+    complete its all-reduce is enqueued on a side stream, so the exchange overlaps the rest of backward (what DDP's
+    reducer does for the reference, configs/base.yaml:19).  The head's bucket goes last.
+    """
+
     def __init__(self, backbone: nn.Module, head: nn.Module, lr: float = 0.05, momentum: float = 0.9,
                  weight_decay: float = 2e-5, label_smoothing: float = 0.1, sync_bn: bool = True,
                  process_group=None, bucket_mb: float = 25.0):
@@ -53,6 +61,10 @@ class Trainer:
         self.label_smoothing = label_smoothing
         self.group = process_group
         self.world = 1
+        self.params = [p for p in list(backbone.parameters()) + list(head.parameters()) if p.requires_grad]
+        dev = self.params[0].device
+        self.dist_cfg: Optional[DistConfig] = None
+        self.avg_in_collective = False
         if process_group is not None:
             import torch.distributed as dist
 
@@ -60,25 +72,80 @@ class Trainer:
             # DDP broadcasts rank 0's parameters and buffers when it wraps the module
             for t in list(backbone.state_dict().values()) + list(head.state_dict().values()):
                 dist.broadcast(t, src=0, group=process_group)
-            backbone.__dict__["_vtb_dist"] = DistConfig(process_group, sync_bn=sync_bn)
-        self.params = [p for p in list(backbone.parameters()) + list(head.parameters()) if p.requires_grad]
-        dev = self.params[0].device
+            self.dist_cfg = DistConfig(process_group, sync_bn=sync_bn, device=dev)
+            self.dist_cfg.on_grads_ready = self._grads_ready
+            backbone.__dict__["_vtb_dist"] = self.dist_cfg
+            self.avg_in_collective = dist.get_backend(process_group) == "nccl"
         sizes = [p.numel() for p in self.params]
         self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
         off = 0
+        self._offset = {}
         for p, n in zip(self.params, sizes):
             p.grad = self.flat[off : off + n].view_as(p)
+            self._offset[id(p)] = off
             off += n
         # the native backward writes backbone gradients straight into these views (engine.Runner grad_sink mode)
         backbone.__dict__["_vtb_grad_sink"] = True
         self.buckets = bucket_ranges(sizes, int(bucket_mb * 1024 * 1024 / 4))
+        # bucket bookkeeping for the overlap: parameters per bucket, the bucket of every parameter
+        starts = [a for a, _ in self.buckets]
+        self._bucket_of = {}
+        self._bucket_size = [0] * len(self.buckets)
+        import bisect
+
+        for p in self.params:
+            b = bisect.bisect_right(starts, self._offset[id(p)]) - 1
+            self._bucket_of[id(p)] = b
+            self._bucket_size[b] += 1
+        self._pending = list(self._bucket_size)
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+        self.comm_stream = torch.cuda.Stream(dev) if (dev.type == "cuda" and self.world > 1) else None
         decay, no_decay = split_decay_groups([backbone, head])
         self.opt = torch.optim.SGD(
             [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}],
             lr=lr, momentum=momentum, fused=dev.type == "cuda")
 
+    # -- gradient exchange
+    def _launch_bucket(self, b: int) -> None:
+        import torch.distributed as dist
+
+        a, e = self.buckets[b]
+        self._launched[b] = True
+        op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self._works.append(dist.all_reduce(self.flat[a:e], op=op, group=self.group, async_op=True))
+        else:
+            self._works.append(dist.all_reduce(self.flat[a:e], op=op, group=self.group, async_op=True))
+
+    def _grads_ready(self, params) -> None:
+        """Called by the native backward when the gradients of `params` are final (written to the flat buffer)."""
+        for p in params:
+            b = self._bucket_of.get(id(p))
+            if b is None:
+                continue
+            self._pending[b] -= 1
+            if self._pending[b] == 0 and not self._launched[b]:
+                self._launch_bucket(b)
+
+    def _finish_exchange(self) -> None:
+        for b in range(len(self.buckets) - 1, -1, -1):   # whatever the overlap did not cover (the head, CPU modules)
+            if not self._launched[b]:
+                self._launch_bucket(b)
+        for w in self._works:
+            w.wait()
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if not self.avg_in_collective:
+            self.flat.mul_(1.0 / self.world)
+        self._works = []
+        self._pending = list(self._bucket_size)
+        self._launched = [False] * len(self.buckets)
+
     def forward_loss(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        f = self.backbone(x)  # (N, C, H, W) bf16
+        f = self.backbone(x)  # (N, C, H, W) bf16 on CUDA
         pooled = f.float().mean(dim=(2, 3))  # AdaptiveAvgPool2d + Flatten (classifier.py:61-62)
         logits = self.head(pooled)
         return F.cross_entropy(logits, y, label_smoothing=self.label_smoothing)
@@ -88,11 +155,6 @@ class Trainer:
         loss = self.forward_loss(x, y)
         loss.backward()
         if self.world > 1:
-            import torch.distributed as dist
-
-            works = [dist.all_reduce(self.flat[a:b], group=self.group, async_op=True) for a, b in self.buckets]
-            for w in works:
-                w.wait()
-            self.flat.mul_(1.0 / self.world)
+            self._finish_exchange()
         self.opt.step()
         return loss.detach()
