@@ -334,19 +334,19 @@ def main() -> None:
 
     # ---------------- roofline of the dominant kernel (instrumented extra step, rank 0) ----------------
     roofline, breakdown = None, None
+    # every rank runs the extra step (it contains the SyncBN / gradient collectives); rank 0 instruments it
+    prof = ProfilingLib(_lib.lib())
+    runners = list(model.__dict__.get("_vtb_plans", {}).values())
     if rank == 0:
-        from vision_toolbox_b200 import engine
-
-        prof = ProfilingLib(_lib.lib())
-        runners = list(model.__dict__.get("_vtb_plans", {}).values())
         for r in runners:
             r.L = prof
-        torch.cuda.synchronize()
-        torch.cuda._sleep(30_000_000)  # let the host run ahead so event intervals contain no launch gaps
-        trainer.step(dev_x[0], dev_y[0])
-        torch.cuda.synchronize()
-        for r in runners:
-            r.L = _lib.lib()
+    barrier()
+    torch.cuda._sleep(30_000_000)  # let the host run ahead so event intervals contain no launch gaps
+    trainer.step(dev_x[0], dev_y[0])
+    barrier()
+    for r in runners:
+        r.L = _lib.lib()
+    if rank == 0:
         agg = {}
         for name, geom, a, b, _ in prof.records:
             t = a.elapsed_time(b)

@@ -71,11 +71,11 @@ int vtb_conv_fprop(const VtbConv* c, const void* x, int ldx, const void* wf, voi
 
 /* Training-mode fusion of the two library calls at components.py:26-36: the convolution above (with statistics)
  * PLUS vtb_bn_finalize below, executed by the last thread block of the convolution kernel to finish - BatchNorm2d's
- * statistics finalisation then costs no kernel launch.  `tickets`: >= 64 zero-initialised uint32 owned by the caller
- * (the kernel leaves them zero; one array can serve every layer launched on the same stream).  Single-GPU statistics
- * only: under SyncBN use vtb_conv_fprop + vtb_bn_stats_reduce + (exchange) + vtb_bn_finalize. */
+ * statistics finalisation then costs no kernel launch.  `tickets`: >= 128 zero-initialised uint32 owned by the caller
+ * (the kernel leaves them zero; one array can serve every layer launched on the same stream). */
+struct VtbSyncBn;
 typedef struct VtbBnTrain {
-  double count;                    /* elements per channel: N*Ho*Wo */
+  double count;                    /* elements per channel: N*Ho*Wo (the GLOBAL count over all ranks under SyncBN) */
   const float* gamma;              /* norm.weight */
   const float* beta;               /* norm.bias */
   float eps, momentum;
@@ -87,6 +87,8 @@ typedef struct VtbBnTrain {
   float* scale;                    /* out [cout]: gamma*invstd */
   float* shift;                    /* out [cout]: beta - mean*scale */
   unsigned int* tickets;
+  const struct VtbSyncBn* sync;    /* NULL: single-GPU statistics; else the last block also exchanges the sums with all
+                                      ranks over NVLink peer memory before finalising (see vtb_bn_sync_* below) */
 } VtbBnTrain;
 int vtb_conv_fprop_bn(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
                       const VtbBnTrain* bn, void* stream);
@@ -167,14 +169,15 @@ int vtb_bn_bwd_apply(const void* dout, int lddo, const void* y, int ldy, long lo
                      const float* shift, const float* mean, const float* invstd, int relu, const float* coef,
                      void* dy, int lddy, void* stream);
 
-/* The three calls above in ONE cooperative launch (single-GPU statistics): reduce -> grid barrier -> finalize -> apply.
- * partial: vtb_bn_bwd_fused_rows(pixels, c) * c * 2 floats of scratch; sync: >= 128 zero-initialised uint32 owned by the
- * caller (left zero); dgamma / dbeta may be NULL.  c % 16 == 0. */
+/* The three calls above in ONE cooperative launch: reduce -> grid barrier -> finalize (-> SyncBN exchange over NVLink
+ * peer memory when `peers` != NULL; `count` is then the GLOBAL element count) -> apply.
+ * partial: vtb_bn_bwd_fused_rows(pixels, c) * c * 2 floats of scratch (+ 2*c floats when peers != NULL);
+ * sync: >= 256 zero-initialised uint32 owned by the caller (left zero); dgamma / dbeta may be NULL.  c % 16 == 0. */
 int vtb_bn_bwd_fused_rows(long long pixels, int c);
 int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long long pixels, int c, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int relu, double count,
                      float* partial, float* dgamma, float* dbeta, int accumulate, unsigned int* sync, void* dy,
-                     int lddy, void* stream);
+                     int lddy, const struct VtbSyncBn* peers, void* stream);
 
 /* dst (+)= src on bf16 NHWC views: gradient fan-out of the residual add (darknet.py:28) when it cannot be
  * aliased, and injection of incoming feature-map gradients. */

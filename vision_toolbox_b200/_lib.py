@@ -27,7 +27,7 @@ class VtbBnTrain(C.Structure):
     _fields_ = [("count", C.c_double), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
                 ("momentum", C.c_float), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
                 ("num_batches_tracked", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
-                ("scale", C.c_void_p), ("shift", C.c_void_p), ("tickets", C.c_void_p)]
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("tickets", C.c_void_p), ("sync", C.c_void_p)]
 
 
 class VtbSyncBn(C.Structure):
@@ -69,7 +69,7 @@ SIGNATURES = {
     "vtb_bn_bwd_finalize": (_i, [_p, _i, _p, _p, _d, _i, _p, _p, _i, _p, _p, _p]),
     "vtb_bn_bwd_apply": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p]),
     "vtb_bn_bwd_fused_rows": (_i, [_ll, _i]),
-    "vtb_bn_bwd_fused": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _d, _p, _p, _p, _i, _p, _p, _i, _p]),
+    "vtb_bn_bwd_fused": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _d, _p, _p, _p, _i, _p, _p, _i, _p, _p]),
     "vtb_grad_add": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p]),
     "vtb_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),
     "vtb_maxpool3s2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p]),

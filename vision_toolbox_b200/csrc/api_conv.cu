@@ -349,6 +349,8 @@ static int fprop_impl(const VtbConv* c, const void* x, int ldx, const void* wf, 
     p.bn_invstd = bn->invstd;
     p.bn_scale = bn->scale;
     p.bn_shift = bn->shift;
+    if (bn->sync && !sync_args_ok(bn->sync, c->cout)) return fail(VTB_EINVAL, "vtb_conv_fprop_bn: bad SyncBN peers");
+    p.sync = make_sync_peers(bn->sync);
   }
   p.scale = scale;
   p.shift = shift;

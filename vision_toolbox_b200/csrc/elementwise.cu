@@ -9,6 +9,7 @@
 
 #include "../../include/vtb.h"
 #include "common.cuh"
+#include "syncbn.cuh"
 
 namespace vtb {
 
@@ -379,7 +380,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv
 // BatchNorm(+ReLU) backward in ONE cooperative launch: stage 1 (partial sums) -> grid barrier over the blocks of a
 // channel chunk -> every block finalises its chunk's (mean dz, mean dz*xhat) from the partial rows (fp64, fixed order)
 // -> stage 3 (apply).  Saves two launches per layer and the second pass finds dout / y in L2 for mid-sized layers.
-// sync[2 * chunk + {0,1}]: zero-initialised arrive / depart counters, left zero again (self-cleaning).
+// sync[4 * chunk + {0,1,2}]: zero-initialised arrive / depart / ready counters, sync[255]: finished chunk exchanges; all
+// left zero again (self-cleaning).  Under SyncBN (sp.world > 1) block 0 of every chunk exchanges the chunk's sums with
+// all ranks over NVLink peer memory (syncbn.cuh) and broadcasts the global means to its sibling blocks through
+// coef_g = partial + gridDim.x * c * 2.
 // ---------------------------------------------------------------------------------------------
 template <bool RELU>
 __global__ void __launch_bounds__(512)
@@ -388,7 +392,7 @@ bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv
                     const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ invstd, float* __restrict__ partial, int c, double count,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
-                    unsigned int* __restrict__ sync, __nv_bfloat16* __restrict__ dy, int lddy) {
+                    unsigned int* __restrict__ sync, __nv_bfloat16* __restrict__ dy, int lddy, SyncPeers sp) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float red[];   // stage 1: [blockDim.x][17] floats; stage 2: doubles [G][pairs][4] then coef [cv*8][2]
@@ -455,20 +459,18 @@ bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv
     }
   }
   // ---------------- barrier over the gridDim.x blocks of this channel chunk
+  unsigned int* cnt = sync + 4 * blockIdx.y;   // arrive, depart, ready
+  unsigned int seq = 0;
   __threadfence();
   __syncthreads();
   if (t == 0) {
-    unsigned int* arrive = sync + 2 * blockIdx.y;
-    atomicAdd(arrive, 1u);
+    if (sp.world > 1) seq = sync_read_seq(sp);   // before any exchange of this launch can complete
+    atomicAdd(cnt, 1u);
     const long long t0 = clock64();
-    while (*reinterpret_cast<volatile unsigned int*>(arrive) < gridDim.x) {
+    while (*reinterpret_cast<volatile unsigned int*>(cnt) < gridDim.x) {
       if (clock64() - t0 > 4000000000LL) __trap();   // co-residency is guaranteed by the cooperative launch
     }
     __threadfence();
-    if (atomicAdd(arrive + 1, 1u) == gridDim.x - 1) {   // last block out: nobody spins any more
-      arrive[0] = 0u;
-      arrive[1] = 0u;
-    }
   }
   __syncthreads();
   // ---------------- stage 2: this chunk's sums, every block redundantly (thread = channel pair x row group)
@@ -479,6 +481,9 @@ bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv
     const int pr = t % pairs, g = t / pairs;
     double* dsum = reinterpret_cast<double*>(red);     // [G][pairs][4]
     float* cf = reinterpret_cast<float*>(dsum + (size_t)G * pairs * 4);   // [chans][2]
+    float* coef_g = partial + (size_t)gridDim.x * c * 2;
+    __shared__ unsigned int s_seq;
+    if (t == 0) s_seq = seq;
     if (g < G) {
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       const float* src = partial + ((size_t)blockIdx.y * cv * 8 + pr * 2) * 2;
@@ -497,26 +502,74 @@ bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv
       d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
     }
     __syncthreads();
+    double a[4] = {0, 0, 0, 0};
     if (t < pairs) {
-      double a[4] = {0, 0, 0, 0};
       for (int gg = 0; gg < G; ++gg) {
         const double* d = dsum + ((size_t)gg * pairs + t) * 4;
         a[0] += d[0]; a[1] += d[1]; a[2] += d[2]; a[3] += d[3];
       }
+      if (blockIdx.x == 0) {   // parameter gradients from the LOCAL sums (the gradient all-reduce averages them)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int lc = t * 2 + h;
-        const int gc = blockIdx.y * cv * 8 + lc;
-        const double s = a[2 * h], q = a[2 * h + 1];
-        cf[lc * 2] = (float)(s / count);
-        cf[lc * 2 + 1] = (float)(q / count);
-        if (blockIdx.x == 0) {
-          if (dgamma) dgamma[gc] = accumulate ? dgamma[gc] + (float)q : (float)q;
-          if (dbeta) dbeta[gc] = accumulate ? dbeta[gc] + (float)s : (float)s;
+        for (int h = 0; h < 2; ++h) {
+          const int gc = blockIdx.y * cv * 8 + t * 2 + h;
+          if (dgamma) dgamma[gc] = accumulate ? dgamma[gc] + (float)a[2 * h + 1] : (float)a[2 * h + 1];
+          if (dbeta) dbeta[gc] = accumulate ? dbeta[gc] + (float)a[2 * h] : (float)a[2 * h];
         }
       }
     }
+    if (sp.world > 1) {
+      if (blockIdx.x == 0) {
+        const unsigned int sq = s_seq;
+        if (t < pairs) {
+          const int gc = blockIdx.y * cv * 8 + t * 2;
+          sync_push(sp, sq, gc, a[0], a[1]);
+          sync_push(sp, sq, gc + 1, a[2], a[3]);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (t < sp.world) sync_signal_wait(sp, kSyncFlagsBwd, blockIdx.y, sq, t);
+        __syncthreads();
+        if (t < pairs) {
+          const int gc = blockIdx.y * cv * 8 + t * 2;
+          const double2 v0 = sync_gather(sp, sq, gc), v1 = sync_gather(sp, sq, gc + 1);
+          *reinterpret_cast<float4*>(coef_g + (size_t)gc * 2) =
+              make_float4((float)(v0.x / count), (float)(v0.y / count), (float)(v1.x / count), (float)(v1.y / count));
+        }
+        __threadfence();
+        __syncthreads();
+        if (t == 0) {
+          *reinterpret_cast<volatile unsigned int*>(cnt + 2) = 1u;   // ready: siblings may read coef_g
+          if (atomicAdd(sync + 255, 1u) == gridDim.y - 1) {          // last chunk exchange of this launch
+            sync[255] = 0u;
+            sync_write_seq(sp, sq);
+          }
+        }
+      } else if (t == 0) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned int*>(cnt + 2) == 0u) {
+          if (clock64() - t0 > 130000000000LL) __trap();
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      for (int lc = t; lc < chans; lc += blockDim.x) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(coef_g + ((size_t)blockIdx.y * cv * 8 + lc) * 2));
+        cf[lc * 2] = v.x;
+        cf[lc * 2 + 1] = v.y;
+      }
+    } else if (t < pairs) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        cf[(t * 2 + h) * 2] = (float)(a[2 * h] / count);
+        cf[(t * 2 + h) * 2 + 1] = (float)(a[2 * h + 1] / count);
+      }
+    }
     __syncthreads();
+    if (t == 0 && atomicAdd(cnt + 1, 1u) == gridDim.x - 1) {   // last block out: nobody spins or reads any more
+      cnt[0] = 0u;
+      cnt[1] = 0u;
+      cnt[2] = 0u;
+    }
     // ---------------- stage 3: dy = sc*dz - k0 - k1*(y - mu)
     if (!active) return;
     float k0[8], k1[8];
@@ -739,13 +792,15 @@ int vtb_bn_bwd_fused_rows(long long pixels, int c) {
 int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long long pixels, int c, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int relu, double count,
                      float* partial, float* dgamma, float* dbeta, int accumulate, unsigned int* sync, void* dy,
-                     int lddy, void* stream) {
+                     int lddy, const VtbSyncBn* peers, void* stream) {
   if (pixels <= 0 || c <= 0 || c % 16 || !VIEW_OK(dout, lddo, c) || !VIEW_OK(y, ldy, c) || !VIEW_OK(dy, lddy, c) ||
       !scale || !shift || !mean || !invstd || !partial || !sync || count <= 0)
     return fail(VTB_EINVAL, "vtb_bn_bwd_fused: bad arguments");
   int c8 = c / 8;
   const EwGeom g = bwd_fused_geom(pixels, c8);
-  if (g.chunks > 64) return fail(VTB_EINVAL, "vtb_bn_bwd_fused: too many channels");
+  if (g.chunks > 60) return fail(VTB_EINVAL, "vtb_bn_bwd_fused: too many channels");
+  if (peers && !sync_args_ok(peers, c)) return fail(VTB_EINVAL, "vtb_bn_bwd_fused: bad SyncBN peers");
+  SyncPeers sp = make_sync_peers(peers);
   int cv = g.cv;
   const dim3 grid(g.rows, g.chunks);
   const dim3 block(g.ppi * g.cv);
@@ -764,7 +819,7 @@ int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long lo
   const __nv_bfloat16* y_p = (const __nv_bfloat16*)y;
   __nv_bfloat16* dy_p = (__nv_bfloat16*)dy;
   void* args[] = {&dout_p, &lddo, &y_p, &ldy, &pixels, &c8, &cv, &scale, &shift, &mean, &invstd, &partial, &c, &count,
-                  &dgamma, &dbeta, &accumulate, &sync, &dy_p, &lddy};
+                  &dgamma, &dbeta, &accumulate, &sync, &dy_p, &lddy, &sp};
   count_launch(1);
   return check_cuda((int)cudaLaunchCooperativeKernel(fn, grid, block, args, sm, (cudaStream_t)stream),
                     "bn_bwd_fused_kernel");

@@ -6,6 +6,7 @@
 // cross row and image boundaries and padding is zero-filled by hardware), accumulators live in TMEM.
 #include "common.cuh"
 #include "igemm.cuh"
+#include "syncbn.cuh"
 #include "ptx.cuh"
 
 namespace vtb {
@@ -361,6 +362,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // pw == 64: up to 4 panels x 4 values (two columns); pw < 64: up to 8 panels x 2 values (one column)
     // (scalars, not an array: a runtime-indexed array would be demoted to local memory = L2 round trips here)
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;   // <= 4 local panels x (sum, sumsq) of one column
+    // SyncBN: the sequence number of this launch must be read before any exchange of the launch can complete
+    unsigned int my_seq = 0;
+    if (do_stats && p.sync.world > 1 && threadIdx.x == 128) my_seq = sync_read_seq(p.sync);
     uint32_t lt = 0;
     long long w_tfull = 0, t_ld = 0, t_cvt = 0, t_drain = 0;
     // work split: with two halves each group drains its own half; with one half the groups take alternate panels
@@ -586,13 +590,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             dsl[(g * p.block_n + col) * 2 + 1] = sq;
           }
           named_bar_sync(1, kEpiWarps * 32);
+          double sx = 0.0, sq = 0.0;
+          const int ch = n0 + et;
           if (et < p.block_n) {
-            double sx = 0.0, sq = 0.0;
             for (int gg = 0; gg < G; ++gg) {
               sx += dsl[(gg * p.block_n + et) * 2];
               sq += dsl[(gg * p.block_n + et) * 2 + 1];
             }
-            const int ch = n0 + et;
+          }
+          if (p.sync.world > 1) {
+            // SyncBN: exchange this n-block's sums with all ranks over NVLink peer memory (syncbn.cuh)
+            named_bar_sync(1, kEpiWarps * 32);          // dsl has been consumed; reuse its first word for the seq
+            if (et == 0) *reinterpret_cast<volatile unsigned int*>(slots) = my_seq;
+            named_bar_sync(1, kEpiWarps * 32);
+            const unsigned int seq = *reinterpret_cast<volatile unsigned int*>(slots);
+            if (et < p.block_n) sync_push(p.sync, seq, ch, sx, sq);
+            __threadfence_system();
+            named_bar_sync(1, kEpiWarps * 32);
+            if (et < p.sync.world) sync_signal_wait(p.sync, kSyncFlagsConv, n_blk, seq, et);
+            named_bar_sync(1, kEpiWarps * 32);
+            if (et < p.block_n) {
+              const double2 v = sync_gather(p.sync, seq, ch);
+              sx = v.x;
+              sq = v.y;
+            }
+            if (et == 0) {   // the last n-block to finish its exchange completes this launch's sequence number
+              const unsigned int done = atomicAdd(p.tickets + 64, 1u);
+              if (done == (unsigned int)(n_blocks - 1)) {
+                p.tickets[64] = 0u;
+                sync_write_seq(p.sync, seq);
+              }
+            }
+          }
+          if (et < p.block_n) {
             const double mean = sx / p.bn_count;
             double var = sq / p.bn_count - mean * mean;
             if (var < 0) var = 0;

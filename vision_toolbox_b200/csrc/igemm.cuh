@@ -11,6 +11,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "syncbn.cuh"
+
 namespace vtb {
 
 constexpr int kBlockM = 128;       // rows per UMMA (M); a conv tile is 1 or 2 such halves (block_m 128 / 256)
@@ -79,6 +81,9 @@ struct ConvIgemmParams {
   float* bn_invstd;
   float* bn_scale;
   float* bn_shift;
+  // SyncBN: peer-mapped exchange buffers (world <= 1: single-GPU statistics); bn_count is then the GLOBAL count and
+  // tickets[64] counts the finished n-block exchanges of the launch
+  SyncPeers sync;
   // optional fused per-channel affine + ReLU (+ residual) epilogue (eval-mode folded BN)
   const float* scale;
   const float* shift;

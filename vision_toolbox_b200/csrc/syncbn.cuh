@@ -1,0 +1,110 @@
+// SyncBatchNorm statistics exchange over NVLink peer memory: buffer layout + device primitives shared by the
+// stand-alone exchange kernels (syncbn.cu), the convolution epilogue (igemm.cu) and the fused BatchNorm backward
+// (elementwise.cu).
+//
+// Every rank owns one zero-initialised buffer that all peers have mapped.  Layout (bytes):
+//   [0,4)            sequence counter: number of exchange LAUNCHES completed by this rank (device resident -> a CUDA
+//                    graph replay stays consistent); every exchange of launch k uses seq = k+1, parity = seq & 1
+//   [4096, +4096)    flags of the stand-alone kernels      [2][64][8] uint32
+//   [8192, +4096)    flags of the convolution epilogues    [2][64 n-blocks][8]
+//   [12288, +4096)   flags of the fused backward kernels   [2][64 channel chunks][8]
+//   [16384, ...)     slots[2][8][VTB_SYNC_MAX_CHANNELS * 2] double: slot[parity][r][ch] = rank r's (sum, sumsq)
+// One exchange of a channel range:
+//   push my fp64 sums into slot[parity][my_rank] of EVERY peer (posted NVLink writes) -> fence.sys -> publish
+//   flags[parity][idx][my_rank] = seq on every peer -> spin on my own flags until all ranks published -> sum the world
+//   slots in rank order (identical order on every rank -> bit-identical statistics everywhere).
+// Parity double-buffering is sufficient because the parity alternates per LAUNCH on every rank: a rank can only start
+// launch k+2 after every peer signalled k+1, which a peer does after its launch k has finished reading.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+
+#include <cuda_runtime.h>
+
+#include "../../include/vtb.h"
+
+namespace vtb {
+
+constexpr int kSyncMaxRanks = VTB_SYNC_MAX_RANKS;
+constexpr int kSyncSlotDoubles = VTB_SYNC_MAX_CHANNELS * 2;
+constexpr size_t kSyncFlagsStd = 4096, kSyncFlagsConv = 8192, kSyncFlagsBwd = 12288, kSyncSlotsOff = 16384;
+constexpr size_t kSyncBufferBytes = kSyncSlotsOff + (size_t)2 * kSyncMaxRanks * kSyncSlotDoubles * sizeof(double);
+
+struct SyncPeers {
+  unsigned char* base[kSyncMaxRanks];
+  int rank, world;   // world <= 1: no exchange
+};
+
+inline SyncPeers make_sync_peers(const VtbSyncBn* s) {
+  SyncPeers p;
+  for (int r = 0; r < kSyncMaxRanks; ++r) p.base[r] = (s && r < s->world) ? (unsigned char*)s->peer_buffers[r] : nullptr;
+  p.rank = s ? s->rank : 0;
+  p.world = s ? s->world : 1;
+  return p;
+}
+inline bool sync_args_ok(const VtbSyncBn* s, int c) {
+  if (!s || s->world < 1 || s->world > kSyncMaxRanks || s->rank < 0 || s->rank >= s->world || c <= 0 ||
+      c > VTB_SYNC_MAX_CHANNELS)
+    return false;
+  for (int r = 0; r < s->world; ++r)
+    if (!s->peer_buffers[r]) return false;
+  return true;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 ld_volatile_d2(const double* p) {
+  double2 v;
+  asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// sequence number of the current launch (read it before any exchange of the launch can complete)
+__device__ __forceinline__ unsigned int sync_read_seq(const SyncPeers& sp) {
+  return *reinterpret_cast<volatile unsigned int*>(sp.base[sp.rank]) + 1u;
+}
+__device__ __forceinline__ void sync_write_seq(const SyncPeers& sp, unsigned int seq) {
+  *reinterpret_cast<volatile unsigned int*>(sp.base[sp.rank]) = seq;
+}
+// push (sum, sumsq) of channel `ch` to every rank's slot[parity][my rank]
+__device__ __forceinline__ void sync_push(const SyncPeers& sp, unsigned int seq, int ch, double s, double q) {
+  const size_t off = (((size_t)(seq & 1u) * kSyncMaxRanks + sp.rank) * kSyncSlotDoubles + (size_t)ch * 2) * sizeof(double);
+  for (int p = 0; p < sp.world; ++p)
+    *reinterpret_cast<double2*>(sp.base[p] + kSyncSlotsOff + off) = make_double2(s, q);
+}
+// to be called by `world` threads (r = 0..world-1) AFTER all pushing threads executed __threadfence_system() and a barrier:
+// publishes my flag on rank r and waits for rank r's flag on me
+static __device__ __noinline__ void sync_timeout_trap(int rank, int r, unsigned int seq) {
+  printf("vtb: SyncBN exchange timeout (rank %d waiting for rank %d, seq %u)\n", rank, r, seq);
+  __trap();
+}
+__device__ __forceinline__ void sync_signal_wait(const SyncPeers& sp, size_t flags_off, int idx, unsigned int seq, int r) {
+  const size_t fo = flags_off + (((size_t)(seq & 1u) * 64 + idx) * kSyncMaxRanks) * sizeof(unsigned int);
+  st_release_sys(reinterpret_cast<unsigned int*>(sp.base[r] + fo) + sp.rank, seq);
+  const unsigned int* mf = reinterpret_cast<const unsigned int*>(sp.base[sp.rank] + fo) + r;
+  const long long t0 = clock64();
+  while (ld_acquire_sys(mf) != seq) {
+    if (clock64() - t0 > 120000000000LL) sync_timeout_trap(sp.rank, r, seq);   // ~60 s: a peer died; fail loudly
+  }
+}
+// world-wide sums of channel `ch` (rank order)
+__device__ __forceinline__ double2 sync_gather(const SyncPeers& sp, unsigned int seq, int ch) {
+  const double* slots = reinterpret_cast<const double*>(sp.base[sp.rank] + kSyncSlotsOff) +
+                        (size_t)(seq & 1u) * kSyncMaxRanks * kSyncSlotDoubles + (size_t)ch * 2;
+  double s = 0.0, q = 0.0;
+  for (int r = 0; r < sp.world; ++r) {
+    const double2 v = ld_volatile_d2(slots + (size_t)r * kSyncSlotDoubles);
+    s += v.x;
+    q += v.y;
+  }
+  return make_double2(s, q);
+}
+#endif
+
+}  // namespace vtb

@@ -202,7 +202,7 @@ class Graph:
         self._stat(op, "partial_f", rows_f * cout * 2)
         self._stat(op, "sums", cout * 4)  # double[c][2]
         if self.need_grad:
-            self._stat(op, "partial_b", rows_b_alloc * cout * 2)
+            self._stat(op, "partial_b", (rows_b_alloc + 1) * cout * 2)   # + one row: global means under SyncBN
             self._stat(op, "coef", cout * 2)
             self._stat(op, "sums_b", cout * 4)
             self._stat(op, "lsums_b", cout * 4)
@@ -349,7 +349,7 @@ class Runner:
         self.dist: Optional[DistConfig] = None
         self.grad_sink = False
         # ticket counters of the fused conv + BatchNorm-finalize kernels (self-cleaning, shared by all layers)
-        self.tickets = torch.zeros(512, dtype=torch.int32, device=device)   # [0,256): conv tickets, [256,512): BN bwd
+        self.tickets = torch.zeros(512, dtype=torch.int32, device=device)   # [0,256): conv kernels, [256,512): BN bwd
 
     # -- helpers
     def _stream(self) -> int:
@@ -446,10 +446,13 @@ class Runner:
             rv = norm.running_var.data_ptr() if track else 0
             nbt = norm.num_batches_tracked.data_ptr() if track else 0
             count = float(out.pixels)
-        if use_batch_stats and world == 1:
-            # conv + statistics + BatchNorm finalisation in ONE launch (last CTA finalises)
-            bn = VtbBnTrain(count, norm.weight.data_ptr(), norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt,
-                            f("mean"), f("invstd"), f("scale"), f("shift"), self.tickets.data_ptr())
+        peer_sync = self.dist.sync if (world > 1 and self.dist is not None) else None
+        fused = use_batch_stats and (world == 1 or peer_sync is not None)
+        if fused:
+            # conv + statistics (+ SyncBN exchange over NVLink) + BatchNorm finalisation in ONE launch
+            bn = VtbBnTrain(count * world, norm.weight.data_ptr(), norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt,
+                            f("mean"), f("invstd"), f("scale"), f("shift"), self.tickets.data_ptr(),
+                            C.addressof(peer_sync) if peer_sync is not None else None)
             check(L.vtb_conv_fprop_bn(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(),
                                       abase + y.byte_offset(), y.ld, f("partial_f"), C.byref(bn), st),
                   "vtb_conv_fprop_bn")
@@ -457,12 +460,7 @@ class Runner:
             check(L.vtb_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(),
                                    abase + y.byte_offset(), y.ld, f("partial_f") if use_batch_stats else 0, 0, 0, 0, 0,
                                    0, st), "vtb_conv_fprop")
-        if use_batch_stats and world > 1 and self.dist.sync is not None:
-            # SyncBN: reduce + NVLink exchange + finalise (GLOBAL element count) in one kernel
-            check(L.vtb_bn_sync_finalize(f("partial_f"), op.rows_f, cout, C.byref(self.dist.sync), count * world,
-                                         norm.weight.data_ptr(), norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt,
-                                         f("mean"), f("invstd"), f("scale"), f("shift"), st), "vtb_bn_sync_finalize")
-        elif use_batch_stats and world > 1:
+        if use_batch_stats and not fused:
             # SyncBN through NCCL: local sums -> cross-rank sum -> finalise with the GLOBAL element count
             check(L.vtb_bn_stats_reduce(f("partial_f"), op.rows_f, cout, f("sums"), st), "vtb_bn_stats_reduce")
             sums = run.stat_view_f64(op.st["sums"], cout * 2, sbase)
@@ -614,12 +612,14 @@ class Runner:
         x, y, out, res = op.x, op.y, op.out, op.residual
         f = lambda name: sbase + 4 * op.st[name]
         dout_p, dout_ld = gp(out), gld(out)
-        if g.training and world == 1:
-            # reduce -> finalize -> apply in one cooperative launch
+        peer_sync = self.dist.sync if (world > 1 and self.dist is not None) else None
+        if g.training and (world == 1 or peer_sync is not None):
+            # reduce -> finalize (-> SyncBN exchange over NVLink) -> apply in one cooperative launch
             check(L.vtb_bn_bwd_fused(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
-                                     f("shift"), f("mean"), f("invstd"), int(op.relu), float(out.pixels),
+                                     f("shift"), f("mean"), f("invstd"), int(op.relu), float(out.pixels) * world,
                                      f("partial_b"), pgrads[op.pidx + 1].data_ptr(), pgrads[op.pidx + 2].data_ptr(), 0,
-                                     self.tickets.data_ptr() + 1024, dybase, cout, st), "vtb_bn_bwd_fused")
+                                     self.tickets.data_ptr() + 1024, dybase, cout,
+                                     C.byref(peer_sync) if peer_sync is not None else None, st), "vtb_bn_bwd_fused")
             self._conv_backward_gemms(op, abase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st)
             return
         check(L.vtb_bn_bwd_reduce(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
@@ -627,11 +627,7 @@ class Runner:
               "vtb_bn_bwd_reduce")
         dgamma, dbeta = pgrads[op.pidx + 1].data_ptr(), pgrads[op.pidx + 2].data_ptr()
         count = float(out.pixels)
-        if g.training and world > 1 and self.dist.sync is not None:
-            check(L.vtb_bn_sync_bwd_finalize(f("partial_b"), op.rows_b, cout,
-                                             C.byref(self.dist.sync), count * world, dgamma, dbeta, 0, f("coef"),
-                                             f("lsums_b"), st), "vtb_bn_sync_bwd_finalize")
-        elif g.training and world > 1:
+        if g.training and world > 1:
             check(L.vtb_bn_bwd_finalize(f("partial_b"), op.rows_b, 0, 0, count, cout, 0, 0, 0, 0, f("lsums_b"), st),
                   "vtb_bn_bwd_finalize(local)")
             sums = run.stat_view_f64(op.st["sums_b"], cout * 2, sbase)
