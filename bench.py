@@ -225,6 +225,7 @@ def main() -> None:
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sync-bn", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph (single GPU)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -267,6 +268,9 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
+    use_graph = world == 1 and not args.no_graph
+    if use_graph:
+        trainer.enable_cuda_graph(dev_x[0], dev_y[0], warmup=2)
     for i in range(W):
         trainer.step(dev_x[i % n_host], dev_y[i % n_host])
     barrier()
@@ -282,6 +286,8 @@ def main() -> None:
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     launches = _lib.launch_count() - launches0
+    if use_graph:
+        launches += K * trainer.graph_launches   # replayed launches do not pass through the host-side counter
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
@@ -342,7 +348,7 @@ def main() -> None:
             r.L = prof
     barrier()
     torch.cuda._sleep(30_000_000)  # let the host run ahead so event intervals contain no launch gaps
-    trainer.step(dev_x[0], dev_y[0])
+    trainer._step_eager(dev_x[0], dev_y[0])   # eager on purpose: per-call events cannot be recorded inside a graph replay
     barrier()
     for r in runners:
         r.L = _lib.lib()
@@ -381,7 +387,8 @@ def main() -> None:
             "config": {"workload": f"{args.model} train step (fwd+loss+bwd+SGD), {res}px, batch {nb}/GPU, bf16, "
                                    f"{'SyncBN+DDP' if world > 1 else 'single GPU'}",
                        "model": args.model, "global_batch": nb * world, "resolution": res,
-                       "parallelism": f"dp{world}", "l2_policy": "inputs+activations >> L2 (multi-GB working set per step)"},
+                       "parallelism": f"dp{world}", "l2_policy": "inputs+activations >> L2 (multi-GB working set per step)",
+                       "cuda_graph": bool(use_graph)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),

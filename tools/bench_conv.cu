@@ -84,7 +84,29 @@ int main(int argc, char** argv) {
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       total += ms; if (ms < best) best = ms;
     }
-    const double avg = total / iters;
+    double avg = total / iters;
+    if (getenv("VTB_GRAPH")) {
+      // GPU-side time per launch with the host out of the picture: 20 back-to-back launches replayed from a CUDA graph
+      cudaStream_t cs; CK(cudaStreamCreate(&cs));
+      auto run_s = [&](cudaStream_t st) {
+        if (which == 0) CV(vtb_conv_fprop(&c, x, c.cin, wf, y, c.cout, stats, nullptr, nullptr, 0, nullptr, 0, st));
+        if (which == 1) CV(vtb_conv_dgrad(&c, dy, c.cout, wd, dx, c.cin, 0, st));
+        if (which == 2) CV(vtb_conv_wgrad(&c, dy, c.cout, x, c.cin, ws, dw, c.cin, 0, st));
+      };
+      cudaGraph_t graph; cudaGraphExec_t exec;
+      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      for (int i = 0; i < 20; ++i) run_s(cs);
+      CK(cudaStreamEndCapture(cs, &graph));
+      CK(cudaGraphInstantiate(&exec, graph, 0));
+      CK(cudaGraphLaunch(exec, cs)); CK(cudaStreamSynchronize(cs));
+      cudaEventRecord(e0, cs);
+      for (int r = 0; r < 5; ++r) CK(cudaGraphLaunch(exec, cs));
+      cudaEventRecord(e1, cs);
+      CK(cudaStreamSynchronize(cs));
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      printf("%-6s graph replay: %8.1f us per launch (host-free, back to back)\n", names[which], ms * 1e3 / 100);
+      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaStreamDestroy(cs);
+    }
     printf("%-6s %4d->%4d k%ds%d %3dx%-3d n%-3d | avg %8.1f us  best %8.1f us | %7.1f TF/s %7.1f GB/s\n", names[which], c.cin, c.cout,
            c.k, c.stride, c.h, c.w, c.n, avg * 1e3, best * 1e3, flops / (avg * 1e-3) / 1e12, bytes / (avg * 1e-3) / 1e9);
     if (which == 2) {

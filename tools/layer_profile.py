@@ -52,11 +52,12 @@ for fn, geom, a, b, args in prof.records:
         key = f"{fn[9:]:8s} {g.cin:4d}->{g.cout:4d} k{g.k}s{g.stride} {g.h:3d}->{ho:3d}"
         fl = conv_flops(geom)
         by = 2.0 * g.n * (g.h * g.w * g.cin + ho * ho * g.cout) + 2.0 * g.k * g.k * g.cin * g.cout
-    elif fn in ("vtb_bn_act", "vtb_bn_bwd_reduce", "vtb_bn_bwd_apply"):
+    elif fn in ("vtb_bn_act", "vtb_bn_bwd_reduce", "vtb_bn_bwd_apply", "vtb_bn_bwd_fused"):
         # args: (y/dout, ld, pixels, c, ...) resp. (dout, lddo, y, ldy, pixels, c, ...)
         pix, c = (args[2], args[3]) if fn == "vtb_bn_act" else (args[4], args[5])
         key = f"{fn[4:]:14s} c{c:4d} pix{pix:8d}"
-        passes = {"vtb_bn_act": 2 + (1 if args[7] else 0), "vtb_bn_bwd_reduce": 2, "vtb_bn_bwd_apply": 3}[fn]
+        passes = {"vtb_bn_act": 2 + (1 if args[7] else 0), "vtb_bn_bwd_reduce": 2, "vtb_bn_bwd_apply": 3,
+                  "vtb_bn_bwd_fused": 5}[fn]
         by = 2.0 * pix * c * passes
     d = agg.setdefault(key, [0.0, 0.0, 0.0, 0])
     d[0] += t; d[1] += fl; d[2] += by; d[3] += 1

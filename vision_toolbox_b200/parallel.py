@@ -65,6 +65,8 @@ class Trainer:
         dev = self.params[0].device
         self.dist_cfg: Optional[DistConfig] = None
         self.avg_in_collective = False
+        self._graph = None
+        self.graph_launches = 0
         if process_group is not None:
             import torch.distributed as dist
 
@@ -150,7 +152,7 @@ class Trainer:
         logits = self.head(pooled)
         return F.cross_entropy(logits, y, label_smoothing=self.label_smoothing)
 
-    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         self.flat.zero_()
         loss = self.forward_loss(x, y)
         loss.backward()
@@ -158,3 +160,40 @@ class Trainer:
             self._finish_exchange()
         self.opt.step()
         return loss.detach()
+
+    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self._graph is not None and tuple(x.shape) == tuple(self._gx.shape) and x.dtype == self._gx.dtype:
+            # the whole step (≈600 kernel launches) replays from ONE CUDA graph: inputs are copied into the captured
+            # buffers, the loss is read from the captured output
+            self._gx.copy_(x, non_blocking=True)
+            self._gy.copy_(y, non_blocking=True)
+            self._graph.replay()
+            return self._gloss
+        return self._step_eager(x, y)
+
+    def enable_cuda_graph(self, x: torch.Tensor, y: torch.Tensor, warmup: int = 3) -> None:
+        """Capture forward + loss + backward + SGD for inputs shaped like (x, y) into a CUDA graph (single process).
+
+        Every kernel of the step is enqueued through the C ABI on the capturing stream, all buffers come from the
+        graph's private pool, parameter gradients land in the flat buffer and the SyncBN/BatchNorm tickets are device
+        resident, so a replay is exactly one training step.  `warmup` eager steps run first (they are REAL steps).
+        """
+        if self.world > 1:
+            raise NotImplementedError("CUDA-graph capture of the data-parallel step is not enabled")
+        dev = x.device
+        self._gx, self._gy = x.clone(), y.clone()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 2)):   # builds the plan, the weight packs and the momentum buffers
+                self._step_eager(self._gx, self._gy)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            self._gloss = self._step_eager(self._gx, self._gy)
+        self.graph_launches = _lib.launch_count() - n0   # kernels of this library inside one replay
+        self._graph = graph
