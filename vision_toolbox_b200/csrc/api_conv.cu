@@ -112,8 +112,9 @@ static ConvTiling plan_conv_tiling(long long M, int ncols, int total_k16) {
     const int acc_stride = (t.block_n + 31) & ~31;
     int ks = 4 / halves;
     while (ks > 1 && (halves * ks * acc_stride > 512 || ks > total_k16)) ks >>= 1;
-    if (total_k16 < 32)
-      while (ks > 1 && 2 * halves * ks * acc_stride > 512) ks >>= 1;
+    // two TMEM sets (the epilogue of tile i overlaps the MMAs of tile i+1) beat extra chains: the kernel is bound by the
+    // operand feed, not by the MMA issue rate (VTB_KSPLIT sweeps in profiles/r01_conv_kernel_bench.txt)
+    while (ks > 1 && 2 * halves * ks * acc_stride > 512) ks >>= 1;
     static const int o_ks = env_int("VTB_KSPLIT");
     if (o_ks > 0 && halves * o_ks * acc_stride <= 512 && o_ks <= total_k16) ks = o_ks;
     t.ksplit = ks;
@@ -211,7 +212,9 @@ static WgradPlan plan_wgrad(const VtbConv* c) {
   w.boxes_per_tap = c->cin / w.cc;
   w.total_boxes = taps * w.boxes_per_tap;
   // column tiling of the flattened tap*cin axis: tiles of <= 256 columns, as even as the box width allows
-  const int max_boxes = 256 / w.cc;
+  // 128-column tiles for the big 3x3 layers: with N = 128 the four K-split accumulator chains fit TMEM, a stage is
+  // 64 KB at 128 pixels (3 stages) and the measured optimum of the kpix x boxes sweep (profiles/r01_wgrad_sweep.txt)
+  const int max_boxes = (taps > 1 && taps * c->cin >= 512 && w.cc == 64) ? 128 / w.cc : 256 / w.cc;
   int best_tiles = (w.total_boxes + max_boxes - 1) / max_boxes, best_bpt = 0, best_waste = 1 << 30;
   for (int nt = best_tiles; nt <= best_tiles + 2; ++nt) {
     const int bpt = (w.total_boxes + nt - 1) / nt;

@@ -407,13 +407,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint32_t v[16];
           const uint32_t ta = taddr + pc * 16;
           tmem_ld16(ta, v);
-          tmem_ld_wait();
-          for (int ksel = 1; ksel < ksplit; ++ksel) {  // sum the K-interleaved partial accumulators
+          if (ksplit >= 2) {   // sum the K-interleaved partial accumulators; loads are issued before the single wait
             uint32_t v2[16];
-            tmem_ld16(ta + ksel * acc_stride, v2);
+            tmem_ld16(ta + acc_stride, v2);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+            for (int ksel = 2; ksel < ksplit; ++ksel) {
+              tmem_ld16(ta + ksel * acc_stride, v2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+            }
+          } else {
+            tmem_ld_wait();
           }
           if (pi + pi_step >= npanels && pc == npieces - 1) {
             tc_fence_before();
@@ -865,9 +872,17 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
       umma_commit(tfull_bar);
       if (timed) dbg[1] = w_full;
     }
-  } else {
+  }
+  if (warp != kWgProducers) {
     // ======================= epilogue: TMEM -> fp32 partial tile of this split =======================
+    // Every warp but the MMA issuer drains: a warp may touch the TMEM lane quarter (warp % 4), so the 8 producer warps
+    // (idle once their last load is issued) and the 4 epilogue warps form 3 parts per quarter that interleave the
+    // 16-column pieces.
+    __syncwarp();
     const int quarter = warp & 3;
+    const int part = (warp < kWgProducers) ? (warp >> 2) : 2;
+    constexpr int nparts = kWgProducers / 4 + 1;
+    const bool dbg_warp = (warp == kWgProducers + 4) && lane == 0;
     const int row = quarter * 32 + lane;
     const int co = co0 + row;
     const int ktot = p.ntaps * p.cin;
@@ -879,21 +894,28 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
       tc_fence_after();
     }
     const long long t_epi = timed ? clock64() : 0;
-    if (timed && quarter == 0 && lane == 0) dbg[3] = w_tf;
+    if (timed && dbg_warp) dbg[3] = w_tf;
     if (co0 + quarter * 32 < p.cout) {   // warp-uniform: skip lane quarters that hold no real output channel
       float* wrow = p.ws + ((size_t)split * p.cout + min(co, p.cout - 1)) * ktot + (size_t)box0 * p.cc;
-      for (int ch = 0; ch < n_mma / 16; ++ch) {
+      for (int ch = part; ch < n_mma / 16; ch += nparts) {
         uint32_t v[16];
         if (nkb > 0) {
           const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 16;
           tmem_ld16(ta, v);
-          tmem_ld_wait();
-          for (int s = 1; s < ks_used; ++s) {
+          if (ks_used >= 2) {   // both loads in flight before the wait
             uint32_t v2[16];
-            tmem_ld16(ta + s * p.acc_stride, v2);
+            tmem_ld16(ta + p.acc_stride, v2);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+            for (int s = 2; s < ks_used; ++s) {
+              tmem_ld16(ta + s * p.acc_stride, v2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+            }
+          } else {
+            tmem_ld_wait();
           }
         } else {
 #pragma unroll
@@ -908,7 +930,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
         }
       }
     }
-    if (timed && quarter == 0 && lane == 0) dbg[4] = clock64() - t_epi;
+    if (timed && dbg_warp) dbg[4] = clock64() - t_epi;
   }
   tc_fence_before();
   __syncthreads();
