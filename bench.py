@@ -365,8 +365,12 @@ def main() -> None:
         igemm_fl = sum(v[1] for v in conv_calls)
         igemm_n = sum(v[2] for v in conv_calls)
         achieved = igemm_fl / (igemm_ms / 1e3) / 1e12 if igemm_ms > 0 else 0.0
+        traffic = None   # dram__bytes_read+write per launch from the committed ncu pass (tools/launches_summary.py)
+        tp = ROOT / "profiles" / "ncu_conv_traffic.json"
+        if tp.exists() and args.model == "cspdarknet53" and nb == 256 and res == 176:
+            traffic = json.loads(tp.read_text()).get("avg_dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (fprop + dgrad launches)", "achieved": achieved,
-                    "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                    "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
                     "peak_source": pk["source"] + ", sustained cuBLAS bf16", "launches": igemm_n,
                     "avg_launch_ms": igemm_ms / max(igemm_n, 1)}
         tot = sum(v[0] for v in agg.values())
