@@ -268,9 +268,21 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("VTB_DP_GRAPH", "1") == "1")
     if use_graph:
-        trainer.enable_cuda_graph(dev_x[0], dev_y[0], warmup=2)
+        try:
+            trainer.enable_cuda_graph(dev_x[0], dev_y[0], warmup=2)
+        except Exception as e:  # noqa: BLE001 - any capture problem -> eager replay of the same kernels
+            if rank == 0:
+                print(f"[bench] CUDA graph disabled: {type(e).__name__}: {e}", file=sys.stderr)
+            trainer._graph = None
+            use_graph = False
+        if world > 1:   # every rank must take the same path
+            flag = torch.tensor([1 if use_graph else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag) == 0:
+                trainer._graph = None
+                use_graph = False
     for i in range(W):
         trainer.step(dev_x[i % n_host], dev_y[i % n_host])
     barrier()
@@ -405,6 +417,13 @@ def main() -> None:
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        barrier()
+        if use_graph:
+            # a captured graph holds NCCL work; tearing the process group down under it can block at interpreter exit,
+            # so leave without running destructors (every rank is past the barrier, rank 0 has printed its line)
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

@@ -178,9 +178,13 @@ class Trainer:
         graph's private pool, parameter gradients land in the flat buffer and the SyncBN/BatchNorm tickets are device
         resident, so a replay is exactly one training step.  `warmup` eager steps run first (they are REAL steps).
         """
-        if self.world > 1:
-            raise NotImplementedError("CUDA-graph capture of the data-parallel step is not enabled")
         dev = x.device
+        if self.world > 1:
+            # NCCL all-reduces (side stream, forked from / joined to the capturing stream) and the SyncBN peer-memory
+            # kernels (device-resident sequence numbers) are capturable; the NCCL-per-layer SyncBN fallback is not used
+            # under capture because it reads tensors back on the host path of torch.distributed
+            if self.dist_cfg is not None and self.dist_cfg.sync_bn and self.dist_cfg.sync is None:
+                raise NotImplementedError("CUDA-graph capture needs the peer-memory SyncBN exchange")
         self._gx, self._gy = x.clone(), y.clone()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
