@@ -189,9 +189,11 @@ int vtb_nchw_to_nhwc(const float* x, int n, int c, int h, int w, void* out, int 
 
 /* ---- VoVNet-only ops ----
  * MaxPool2d(3, 2, 1) (vovnet.py:94): -inf padding, first maximum wins ties in backward. */
-int vtb_maxpool3s2_fwd(const void* x, int ldx, int n, int h, int w, int c, void* out, int ldo, void* stream);
+/* idx (optional, n*ho*wo*c bytes): the window position of the first maximum of every output element, i.e. what
+ * aten::max_pool2d_with_indices keeps for backward; with it the backward needs neither x nor a 36-load recomputation. */
+int vtb_maxpool3s2_fwd(const void* x, int ldx, int n, int h, int w, int c, void* out, int ldo, void* idx, void* stream);
 int vtb_maxpool3s2_bwd(const void* x, int ldx, int n, int h, int w, int c, const void* dout, int lddo, void* dx,
-                       int lddx, int accumulate, void* stream);
+                       int lddx, int accumulate, const void* idx, void* stream);
 /* ESEBlock (vovnet.py:20-28): out = x * hardsigmoid(W * mean_hw(x) + b) [+ residual] (vovnet.py:58-61).
  * weight [c][c] fp32 (the (C,C,1,1) Conv2d weight), bias [c]; pool/z/gate: [n][c] fp32 saved for backward.
  * bwd scratch: 3*n*c floats. dweight/dbias are fp32 parameter gradients. */

@@ -72,8 +72,8 @@ SIGNATURES = {
     "vtb_bn_bwd_fused": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _d, _p, _p, _p, _i, _p, _p, _i, _p, _p]),
     "vtb_grad_add": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p]),
     "vtb_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),
-    "vtb_maxpool3s2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p]),
-    "vtb_maxpool3s2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p]),
+    "vtb_maxpool3s2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
+    "vtb_maxpool3s2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p]),
     "vtb_ese_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
     "vtb_ese_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i, _i, _p, _p, _i, _p, _p]),
 }

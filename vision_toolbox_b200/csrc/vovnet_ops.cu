@@ -34,8 +34,10 @@ static int vgrid(long long work, int block) {
 }
 
 // ------------------------------------------------------------------ MaxPool2d(k=3, s=2, p=1)
+// idx (optional): per output element the window position r*3+s of its FIRST maximum (uint8, [pixel][c]) - what
+// aten::max_pool2d_with_indices saves for backward
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int c8, int ho,
-                                   int wo, __nv_bfloat16* __restrict__ out, int ldo) {
+                                   int wo, __nv_bfloat16* __restrict__ out, int ldo, unsigned char* __restrict__ idx) {
   pdl_wait();
   pdl_trigger();
   const long long total = (long long)n * ho * wo * c8;
@@ -47,8 +49,9 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
     const int oh = (int)(t % ho);
     const int img = (int)(t / ho);
     float m[8];
+    unsigned int arg[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; arg[j] = 255u; }
     for (int r = 0; r < 3; ++r) {
       const int ih = oh * 2 - 1 + r;
       if (ih < 0 || ih >= h) continue;
@@ -58,10 +61,18 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
         float f[8];
         v_unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)img * h + ih) * w + iw) * ldx + v * 8)), f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = (f[j] > m[j] || f[j] != f[j]) ? f[j] : m[j];
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > m[j] || f[j] != f[j]) { m[j] = f[j]; arg[j] = r * 3 + s; }
       }
     }
-    *reinterpret_cast<uint4*>(out + (((long long)img * ho + oh) * wo + ow) * ldo + v * 8) = v_pack8(m);
+    const long long opix = ((long long)img * ho + oh) * wo + ow;
+    *reinterpret_cast<uint4*>(out + opix * ldo + v * 8) = v_pack8(m);
+    if (idx != nullptr) {
+      uint2 pk;
+      pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(idx + (opix * c8 + v) * 8) = pk;
+    }
   }
 }
 
@@ -124,6 +135,120 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
     }
     *reinterpret_cast<uint4*>(dst) = v_pack8(acc);
   }
+}
+
+// same result from the saved argmax indices: <= 4 index + gradient loads per input pixel instead of 36 input loads
+template <bool ADD>
+__global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, int n, int h, int w, int c8, int ho, int wo,
+                                       const __nv_bfloat16* __restrict__ dout, int lddo,
+                                       __nv_bfloat16* __restrict__ dx, int lddx) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = (long long)n * h * w * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c8);
+    long long t = i / c8;
+    const int iw0 = (int)(t % w);
+    t /= w;
+    const int ih0 = (int)(t % h);
+    const int img = (int)(t / h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int oh_lo = ih0 / 2, oh_hi = min(ho - 1, (ih0 + 1) / 2);
+    const int ow_lo = iw0 / 2, ow_hi = min(wo - 1, (iw0 + 1) / 2);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        const int r0 = ih0 - (oh * 2 - 1), s0 = iw0 - (ow * 2 - 1);
+        if (r0 < 0 || r0 > 2 || s0 < 0 || s0 > 2) continue;
+        const unsigned int me = r0 * 3 + s0;
+        const long long opix = ((long long)img * ho + oh) * wo + ow;
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + (opix * c8 + v) * 8));
+        float g[8];
+        v_unpack8(__ldg(reinterpret_cast<const uint4*>(dout + opix * lddo + v * 8)), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned int a = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 255u;
+          if (a == me) acc[j] += g[j];
+        }
+      }
+    __nv_bfloat16* dst = dx + (((long long)img * h + ih0) * w + iw0) * lddx + v * 8;
+    if (ADD) {
+      float o[8];
+      v_unpack8(*reinterpret_cast<const uint4*>(dst), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = v_rbf(acc[j]) + o[j];
+    }
+    *reinterpret_cast<uint4*>(dst) = v_pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------ small fp32 GEMM for the eSE 1x1 "conv" on (N,C,1,1)
+// C[i][j] = sum_k A(i,k) * B(k,j), A(i,k) = a[i*sai + k*sak], B(k,j) = b[k*sbk + j*sbj]; operands optionally rounded to
+// bf16 first (autocast runs nn.Conv2d in bf16).  32x32 tiles, 16-deep k steps, 256 threads x (2x2) results.
+// EPI 0: plain store (scaled by alpha); 1: z / gate epilogue of the eSE forward; 2: accumulate-or-store (dW)
+template <bool RA, bool RB, int EPI>
+__global__ void __launch_bounds__(256)
+small_gemm_kernel(const float* __restrict__ a, long long sai, long long sak, const float* __restrict__ b, long long sbk,
+                  long long sbj, int M, int N, int K, float alpha, float* __restrict__ out, long long ldc,
+                  const float* __restrict__ bias, float* __restrict__ out2, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float As[16][33], Bs[16][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = threadIdx.x; e < 512; e += 256) {
+      // choose the fast index so that global reads are as contiguous as the operand allows
+      int kk, ii;
+      if (sak == 1) { kk = e & 15; ii = e >> 4; } else { ii = e & 31; kk = e >> 5; }
+      const int gi = i0 + ii, gk = k0 + kk;
+      float v = (gi < M && gk < K) ? __ldg(a + gi * sai + gk * sak) : 0.f;
+      As[kk][ii] = RA ? v_rbf(v) : v;
+      int kb, jj;
+      if (sbk == 1) { kb = e & 15; jj = e >> 4; } else { jj = e & 31; kb = e >> 5; }
+      const int gj = j0 + jj, gkb = k0 + kb;
+      float u = (gj < N && gkb < K) ? __ldg(b + gkb * sbk + gj * sbj) : 0.f;
+      Bs[kb][jj] = RB ? v_rbf(u) : u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
+      const float b0 = Bs[kk][tx * 2], b1 = Bs[kk][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int gi = i0 + ty * 2 + u, gj = j0 + tx * 2 + w;
+      if (gi >= M || gj >= N) continue;
+      float* dst = out + gi * ldc + gj;
+      if (EPI == 0) {
+        *dst = acc[u][w] * alpha;
+      } else if (EPI == 1) {
+        const float zz = v_rbf(acc[u][w] + v_rbf(bias[gj]));
+        *dst = zz;
+        out2[gi * ldc + gj] = v_rbf(fminf(fmaxf(zz * (1.f / 6.f) + 0.5f, 0.f), 1.f));
+      } else {
+        *dst = accumulate ? *dst + acc[u][w] : acc[u][w];
+      }
+    }
+}
+// db[co] (+)= sum_n dz[n][co]
+__global__ void ese_dbias_kernel(const float* __restrict__ dz, int n, int c, float* __restrict__ db, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= c) return;
+  float acc = 0.f;
+  for (int img = 0; img < n; ++img) acc += dz[(long long)img * c + co];
+  db[co] = accumulate ? db[co] + acc : acc;
 }
 
 // ------------------------------------------------------------------ eSE
@@ -293,24 +418,34 @@ using namespace vtb;
 
 extern "C" {
 
-int vtb_maxpool3s2_fwd(const void* x, int ldx, int n, int h, int w, int c, void* out, int ldo, void* stream) {
+int vtb_maxpool3s2_fwd(const void* x, int ldx, int n, int h, int w, int c, void* out, int ldo, void* idx, void* stream) {
   if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 || !VVIEW_OK(x, ldx, c) || !VVIEW_OK(out, ldo, c))
     return fail(VTB_EINVAL, "vtb_maxpool3s2_fwd: bad arguments");
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
   launch_pdl(maxpool_fwd_kernel, dim3(vgrid(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8,
-                                                                          ho, wo, (__nv_bfloat16*)out, ldo);
+                                                                          ho, wo, (__nv_bfloat16*)out, ldo, (unsigned char*)idx);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "maxpool_fwd_kernel");
 }
 
 int vtb_maxpool3s2_bwd(const void* x, int ldx, int n, int h, int w, int c, const void* dout, int lddo, void* dx,
-                       int lddx, int accumulate, void* stream) {
-  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 || !VVIEW_OK(x, ldx, c) || !VVIEW_OK(dout, lddo, c) ||
+                       int lddx, int accumulate, const void* idx, void* stream) {
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 || (!idx && !VVIEW_OK(x, ldx, c)) || !VVIEW_OK(dout, lddo, c) ||
       !VVIEW_OK(dx, lddx, c))
     return fail(VTB_EINVAL, "vtb_maxpool3s2_bwd: bad arguments");
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   const long long total = (long long)n * h * w * (c / 8);
+  if (idx) {
+    if (accumulate)
+      launch_pdl(maxpool_bwd_idx_kernel<true>, dim3(vgrid(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+                 (const unsigned char*)idx, n, h, w, c / 8, ho, wo, (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx);
+    else
+      launch_pdl(maxpool_bwd_idx_kernel<false>, dim3(vgrid(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+                 (const unsigned char*)idx, n, h, w, c / 8, ho, wo, (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx);
+    count_launch(1);
+    return check_cuda((int)cudaGetLastError(), "maxpool_bwd_idx_kernel");
+  }
   if (accumulate)
     launch_pdl(maxpool_bwd_kernel<true>, dim3(vgrid(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, ho, wo, (const __nv_bfloat16*)dout, lddo, (__nv_bfloat16*)dx, lddx);
@@ -330,8 +465,9 @@ int vtb_ese_fwd(const void* x, int ldx, int n, int hw, int c, const float* weigh
   const int c8 = c / 8;
   launch_pdl(hw_reduce_kernel<false>, dim3(dim3((c8 + 31) / 32, n)), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, nullptr, 0, hw, c8,
                                                                    pool, c, 1.f / hw);
-  const long long warps = (long long)n * c;
-  launch_pdl(ese_fc_fwd_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st, pool, weight, bias, n, c, z, gate);
+  // z[n][co] = bf16(sum_ci bf16(pool[n][ci]) * bf16(W[co][ci]) + bf16(b[co])), gate = bf16(hardsigmoid(z))
+  launch_pdl(small_gemm_kernel<true, true, 1>, dim3((c + 31) / 32, (n + 31) / 32), dim3(256), 0, st, (const float*)pool,
+             (long long)c, 1LL, weight, 1LL, (long long)c, n, c, c, 1.f, z, (long long)c, bias, gate, 0);
   const long long pixels = (long long)n * hw;
   if (residual)
     launch_pdl(ese_scale_kernel<true>, dim3(vgrid(pixels * c8, 256)), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, gate, hw, pixels, c8,
@@ -359,9 +495,15 @@ int vtb_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weigh
   launch_pdl(hw_reduce_kernel<true>, dim3(dim3((c8 + 31) / 32, n)), dim3(256), 0, st, (const __nv_bfloat16*)dout, lddo,
                                                                   (const __nv_bfloat16*)x, ldx, hw, c8, dgate, c, 1.f);
   launch_pdl(ese_dz_kernel, dim3((unsigned)((nc + 255) / 256)), dim3(256), 0, st, dgate, z, nc, dz);
-  launch_pdl(ese_dpool_kernel, dim3((unsigned)((nc + 255) / 256)), dim3(256), 0, st, dz, weight, n, c, 1.f / hw, dpool);
-  launch_pdl(ese_dw_kernel, dim3((unsigned)(((long long)c * c + 255) / 256)), dim3(256), 0, st, dz, pool, n, c, dweight, dbias,
-                                                                            accumulate_dw);
+  // dpool[n][ci] = (1/hw) sum_co dz[n][co] * bf16(W[co][ci])
+  launch_pdl(small_gemm_kernel<false, true, 0>, dim3((c + 31) / 32, (n + 31) / 32), dim3(256), 0, st, (const float*)dz,
+             (long long)c, 1LL, weight, (long long)c, 1LL, n, c, c, 1.f / hw, dpool, (long long)c, (const float*)nullptr,
+             (float*)nullptr, 0);
+  // dW[co][ci] (+)= sum_n dz[n][co] * bf16(pool[n][ci]);  db[co] (+)= sum_n dz[n][co]
+  launch_pdl(small_gemm_kernel<false, true, 2>, dim3((c + 31) / 32, (c + 31) / 32), dim3(256), 0, st, (const float*)dz, 1LL,
+             (long long)c, pool, (long long)c, 1LL, c, c, n, 1.f, dweight, (long long)c, (const float*)nullptr,
+             (float*)nullptr, accumulate_dw);
+  launch_pdl(ese_dbias_kernel, dim3((c + 255) / 256), dim3(256), 0, st, (const float*)dz, n, c, dbias, accumulate_dw);
   const long long pixels = (long long)n * hw;
   if (accumulate_dx)
     launch_pdl(ese_bwd_dx_kernel<true>, dim3(vgrid(pixels * c8, 256)), dim3(256), 0, st, (const __nv_bfloat16*)dout, lddo, gate, dpool, hw,
@@ -369,7 +511,7 @@ int vtb_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weigh
   else
     launch_pdl(ese_bwd_dx_kernel<false>, dim3(vgrid(pixels * c8, 256)), dim3(256), 0, st, (const __nv_bfloat16*)dout, lddo, gate, dpool, hw,
                                                                       pixels, c8, (__nv_bfloat16*)dx, lddx);
-  count_launch(5);
+  count_launch(6);
   return check_cuda((int)cudaGetLastError(), "ese backward kernels");
 }
 

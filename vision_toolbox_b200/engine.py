@@ -89,6 +89,7 @@ class ConvOp:
 class PoolOp:
     x: TView
     out: TView
+    idx: Optional[TView] = None   # saved argmax positions (uint8 per element), only when gradients are needed
     kind: str = "pool"
 
 
@@ -217,7 +218,9 @@ class Graph:
         if out is None:
             out = self.new_tensor(x.n, ho, wo, x.c)
         x.consumers.append(len(self.ops))
-        self.ops.append(PoolOp(x, out))
+        # one byte per output element, carved out of the arena as a (c/2)-channel bf16 tensor
+        idx = self.new_tensor(x.n, ho, wo, _round_up(x.c // 2, 8), "raw") if self.need_grad else None
+        self.ops.append(PoolOp(x, out, idx))
         return out
 
     def ese(self, mod, x: TView, residual: Optional[TView] = None, out: Optional[TView] = None) -> TView:
@@ -408,7 +411,9 @@ class Runner:
             elif op.kind == "pool":
                 xx, oo = op.x, op.out
                 check(L.vtb_maxpool3s2_fwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h, xx.w, xx.c,
-                                           abase + oo.byte_offset(), oo.ld, st), "vtb_maxpool3s2_fwd")
+                                           abase + oo.byte_offset(), oo.ld,
+                                           abase + op.idx.byte_offset() if op.idx is not None else 0, st),
+                      "vtb_maxpool3s2_fwd")
             elif op.kind == "ese":
                 xx, oo, rr = op.x, op.out, op.residual
                 lin = op.mod.linear
@@ -573,7 +578,9 @@ class Runner:
                 xx, oo = op.x, op.out
                 if not (xx.is_input and not run.x_requires_grad):
                     check(L.vtb_maxpool3s2_bwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h, xx.w, xx.c, gp(oo), gld(oo),
-                                               gp(xx), gld(xx), int(is_init(xx)), st), "vtb_maxpool3s2_bwd")
+                                               gp(xx), gld(xx), int(is_init(xx)),
+                                               abase + op.idx.byte_offset() if op.idx is not None else 0, st),
+                          "vtb_maxpool3s2_bwd")
                     mark(xx)
             elif op.kind == "ese":
                 xx, oo, rr = op.x, op.out, op.residual
