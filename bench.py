@@ -111,7 +111,7 @@ class ProfilingLib:
     def __getattr__(self, name):
         fn = getattr(self._real, name)
         if not name.startswith("vtb_") or name in ("vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows",
-                                                   "vtb_conv_wgrad_workspace_bytes", "vtb_launch_count"):
+                                                   "vtb_conv_wgrad_workspace_bytes", "vtb_launch_count", "vtb_pack_job_blocks"):
             return fn
 
         def wrapped(*args):
@@ -131,6 +131,18 @@ def conv_flops(geom, cin_real=None) -> float:
     wo = (g.w + 2 * g.pad - g.k) // g.stride + 1
     cin = g.cin if g.cin > 16 or cin_real is None else cin_real
     return 2.0 * g.n * ho * wo * g.cout * g.k * g.k * cin
+
+
+def conv_bytes(geom, name: str) -> float:
+    """Algorithmic HBM bytes of one conv launch: read the bf16 input view once, write the bf16
+    output once, read the bf16 weights; wgrad reads both activations and writes the fp32 weight gradient."""
+    g = geom._obj if hasattr(geom, "_obj") else geom
+    ho = (g.h + 2 * g.pad - g.k) // g.stride + 1
+    wo = (g.w + 2 * g.pad - g.k) // g.stride + 1
+    a_in, a_out, w = g.n * g.h * g.w * g.cin * 2.0, g.n * ho * wo * g.cout * 2.0, g.cout * g.k * g.k * g.cin * 2.0
+    if name == "vtb_conv_wgrad":
+        return a_in + a_out + 2.0 * w
+    return a_in + a_out + w
 
 
 def reference_arm(args, rank: int, world: int) -> None:
@@ -366,12 +378,22 @@ def main() -> None:
         r.L = _lib.lib()
     if rank == 0:
         agg = {}
+        pk = peaks()
+        # every conv_igemm launch is also classified by the roofline that bounds ITS shape (algorithmic flops / bytes
+        # against the measured peaks): the 3x3 layers with >= 128 channels are tensor-bound, stems / 1x1 / narrow
+        # layers are HBM-bound; "roofline" below is the kernel as a whole, "roofline.split" the two classes apart
+        split = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}   # ms, flops, bytes, launches
         for name, geom, a, b, _ in prof.records:
             t = a.elapsed_time(b)
-            fl = conv_flops(geom) if geom is not None and name in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_wgrad") else 0.0
+            is_conv = geom is not None and name in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_wgrad")
+            fl = conv_flops(geom) if is_conv else 0.0
             d = agg.setdefault(name, [0.0, 0.0, 0])
             d[0] += t; d[1] += fl; d[2] += 1
-        pk = peaks()
+            if is_conv and name != "vtb_conv_wgrad":
+                by = conv_bytes(geom, name)
+                cls = "tensor" if fl / (pk["tflops"] * 1e12) >= by / (pk["gbs"] * 1e9) else "hbm"
+                c = split[cls]
+                c[0] += t; c[1] += fl; c[2] += by; c[3] += 1
         conv_calls = [agg.get(k, [0, 0, 0]) for k in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad")]
         igemm_ms = sum(v[0] for v in conv_calls)
         igemm_fl = sum(v[1] for v in conv_calls)
@@ -385,6 +407,12 @@ def main() -> None:
                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
                     "peak_source": pk["source"] + ", sustained cuBLAS bf16", "launches": igemm_n,
                     "avg_launch_ms": igemm_ms / max(igemm_n, 1)}
+        tb, hb = split["tensor"], split["hbm"]
+        roofline["split"] = {
+            "tensor_bound": {"launches": tb[3], "ms": round(tb[0], 3), "achieved": tb[1] / max(tb[0], 1e-9) / 1e9,
+                             "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tb[1] / max(tb[0], 1e-9) / 1e9 / pk["tflops"]},
+            "hbm_bound": {"launches": hb[3], "ms": round(hb[0], 3), "achieved": hb[2] / max(hb[0], 1e-9) / 1e6,
+                          "peak": pk["gbs"], "unit": "GB/s", "frac": hb[2] / max(hb[0], 1e-9) / 1e6 / pk["gbs"]}}
         tot = sum(v[0] for v in agg.values())
         breakdown = {k: {"ms": round(v[0], 3), "share": round(v[0] / tot, 3), "calls": v[2],
                          **({"tflops": round(v[1] / (v[0] / 1e3) / 1e12, 1)} if v[1] else {})}

@@ -58,6 +58,21 @@ size_t vtb_conv_wgrad_workspace_bytes(const VtbConv* c);
  * tensor-core kernels consume: wf[cout][k*k][cin] (fprop / wgrad K-order) and wd[cin][k*k][cout] (dgrad).
  * cin_real <= c->cin is the channel count of the fp32 tensor (3 for the image stem). wd may be NULL. */
 int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* wf, void* wd, void* stream);
+/* The same re-pack for every convolution of a model in ONE launch.  The host code runs it at the start of every forward:
+ * a parameter's torch version counter cannot tell whether the weights changed (fused optimizers such as
+ * torch.optim.SGD(fused=True) update parameters without bumping it), so the bf16 operands are always rebuilt from the
+ * fp32 masters (reads 4 B + writes 2 x 2 B per weight: ~35 us for CSPDarknet-53).
+ * jobs_device: njobs VtbPackJob records in DEVICE memory, first_block = running sum of vtb_pack_job_blocks() over the
+ * preceding jobs (first job: 0); total_blocks = the sum over all jobs. */
+typedef struct VtbPackJob {
+  const float* w;        /* OIHW fp32 master, [cout][cin_real][kk] */
+  void* wf;              /* bf16 [cout][kk][cin] */
+  void* wd;              /* bf16 [cin][kk][cout], may be NULL */
+  int cout, cin_real, cin, kk;
+  long long first_block;
+} VtbPackJob;
+long long vtb_pack_job_blocks(int cout, int cin, int kk);
+int vtb_pack_weights(const VtbPackJob* jobs_device, int njobs, long long total_blocks, void* stream);
 
 /* ---- convolution: replaces aten::convolution (cuDNN) at components.py:26-35 ----
  * y[n,ho,wo,:] = conv(x)  (bf16, fp32 accumulate).
@@ -202,6 +217,48 @@ int vtb_ese_fwd(const void* x, int ldx, int n, int hw, int c, const float* weigh
 int vtb_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weight, const float* pool, const float* z,
                 const float* gate, const void* dout, int lddo, void* dx, int lddx, int accumulate_dx, float* dweight,
                 float* dbias, int accumulate_dw, float* scratch, void* stream);
+
+/* ---- fp32 parity mode ------------------------------------------------------------------------------------------------
+ * BASELINE north_star: "forward feature maps and gradients within 1e-4 relative in fp32 mode" - the reference run WITHOUT
+ * autocast (components.py:26-39 in fp32).  Same dataflow and view conventions as above, but every activation / gradient
+ * view is fp32 (ld in elements, 4-byte aligned, any channel count), weights are read straight from the OIHW fp32 master
+ * (no packing), contractions are FMA loops on the CUDA cores in a fixed order, statistics are accumulated in fp64.
+ * BatchNorm finalisation reuses vtb_bn_finalize / vtb_bn_bwd_finalize with their `sums` (double) inputs, so SyncBN in this
+ * mode is one all-reduce of `sums` between the two calls.  Selected from Python with vision_toolbox_b200.precision("fp32"). */
+int vtb_f32_nchw_to_nhwc(const float* x, int n, int c, int h, int w, float* out, int cpad, void* stream);
+/* aten::convolution / convolution_backward at components.py:26-35, fp32. cin_real <= c->cin as in vtb_pack_weight. */
+int vtb_f32_conv_fprop(const VtbConv* c, const float* x, int ldx, const float* w_oihw, int cin_real, float* y, int ldy,
+                       void* stream);
+int vtb_f32_conv_dgrad(const VtbConv* c, const float* dy, int lddy, const float* w_oihw, int cin_real, float* dx, int lddx,
+                       int accumulate, void* stream);
+size_t vtb_f32_conv_wgrad_workspace_bytes(const VtbConv* c);
+int vtb_f32_conv_wgrad(const VtbConv* c, const float* dy, int lddy, const float* x, int ldx, void* workspace, float* dw_oihw,
+                       int cin_real, int accumulate, void* stream);
+/* BatchNorm2d statistics (components.py:36): sums[c][2] = (sum y, sum y*y) in double; partial: vtb_f32_bn_rows(pixels, c)
+ * * c * 2 doubles of scratch.  Follow with vtb_bn_finalize(NULL, 0, sums, ...). */
+int vtb_f32_bn_rows(long long pixels, int c);
+int vtb_f32_bn_stats(const float* y, int ldy, long long pixels, int c, double* partial, double* sums, void* stream);
+/* out = [relu]((y - mean) * invstd * gamma + beta) [+ residual]  (components.py:36-39, darknet.py:28, vovnet.py:60-61) */
+int vtb_f32_bn_act(const float* y, int ldy, long long pixels, int c, const float* mean, const float* invstd, const float* gamma,
+                   const float* beta, int relu, const float* residual, int ldr, float* out, int ldo, void* stream);
+/* BatchNorm2d + ReLU backward: sums[c][2] = (sum dz, sum dz*xhat) in double -> vtb_bn_bwd_finalize(NULL, 0, sums, ...) ->
+ * dy = gamma * invstd * (dz - coef0 - xhat * coef1). */
+int vtb_f32_bn_bwd_reduce(const float* dout, int lddo, const float* y, int ldy, long long pixels, int c, const float* mean,
+                          const float* invstd, const float* gamma, const float* beta, int relu, double* partial, double* sums,
+                          void* stream);
+int vtb_f32_bn_bwd_apply(const float* dout, int lddo, const float* y, int ldy, long long pixels, int c, const float* mean,
+                         const float* invstd, const float* gamma, const float* beta, int relu, const float* coef, float* dy,
+                         int lddy, void* stream);
+/* fp32 twins of vtb_grad_add / vtb_maxpool3s2_* / vtb_ese_* (identical signatures; idx is required by the pool backward) */
+int vtb_f32_grad_add(void* dst, int ldd, const void* src, int lds, long long pixels, int c, int accumulate, void* stream);
+int vtb_f32_maxpool3s2_fwd(const void* x, int ldx, int n, int h, int w, int c, void* out, int ldo, void* idx, void* stream);
+int vtb_f32_maxpool3s2_bwd(const void* x, int ldx, int n, int h, int w, int c, const void* dout, int lddo, void* dx, int lddx,
+                           int accumulate, const void* idx, void* stream);
+int vtb_f32_ese_fwd(const void* x, int ldx, int n, int hw, int c, const float* weight, const float* bias, const void* residual,
+                    int ldr, void* out, int ldo, float* pool, float* z, float* gate, void* stream);
+int vtb_f32_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weight, const float* pool, const float* z,
+                    const float* gate, const void* dout, int lddo, void* dx, int lddx, int accumulate_dx, float* dweight,
+                    float* dbias, int accumulate_dw, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -113,3 +113,33 @@ def test_forward_is_deterministic_and_repeatable():
         b = module_outputs(m, x)
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_training_steps_use_updated_weights(graph):
+    """The bf16 operand packs must follow the fp32 masters: torch's fused SGD updates parameters WITHOUT bumping
+    Parameter._version, so after a few optimizer steps the forward has to equal the oracle run on the CURRENT
+    state_dict (and differ clearly from the run on the initial one).  Eager steps and CUDA-graph replays."""
+    from vision_toolbox_b200.parallel import Trainer
+
+    name = "model_cspdarknet"
+    g = load_golden(name)
+    m = _native(name, g)
+    head = torch.nn.Linear(32, 10).cuda()
+    tr = Trainer(m, head, lr=0.2, momentum=0.9, weight_decay=0.0)
+    x = g["x"].cuda()
+    y = torch.tensor([3, 7], device="cuda")
+    if graph:
+        tr.enable_cuda_graph(x, y, warmup=2)
+    losses = [float(tr.step(x, y)) for _ in range(6)]
+    torch.cuda.synchronize()
+    assert losses[-1] < 0.7 * losses[0], losses          # two samples, ten classes: this must overfit quickly
+    with torch.no_grad():
+        outs = module_outputs(m, x)
+    sd_now = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        o_now = oracle_outputs(name, sd_now, g["x"], True, "bf16")
+        o_old = oracle_outputs(name, g["state_dict"], g["x"], True, "bf16")
+    for o, a, b in zip(outs, o_now, o_old):
+        assert rel_err(o.float(), a) < BF16_TOL, rel_err(o.float(), a)
+        assert rel_err(b, a) > 5 * BF16_TOL, "weights barely moved: the test would not see stale packs"

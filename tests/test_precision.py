@@ -1,0 +1,59 @@
+"""Host-side logic of the precision switch (bf16 tensor-core path | fp32 parity mode): no GPU needed."""
+import pytest
+import torch
+
+import vision_toolbox_b200 as vtb
+from vision_toolbox_b200 import engine
+from vision_toolbox_b200.backbones import Darknet, VoVNet
+from vision_toolbox_b200.backbones.darknet import CSPDarknetStage
+
+
+def test_precision_api():
+    assert vtb.get_precision() == "bf16"          # default: the tensor-core path
+    with vtb.precision("fp32"):
+        assert vtb.get_precision() == "fp32" and engine._resolve_f32()
+        with vtb.precision("bf16"):
+            assert not engine._resolve_f32()
+        assert vtb.get_precision() == "fp32"
+    assert vtb.get_precision() == "bf16"
+    with pytest.raises(KeyError):
+        vtb.set_precision("fp16")
+    with vtb.precision("auto"):                   # what the reference would compute for the same call
+        assert engine._resolve_f32()
+        if torch.cuda.is_available():             # torch disables CUDA autocast on a machine without CUDA
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                assert not engine._resolve_f32()
+
+
+def _plan(m, shape, training, need_grad, f32):
+    m.train(training)
+    g = engine.Graph(training, need_grad, f32)
+    outs = m._emit(g, g.input_image(*shape))
+    for t in ([outs] if isinstance(outs, engine.TView) else outs):
+        g.mark_output(t)
+    g.finalize()
+    return g
+
+
+@pytest.mark.parametrize("build", [lambda: Darknet(16, [(1, 32), (2, 32)], CSPDarknetStage),
+                                   lambda: VoVNet(32, [(1, 16, 2, 32), (2, 16, 3, 32)], ese=True)])
+def test_fp32_plan_mirrors_bf16_plan(build):
+    m = build()
+    g16 = _plan(m, (2, 3, 32, 32), True, True, False)
+    g32 = _plan(m, (2, 3, 32, 32), True, True, True)
+    assert len(g16.ops) == len(g32.ops) and len(g16.buffers) == len(g32.buffers)
+    assert all(b.esize == 2 for b in g16.buffers) and all(b.esize == 4 for b in g32.buffers)
+    for a, b in zip(g16.ops, g32.ops):
+        assert a.kind == b.kind
+        assert (a.out.coff, a.out.c, a.out.ld) == (b.out.coff, b.out.c, b.out.ld)   # same concat slices
+    assert g32.grad_bytes >= 2 * g16.grad_bytes - 1024 * len(g16.buffers)
+    assert g32.dy_bytes == 2 * g16.dy_bytes
+    # views never overlap inside the arena
+    spans = sorted((b.offset, b.offset + b.nbytes) for b in g32.buffers)
+    assert all(e0 <= s1 for (_, e0), (s1, _) in zip(spans, spans[1:]))
+    # eval without gradients: bf16 uses the fused epilogue (no raw conv output), fp32 keeps conv and normalise apart
+    e16 = _plan(m, (2, 3, 32, 32), False, False, False)
+    e32 = _plan(m, (2, 3, 32, 32), False, False, True)
+    assert e16.fused_eval and not e32.fused_eval
+    assert all(op.y is None for op in e16.ops if op.kind == "conv")
+    assert all(op.y is not None for op in e32.ops if op.kind == "conv")

@@ -5,6 +5,7 @@ gau-nernst/vision-toolbox.  ``from vision_toolbox_b200 import backbones`` mirror
 from . import backbones, components
 from .backbones import *  # noqa: F401,F403
 from .components import *  # noqa: F401,F403
+from .engine import get_precision, precision, set_precision  # noqa: F401  (bf16 tensor-core path | fp32 parity mode)
 
 __version__ = "0.1.0"
 

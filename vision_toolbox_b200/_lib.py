@@ -30,6 +30,13 @@ class VtbBnTrain(C.Structure):
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("tickets", C.c_void_p), ("sync", C.c_void_p)]
 
 
+class VtbPackJob(C.Structure):
+    """struct VtbPackJob of include/vtb.h (one convolution's weight re-pack inside the batched launch)."""
+
+    _fields_ = [("w", C.c_void_p), ("wf", C.c_void_p), ("wd", C.c_void_p), ("cout", C.c_int), ("cin_real", C.c_int),
+                ("cin", C.c_int), ("kk", C.c_int), ("first_block", C.c_longlong)]
+
+
 class VtbSyncBn(C.Structure):
     """struct VtbSyncBn of include/vtb.h (peer-mapped SyncBN exchange buffers)."""
 
@@ -53,6 +60,8 @@ SIGNATURES = {
     "vtb_conv_stats_rows": (_i, [_cp]),
     "vtb_conv_wgrad_workspace_bytes": (C.c_size_t, [_cp]),
     "vtb_pack_weight": (_i, [_cp, _p, _i, _p, _p, _p]),
+    "vtb_pack_job_blocks": (_ll, [_i, _i, _i]),
+    "vtb_pack_weights": (_i, [_p, _i, _ll, _p]),
     "vtb_conv_fprop": (_i, [_cp, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _p]),
     "vtb_conv_fprop_bn": (_i, [_cp, _p, _i, _p, _p, _i, _p, C.POINTER(VtbBnTrain), _p]),
     "vtb_conv_dgrad": (_i, [_cp, _p, _i, _p, _p, _i, _i, _p]),
@@ -76,6 +85,22 @@ SIGNATURES = {
     "vtb_maxpool3s2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p]),
     "vtb_ese_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
     "vtb_ese_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i, _i, _p, _p, _i, _p, _p]),
+    # fp32 parity mode (csrc/parity_f32.cu)
+    "vtb_f32_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),
+    "vtb_f32_conv_fprop": (_i, [_cp, _p, _i, _p, _i, _p, _i, _p]),
+    "vtb_f32_conv_dgrad": (_i, [_cp, _p, _i, _p, _i, _p, _i, _i, _p]),
+    "vtb_f32_conv_wgrad_workspace_bytes": (C.c_size_t, [_cp]),
+    "vtb_f32_conv_wgrad": (_i, [_cp, _p, _i, _p, _i, _p, _p, _i, _i, _p]),
+    "vtb_f32_bn_rows": (_i, [_ll, _i]),
+    "vtb_f32_bn_stats": (_i, [_p, _i, _ll, _i, _p, _p, _p]),
+    "vtb_f32_bn_act": (_i, [_p, _i, _ll, _i, _p, _p, _p, _p, _i, _p, _i, _p, _i, _p]),
+    "vtb_f32_bn_bwd_reduce": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _p]),
+    "vtb_f32_bn_bwd_apply": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p]),
+    "vtb_f32_grad_add": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p]),
+    "vtb_f32_maxpool3s2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
+    "vtb_f32_maxpool3s2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p]),
+    "vtb_f32_ese_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
+    "vtb_f32_ese_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i, _i, _p, _p, _i, _p, _p]),
 }
 
 _lib = None

@@ -153,6 +153,35 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
+// The same re-pack for EVERY convolution of a plan in one launch (VtbPackJob table in device memory): block b serves the
+// job with the largest first_block <= b and packs kPackPerBlock elements of it.
+constexpr int kPackPerBlock = 2048;
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const VtbPackJob* __restrict__ jobs, int njobs) {
+  pdl_wait();
+  pdl_trigger();
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_block <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const VtbPackJob J = jobs[lo];
+  const long long total = (long long)J.cout * J.kk * J.cin;
+  const long long base = ((long long)blockIdx.x - J.first_block) * kPackPerBlock;
+  const long long end = (base + kPackPerBlock < total) ? base + kPackPerBlock : total;
+  const float* __restrict__ w = J.w;
+  __nv_bfloat16* __restrict__ wf = reinterpret_cast<__nv_bfloat16*>(J.wf);
+  __nv_bfloat16* __restrict__ wd = reinterpret_cast<__nv_bfloat16*>(J.wd);
+  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+    const int ci = (int)(i % J.cin);
+    const int t = (int)((i / J.cin) % J.kk);
+    const int co = (int)(i / ((long long)J.cin * J.kk));
+    const float v = (ci < J.cin_real) ? w[((long long)co * J.cin_real + ci) * J.kk + t] : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    wf[i] = b;
+    if (wd) wd[((long long)ci * J.kk + t) * J.cout + co] = b;
+  }
+}
+
 // dw[co][ci][t] (+)= sum_split ws[split][co][t*cin + ci].  One block per (output channel, slice of EW <= 64 input
 // channels).  The 256 threads are EW channel lanes x SG split groups: every group sums its share of the splits with
 // coalesced reads (many independent loads in flight: the split count, not the tile, carries the parallelism for small
@@ -297,6 +326,21 @@ int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* w
   return check_cuda((int)launch_pdl(pack_weight_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, w_oihw, c->cout,
                                     cin_real, c->cin, c->k * c->k, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd),
                     "pack_weight_kernel");
+}
+
+long long vtb_pack_job_blocks(int cout, int cin, int kk) {
+  if (cout <= 0 || cin <= 0 || kk <= 0) return fail(VTB_EINVAL, "vtb_pack_job_blocks: bad arguments");
+  const long long total = (long long)cout * kk * cin;
+  return (total + kPackPerBlock - 1) / kPackPerBlock;
+}
+
+int vtb_pack_weights(const VtbPackJob* jobs_device, int njobs, long long total_blocks, void* stream) {
+  if (!jobs_device || njobs <= 0 || total_blocks <= 0 || total_blocks > 0x7fffffffLL)
+    return fail(VTB_EINVAL, "vtb_pack_weights: bad arguments");
+  count_launch(1);
+  return check_cuda((int)launch_pdl(pack_weights_batched_kernel, dim3((unsigned)total_blocks), dim3(256), 0, (cudaStream_t)stream,
+                                    jobs_device, njobs),
+                    "pack_weights_batched_kernel");
 }
 
 static int fprop_impl(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,

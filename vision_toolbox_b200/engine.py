@@ -21,6 +21,50 @@ from . import _lib
 from ._lib import VtbBnTrain, VtbConv, check
 
 BF16 = 2
+F32 = 4
+
+# ----------------------------------------------------------------------------------------------------
+# precision mode
+#   "bf16" (default): NHWC bf16 activations, tcgen05 implicit-GEMM kernels - the reference under torch.autocast(bf16)
+#   "fp32"          : NHWC fp32 activations, CUDA-core FMA kernels of csrc/parity_f32.cu - the reference WITHOUT autocast,
+#                     the north star's "fp32 mode" (1e-4 relative); a parity instrument, not a fast path
+#   "auto"          : what the reference would do with the same call: bf16 inside torch.autocast(dtype=bfloat16), else fp32
+# ----------------------------------------------------------------------------------------------------
+import contextlib as _contextlib
+import os as _os
+
+_PRECISIONS = ("bf16", "fp32", "auto")
+_precision = _os.environ.get("VTB_PRECISION", "bf16")
+if _precision not in _PRECISIONS:
+    raise ValueError(f"VTB_PRECISION must be one of {_PRECISIONS}, got {_precision!r}")
+
+
+def set_precision(mode: str) -> None:
+    global _precision
+    if mode not in _PRECISIONS:
+        raise KeyError(f"unknown precision {mode!r}; expected one of {_PRECISIONS}")
+    _precision = mode
+
+
+def get_precision() -> str:
+    return _precision
+
+
+@_contextlib.contextmanager
+def precision(mode: str):
+    """``with precision("fp32"): model(x)`` - run CUDA tensors through the fp32 parity kernels."""
+    old = _precision
+    set_precision(mode)
+    try:
+        yield
+    finally:
+        set_precision(old)
+
+
+def _resolve_f32() -> bool:
+    if _precision == "auto":
+        return not (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+    return _precision == "fp32"
 
 
 def _round_up(a: int, b: int) -> int:
@@ -33,8 +77,9 @@ def _round_up(a: int, b: int) -> int:
 class Buffer:
     """A dense NHWC bf16 allocation of `pixels` x `c` elements inside the activation (or gradient) arena."""
 
-    def __init__(self, idx: int, n: int, h: int, w: int, c: int, kind: str):
+    def __init__(self, idx: int, n: int, h: int, w: int, c: int, kind: str, esize: int = BF16):
         self.idx, self.n, self.h, self.w, self.c, self.kind = idx, n, h, w, c, kind
+        self.esize = esize  # bytes per element: 2 (bf16 mode) or 4 (fp32 parity mode)
         self.offset = -1  # bytes, assigned by Graph.finalize
         self.exclusive_owner: Optional["TView"] = None
 
@@ -44,7 +89,7 @@ class Buffer:
 
     @property
     def nbytes(self) -> int:
-        return self.pixels * self.c * BF16
+        return self.pixels * self.c * self.esize
 
 
 class TView:
@@ -64,7 +109,7 @@ class TView:
     pixels = property(lambda s: s.buf.pixels)
 
     def byte_offset(self) -> int:
-        return self.buf.offset + self.coff * BF16
+        return self.buf.offset + self.coff * self.buf.esize
 
     def __repr__(self):
         return f"TView(buf{self.buf.idx}[{self.coff}:{self.coff + self.c}] {self.n}x{self.h}x{self.w} ld{self.ld})"
@@ -108,11 +153,14 @@ class EseOp:
 # graph builder
 # ----------------------------------------------------------------------------------------------------
 class Graph:
-    def __init__(self, training: bool, need_grad: bool):
+    def __init__(self, training: bool, need_grad: bool, f32: bool = False):
         self.training = training
         self.need_grad = need_grad
+        self.f32 = f32
+        self.esize = F32 if f32 else BF16
         # BN uses batch statistics only in training mode; the 1-kernel fused epilogue needs frozen statistics
-        self.fused_eval = (not training) and (not need_grad)
+        # (fp32 parity mode keeps conv and normalise separate: it mirrors the reference's op order)
+        self.fused_eval = (not training) and (not need_grad) and (not f32)
         self.buffers: list[Buffer] = []
         self.ops: list[Any] = []
         self.params: list[torch.Tensor] = []
@@ -126,7 +174,7 @@ class Graph:
 
     # -- allocation
     def new_buffer(self, n: int, h: int, w: int, c: int, kind: str = "act") -> Buffer:
-        b = Buffer(len(self.buffers), n, h, w, c, kind)
+        b = Buffer(len(self.buffers), n, h, w, c, kind, self.esize)
         self.buffers.append(b)
         return b
 
@@ -193,22 +241,31 @@ class Graph:
         op.pidx = len(self.params)
         self.params += [conv.weight, norm.weight, norm.bias]
         L = _lib.lib()
-        rows_f = L.vtb_conv_stats_rows(C.byref(geom))
-        if rows_f <= 0:
-            check(-1, "vtb_conv_stats_rows")
-        rows_b = L.vtb_bn_bwd_rows(out.pixels, cout)            # rows written by vtb_bn_bwd_reduce
-        rows_b_alloc = max(rows_b, L.vtb_bn_bwd_fused_rows(out.pixels, cout))   # scratch also serves the fused kernel
+        if self.f32:
+            # fp32 parity mode: two-level fp64 sums (vtb_f32_bn_stats / vtb_f32_bn_bwd_reduce), rows of double[c][2]
+            rows_f = rows_b = rows_b_alloc = L.vtb_f32_bn_rows(out.pixels, cout)
+            if rows_f <= 0:
+                check(-1, "vtb_f32_bn_rows")
+            per_row = cout * 4
+        else:
+            rows_f = L.vtb_conv_stats_rows(C.byref(geom))
+            if rows_f <= 0:
+                check(-1, "vtb_conv_stats_rows")
+            rows_b = L.vtb_bn_bwd_rows(out.pixels, cout)            # rows written by vtb_bn_bwd_reduce
+            rows_b_alloc = max(rows_b, L.vtb_bn_bwd_fused_rows(out.pixels, cout))   # scratch also serves the fused kernel
+            per_row = cout * 2
         for name in ("mean", "invstd", "scale", "shift"):
             self._stat(op, name, cout)
-        self._stat(op, "partial_f", rows_f * cout * 2)
+        self._stat(op, "partial_f", rows_f * per_row)
         self._stat(op, "sums", cout * 4)  # double[c][2]
         if self.need_grad:
-            self._stat(op, "partial_b", (rows_b_alloc + 1) * cout * 2)   # + one row: global means under SyncBN
+            self._stat(op, "partial_b", (rows_b_alloc + 1) * per_row)   # + one row: global means under SyncBN
             self._stat(op, "coef", cout * 2)
             self._stat(op, "sums_b", cout * 4)
             self._stat(op, "lsums_b", cout * 4)
-            self.ws_bytes = max(self.ws_bytes, int(L.vtb_conv_wgrad_workspace_bytes(C.byref(geom))))
-            self.dy_bytes = max(self.dy_bytes, out.pixels * cout * BF16)
+            wsq = L.vtb_f32_conv_wgrad_workspace_bytes if self.f32 else L.vtb_conv_wgrad_workspace_bytes
+            self.ws_bytes = max(self.ws_bytes, int(wsq(C.byref(geom))))
+            self.dy_bytes = max(self.dy_bytes, out.pixels * cout * self.esize)
         op.rows_f, op.rows_b = rows_f, rows_b
         self.ops.append(op)
         return out
@@ -219,7 +276,7 @@ class Graph:
             out = self.new_tensor(x.n, ho, wo, x.c)
         x.consumers.append(len(self.ops))
         # one byte per output element, carved out of the arena as a (c/2)-channel bf16 tensor
-        idx = self.new_tensor(x.n, ho, wo, _round_up(x.c // 2, 8), "raw") if self.need_grad else None
+        idx = self.new_tensor(x.n, ho, wo, _round_up(-(-x.c // self.esize), 8), "raw") if self.need_grad else None
         self.ops.append(PoolOp(x, out, idx))
         return out
 
@@ -353,34 +410,72 @@ class Runner:
         self.grad_sink = False
         # ticket counters of the fused conv + BatchNorm-finalize kernels (self-cleaning, shared by all layers)
         self.tickets = torch.zeros(512, dtype=torch.int32, device=device)   # [0,256): conv kernels, [256,512): BN bwd
+        # element type of the activation / gradient arenas and the entry points whose two precisions share a signature
+        L = self.L
+        self.f32 = graph.f32
+        self._conv_ops = [op for op in graph.ops if op.kind == "conv"]
+        self._pack_key, self._pack_jobs, self._pack_blocks, self._pack_srcs = None, None, 0, None
+        self.tdtype = torch.float32 if self.f32 else torch.bfloat16
+        self.fn_grad_add = L.vtb_f32_grad_add if self.f32 else L.vtb_grad_add
+        self.fn_to_nhwc = L.vtb_f32_nchw_to_nhwc if self.f32 else L.vtb_nchw_to_nhwc
+        self.fn_pool_fwd = L.vtb_f32_maxpool3s2_fwd if self.f32 else L.vtb_maxpool3s2_fwd
+        self.fn_pool_bwd = L.vtb_f32_maxpool3s2_bwd if self.f32 else L.vtb_maxpool3s2_bwd
+        self.fn_ese_fwd = L.vtb_f32_ese_fwd if self.f32 else L.vtb_ese_fwd
+        self.fn_ese_bwd = L.vtb_f32_ese_bwd if self.f32 else L.vtb_ese_bwd
 
     # -- helpers
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _refresh_packs(self, st: int) -> None:
+        """Rebuild the bf16 operand packs (``[Cout][tap][Cin]`` for fprop / wgrad order, ``[Cin][tap][Cout]`` for dgrad) of
+        EVERY convolution of the plan from the fp32 master weights: one launch at the start of every forward.
+
+        Not cached on ``Parameter._version``: fused optimizers (``torch.optim.SGD(fused=True)``, fused AdamW) update
+        parameters in place WITHOUT bumping the version counter, so a version-keyed cache silently serves stale weights.
+        """
+        L = self.L
+        convs = self._conv_ops
+        if not convs:
+            return
+        srcs = []
+        for op in convs:
+            w = op.mod.conv.weight.detach()
+            if w.dtype != torch.float32 or not w.is_contiguous():
+                w = w.float().contiguous()
+            srcs.append(w)
+        key = tuple(w.data_ptr() for w in srcs)
+        if key != self._pack_key:
+            jobs = (_lib.VtbPackJob * len(convs))()
+            blk = 0
+            for j, (op, w) in enumerate(zip(convs, srcs)):
+                g = op.geom
+                n = g.cout * g.k * g.k * g.cin
+                cache = op.mod.__dict__.get("_vtb_wpack")
+                if cache is None or cache[0].numel() != n or cache[0].device != w.device:
+                    cache = (torch.empty(n, dtype=torch.bfloat16, device=w.device),
+                             torch.empty(n, dtype=torch.bfloat16, device=w.device))
+                    op.mod.__dict__["_vtb_wpack"] = cache
+                jobs[j] = _lib.VtbPackJob(w.data_ptr(), cache[0].data_ptr(), cache[1].data_ptr(), g.cout, op.cin_real,
+                                          g.cin, g.k * g.k, blk)
+                nb = int(L.vtb_pack_job_blocks(g.cout, g.cin, g.k * g.k))
+                if nb <= 0:
+                    check(-1, "vtb_pack_job_blocks")
+                blk += nb
+            table = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
+            self._pack_jobs = table.to(self.device)
+            self._pack_blocks, self._pack_key = blk, key
+        self._pack_srcs = srcs   # converted copies (non-fp32 masters) must outlive the launch
+        check(L.vtb_pack_weights(self._pack_jobs.data_ptr(), len(convs), self._pack_blocks, st), "vtb_pack_weights")
+
     @staticmethod
-    def _packed(op: ConvOp, L, stream: int):
-        """bf16 re-pack of the fp32 master weight, refreshed whenever the parameter was modified in place."""
-        w = op.mod.conv.weight
-        cache = op.mod.__dict__.get("_vtb_wpack")
-        key = (w.data_ptr(), w._version, op.geom.cin)
-        if cache is None or cache[0] != key:
-            g = op.geom
-            n = g.cout * g.k * g.k * g.cin
-            wf = torch.empty(n, dtype=torch.bfloat16, device=w.device)
-            wd = torch.empty(n, dtype=torch.bfloat16, device=w.device)
-            wsrc = w.detach()
-            if wsrc.dtype != torch.float32 or not wsrc.is_contiguous():
-                wsrc = wsrc.float().contiguous()
-            check(L.vtb_pack_weight(C.byref(g), wsrc.data_ptr(), op.cin_real, wf.data_ptr(), wd.data_ptr(), stream),
-                  "vtb_pack_weight")
-            cache = (key, wf, wd, wsrc)
-            op.mod.__dict__["_vtb_wpack"] = cache
-        return cache[1], cache[2]
+    def _packed(op: ConvOp):
+        """(wf, wd) bf16 packs of this convolution, current as of the last forward of its module."""
+        return op.mod.__dict__["_vtb_wpack"]
 
     def view_tensor(self, arena: torch.Tensor, t: TView) -> torch.Tensor:
-        """Zero-copy logical-NCHW (channels_last strided) bf16 tensor over a view of the arena."""
-        base = arena[t.buf.offset : t.buf.offset + t.buf.nbytes].view(torch.bfloat16)
+        """Zero-copy logical-NCHW (channels_last strided) tensor over a view of the arena."""
+        base = arena[t.buf.offset : t.buf.offset + t.buf.nbytes].view(self.tdtype)
         ld = t.ld
         return base.as_strided((t.n, t.c, t.h, t.w), (t.h * t.w * ld, 1, t.w * ld, ld), base.storage_offset() + t.coff)
 
@@ -402,22 +497,27 @@ class Runner:
             xin = xin.float().contiguous()
         n, c, h, w = xin.shape
         t_in = g.input
-        check(L.vtb_nchw_to_nhwc(xin.data_ptr(), n, c, h, w, abase + t_in.byte_offset(), t_in.c, st), "vtb_nchw_to_nhwc")
+        check(self.fn_to_nhwc(xin.data_ptr(), n, c, h, w, abase + t_in.byte_offset(), t_in.c, st), "vtb_nchw_to_nhwc")
 
+        if not self.f32:
+            self._refresh_packs(st)
         world = self.dist.world if (self.dist is not None and self.dist.sync_bn) else 1
         for op in g.ops:
             if op.kind == "conv":
-                self._conv_forward(op, abase, sbase, run, st, world)
+                if self.f32:
+                    self._conv_forward_f32(op, abase, sbase, run, st, world)
+                else:
+                    self._conv_forward(op, abase, sbase, run, st, world)
             elif op.kind == "pool":
                 xx, oo = op.x, op.out
-                check(L.vtb_maxpool3s2_fwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h, xx.w, xx.c,
+                check(self.fn_pool_fwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h, xx.w, xx.c,
                                            abase + oo.byte_offset(), oo.ld,
                                            abase + op.idx.byte_offset() if op.idx is not None else 0, st),
                       "vtb_maxpool3s2_fwd")
             elif op.kind == "ese":
                 xx, oo, rr = op.x, op.out, op.residual
                 lin = op.mod.linear
-                check(L.vtb_ese_fwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h * xx.w, xx.c,
+                check(self.fn_ese_fwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h * xx.w, xx.c,
                                     lin.weight.data_ptr(), lin.bias.data_ptr(),
                                     0 if rr is None else abase + rr.byte_offset(), 0 if rr is None else rr.ld,
                                     abase + oo.byte_offset(), oo.ld, sbase + 4 * op.st["pool"], sbase + 4 * op.st["z"],
@@ -428,7 +528,7 @@ class Runner:
     def _conv_forward(self, op: ConvOp, abase: int, sbase: int, run: Run, st: int, world: int) -> None:
         g, L = self.g, self.L
         geom, norm = op.geom, op.mod.norm
-        wf, _ = self._packed(op, L, st)
+        wf, _ = self._packed(op)
         x, out, res = op.x, op.out, op.residual
         f = lambda name: sbase + 4 * op.st[name]
         cout = geom.cout
@@ -485,6 +585,98 @@ class Runner:
         check(L.vtb_bn_act(abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"), f("shift"), int(op.relu),
                            res_p, res_ld, abase + out.byte_offset(), out.ld, st), "vtb_bn_act")
 
+    def _conv_forward_f32(self, op: ConvOp, abase: int, sbase: int, run: Run, st: int, world: int) -> None:
+        """fp32 parity mode of one ConvNormAct (reference components.py:26-39 without autocast): conv -> fp64 statistics
+        (-> all-reduce of the sums under SyncBN) -> finalise -> normalise + ReLU (+ residual)."""
+        g, L = self.g, self.L
+        geom, norm, conv = op.geom, op.mod.norm, op.mod.conv
+        x, y, out, res = op.x, op.y, op.out, op.residual
+        f = lambda name: sbase + 4 * op.st[name]
+        cout = geom.cout
+        w = self._master_weight(op)
+        check(L.vtb_f32_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, w.data_ptr(), op.cin_real,
+                                   abase + y.byte_offset(), y.ld, st), "vtb_f32_conv_fprop")
+        if g.training:
+            mom = norm.momentum if norm.momentum is not None else 0.1
+            track = norm.track_running_stats and norm.running_mean is not None
+            rm = norm.running_mean.data_ptr() if track else 0
+            rv = norm.running_var.data_ptr() if track else 0
+            nbt = norm.num_batches_tracked.data_ptr() if track else 0
+            check(L.vtb_f32_bn_stats(abase + y.byte_offset(), y.ld, out.pixels, cout, f("partial_f"), f("sums"), st),
+                  "vtb_f32_bn_stats")
+            if world > 1:
+                self.dist.all_reduce_(run.stat_view_f64(op.st["sums"], cout * 2, sbase))
+            check(L.vtb_bn_finalize(0, 0, f("sums"), float(out.pixels) * world, cout, norm.weight.data_ptr(),
+                                    norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt, f("mean"), f("invstd"),
+                                    f("scale"), f("shift"), st), "vtb_bn_finalize")
+        else:
+            run.stat_view_f32(op.st["mean"], cout, sbase).copy_(norm.running_mean)
+            run.stat_view_f32(op.st["invstd"], cout, sbase).copy_(torch.rsqrt(norm.running_var + norm.eps))
+        check(L.vtb_f32_bn_act(abase + y.byte_offset(), y.ld, out.pixels, cout, f("mean"), f("invstd"),
+                               norm.weight.data_ptr(), norm.bias.data_ptr(), int(op.relu),
+                               0 if res is None else abase + res.byte_offset(), 0 if res is None else res.ld,
+                               abase + out.byte_offset(), out.ld, st), "vtb_f32_bn_act")
+
+    @staticmethod
+    def _master_weight(op: ConvOp) -> torch.Tensor:
+        """The OIHW fp32 master weight as the fp32 kernels read it (no packing in parity mode)."""
+        w = op.mod.conv.weight.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+            op.mod.__dict__["_vtb_w32"] = w   # keep the converted copy alive until the stream has consumed it
+        return w
+
+    def _conv_backward_f32(self, op: ConvOp, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world):
+        g, L = self.g, self.L
+        geom, cout, norm = op.geom, op.geom.cout, op.mod.norm
+        x, y, out, res = op.x, op.y, op.out, op.residual
+        f = lambda name: sbase + 4 * op.st[name]
+        dout_p, dout_ld = gp(out), gld(out)
+        bn = (f("mean"), f("invstd"), norm.weight.data_ptr(), norm.bias.data_ptr(), int(op.relu))
+        count = float(out.pixels)
+        dgamma, dbeta = pgrads[op.pidx + 1].data_ptr(), pgrads[op.pidx + 2].data_ptr()
+        check(L.vtb_f32_bn_bwd_reduce(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, *bn,
+                                      f("partial_b"), f("lsums_b"), st), "vtb_f32_bn_bwd_reduce")
+        if g.training and world > 1:
+            sums = run.stat_view_f64(op.st["sums_b"], cout * 2, sbase)
+            sums.copy_(run.stat_view_f64(op.st["lsums_b"], cout * 2, sbase))
+            self.dist.all_reduce_(sums)
+            check(L.vtb_bn_bwd_finalize(0, 0, f("sums_b"), f("lsums_b"), count * world, cout, dgamma, dbeta, 0,
+                                        f("coef"), 0, st), "vtb_bn_bwd_finalize")
+        else:
+            check(L.vtb_bn_bwd_finalize(0, 0, f("lsums_b"), 0, count, cout, dgamma, dbeta, 0, f("coef"), 0, st),
+                  "vtb_bn_bwd_finalize")
+            if not g.training:
+                # frozen statistics: mean/var are constants, so dy = gamma * invstd * dz
+                run.stat_view_f32(op.st["coef"], cout * 2, sbase).zero_()
+        check(L.vtb_f32_bn_bwd_apply(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, *bn, f("coef"),
+                                     dybase, cout, st), "vtb_f32_bn_bwd_apply")
+        w = self._master_weight(op)
+        if not (x.is_input and not run.x_requires_grad):
+            check(L.vtb_f32_conv_dgrad(C.byref(geom), dybase, cout, w.data_ptr(), op.cin_real, gp(x), gld(x),
+                                       int(is_init(x)), st), "vtb_f32_conv_dgrad")
+            mark(x)
+        check(L.vtb_f32_conv_wgrad(C.byref(geom), dybase, cout, abase + x.byte_offset(), x.ld, wsbase,
+                                   pgrads[op.pidx].data_ptr(), op.cin_real, 0, st), "vtb_f32_conv_wgrad")
+        self._residual_grad(op, gp, gld, is_init, mark, st)
+
+    def _residual_grad(self, op: ConvOp, gp, gld, is_init, mark, st) -> None:
+        """Gradient of the post-activation residual add (darknet.py:28): identity into `res` unless it is aliased."""
+        out, res = op.out, op.residual
+        if res is None:
+            return
+        rv = res
+        while rv.grad_alias is not None:
+            rv = rv.grad_alias
+        ov = out
+        while ov.grad_alias is not None:
+            ov = ov.grad_alias
+        if rv is not ov:
+            check(self.fn_grad_add(gp(res), gld(res), gp(out), gld(out), out.pixels, out.c, int(is_init(res)), st),
+                  "vtb_grad_add")
+            mark(res)
+        # aliased: the gradient of `res` already sits in out's gradient memory (initialised by definition)
+
     # -- backward
     def backward(self, run: Run, gouts):
         g, L = self.g, self.L
@@ -539,10 +731,10 @@ class Runner:
             if go is None:
                 continue
             go = go.detach()
-            if go.dtype != torch.bfloat16:
-                go = go.to(torch.bfloat16)
+            if go.dtype != self.tdtype:
+                go = go.to(self.tdtype)
             go = go.contiguous(memory_format=torch.channels_last)
-            check(L.vtb_grad_add(gp(t), gld(t), go.data_ptr(), t.c, t.pixels, t.c, int(is_init(t)), st), "vtb_grad_add")
+            check(self.fn_grad_add(gp(t), gld(t), go.data_ptr(), t.c, t.pixels, t.c, int(is_init(t)), st), "vtb_grad_add")
             mark(t)
 
         pending: list[tuple[TView, TView]] = []
@@ -553,7 +745,7 @@ class Runner:
             for item in list(pending):
                 rr, src = item
                 if is_init(rr) or rr is force_for:
-                    check(L.vtb_grad_add(gp(rr), gld(rr), gp(src), gld(src), src.pixels, src.c, int(is_init(rr)), st),
+                    check(self.fn_grad_add(gp(rr), gld(rr), gp(src), gld(src), src.pixels, src.c, int(is_init(rr)), st),
                           "vtb_grad_add")
                     mark(rr)
                     pending.remove(item)
@@ -571,13 +763,14 @@ class Runner:
                         ready_cb(g.params[op.pidx : op.pidx + n_p])
                 continue
             if op.kind == "conv":
-                self._conv_backward(op, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world)
+                bwd = self._conv_backward_f32 if self.f32 else self._conv_backward
+                bwd(op, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world)
                 if ready_cb is not None:
                     ready_cb(g.params[op.pidx : op.pidx + 3])
             elif op.kind == "pool":
                 xx, oo = op.x, op.out
                 if not (xx.is_input and not run.x_requires_grad):
-                    check(L.vtb_maxpool3s2_bwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h, xx.w, xx.c, gp(oo), gld(oo),
+                    check(self.fn_pool_bwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h, xx.w, xx.c, gp(oo), gld(oo),
                                                gp(xx), gld(xx), int(is_init(xx)),
                                                abase + op.idx.byte_offset() if op.idx is not None else 0, st),
                           "vtb_maxpool3s2_bwd")
@@ -585,7 +778,7 @@ class Runner:
             elif op.kind == "ese":
                 xx, oo, rr = op.x, op.out, op.residual
                 lin = op.mod.linear
-                check(L.vtb_ese_bwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h * xx.w, xx.c, lin.weight.data_ptr(),
+                check(self.fn_ese_bwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h * xx.w, xx.c, lin.weight.data_ptr(),
                                     sbase + 4 * op.st["pool"], sbase + 4 * op.st["z"], sbase + 4 * op.st["gate"],
                                     gp(oo), gld(oo), gp(xx), gld(xx), int(is_init(xx)),
                                     pgrads[op.pidx].data_ptr(), pgrads[op.pidx + 1].data_ptr(), 0,
@@ -658,25 +851,14 @@ class Runner:
         geom, cout = op.geom, op.geom.cout
         x, out, res = op.x, op.out, op.residual
         dout_p, dout_ld = gp(out), gld(out)
-        _, wd = self._packed(op, L, st)
+        _, wd = self._packed(op)
         if not (x.is_input and not run.x_requires_grad):
             check(L.vtb_conv_dgrad(C.byref(geom), dybase, cout, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
                   "vtb_conv_dgrad")
             mark(x)
         check(L.vtb_conv_wgrad(C.byref(geom), dybase, cout, abase + x.byte_offset(), x.ld, wsbase,
                                pgrads[op.pidx].data_ptr(), op.cin_real, 0, st), "vtb_conv_wgrad")
-        if res is not None:
-            rv = res
-            while rv.grad_alias is not None:
-                rv = rv.grad_alias
-            ov = out
-            while ov.grad_alias is not None:
-                ov = ov.grad_alias
-            if rv is not ov:
-                check(L.vtb_grad_add(gp(res), gld(res), dout_p, dout_ld, out.pixels, out.c, int(is_init(res)), st),
-                      "vtb_grad_add")
-                mark(res)
-            # aliased: the gradient of `res` already sits in out's gradient memory (initialised by definition)
+        self._residual_grad(op, gp, gld, is_init, mark, st)
 
 
 def _stat_view_f32(self, off_floats: int, n: int, sbase: int) -> torch.Tensor:
@@ -721,12 +903,13 @@ def run_native(module: nn.Module, x: torch.Tensor) -> list[torch.Tensor]:
     need_grad = torch.is_grad_enabled() and (
         x.requires_grad or any(p.requires_grad for p in module.parameters())
     )
-    key = (tuple(x.shape), module.training, need_grad, x.device.index)
+    f32 = _resolve_f32()
+    key = (tuple(x.shape), module.training, need_grad, x.device.index, f32)
     plans = module.__dict__.setdefault("_vtb_plans", {})
     runner = plans.get(key)
     if runner is None:
         with torch.cuda.device(x.device):
-            g = Graph(module.training, need_grad)
+            g = Graph(module.training, need_grad, f32)
             t_in = g.input_image(*x.shape)
             outs = module._emit(g, t_in)
             if isinstance(outs, TView):
