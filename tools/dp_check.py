@@ -6,6 +6,8 @@
     bf16 roundings flip for ~1e-5 of the activations per layer and train-mode gradients amplify that.
   * the peer-memory SyncBN exchange vs the NCCL all-reduce exchange in the SAME world: must agree to fp32 round-off.
   * BatchNorm running statistics identical on every rank and equal to the single-process ones.
+  * fp32 parity mode (vision_toolbox_b200.precision("fp32"), SyncBN through one all-reduce of the fp64 sums): the same
+    comparison at fp32 accuracy - a single unit to 1e-4 (measured ~1e-6), the deep model to 2e-3, running statistics 1e-5.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py
 """
@@ -17,6 +19,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 import torch.distributed as dist
 
+import vision_toolbox_b200 as vtb
 from vision_toolbox_b200 import parallel
 from vision_toolbox_b200.backbones import Darknet
 from vision_toolbox_b200.backbones.darknet import CSPDarknetStage
@@ -82,6 +85,19 @@ def main():
         print(f"rank {rank} [{kind}] SyncBN {path_p}: grads vs single-process global batch {err:.3e} (tol {tol}), "
               f"vs {path_n} exchange {cross:.1e}, loss diff {loss_err:.1e}, running stats {serr:.1e}, identical on all ranks "
               f"{same} -> {'OK' if ok else 'FAIL'}", flush=True)
+    for kind, tol in (("unit", 1e-4), ("deep", 2e-3)):
+        with vtb.precision("fp32"):
+            ref, l1, s1, _ = run(kind, dev, X, Y, None, None)
+            gp, lp, sp, _ = run(kind, dev, xs, ys, dist.group.WORLD, "nccl")
+        err = float((gp - ref).norm() / ref.norm())
+        lsum = torch.tensor([lp], device=dev)
+        dist.all_reduce(lsum)
+        loss_err = abs(float(lsum) / world - l1)
+        serr = max(float((sp[k] - v).abs().max() / v.abs().max().clamp_min(1e-6)) for k, v in s1.items())
+        ok = err < tol and loss_err < 1e-5 and serr < 1e-5
+        ok_all &= ok
+        print(f"rank {rank} [{kind}] fp32 mode: grads vs single-process global batch {err:.3e} (tol {tol}), loss diff "
+              f"{loss_err:.1e}, running stats {serr:.1e} -> {'OK' if ok else 'FAIL'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok_all else 1)
 
