@@ -140,7 +140,7 @@ def conv_bytes(geom, name: str) -> float:
     ho = (g.h + 2 * g.pad - g.k) // g.stride + 1
     wo = (g.w + 2 * g.pad - g.k) // g.stride + 1
     a_in, a_out, w = g.n * g.h * g.w * g.cin * 2.0, g.n * ho * wo * g.cout * 2.0, g.cout * g.k * g.k * g.cin * 2.0
-    if name == "vtb_conv_wgrad":
+    if name.startswith("vtb_conv_wgrad"):
         return a_in + a_out + 2.0 * w
     return a_in + a_out + w
 
@@ -385,11 +385,11 @@ def main() -> None:
         split = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}   # ms, flops, bytes, launches
         for name, geom, a, b, _ in prof.records:
             t = a.elapsed_time(b)
-            is_conv = geom is not None and name in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_wgrad")
+            is_conv = geom is not None and name in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_wgrad", "vtb_conv_wgrad_pair")
             fl = conv_flops(geom) if is_conv else 0.0
             d = agg.setdefault(name, [0.0, 0.0, 0])
             d[0] += t; d[1] += fl; d[2] += 1
-            if is_conv and name != "vtb_conv_wgrad":
+            if is_conv and not name.startswith("vtb_conv_wgrad"):
                 by = conv_bytes(geom, name)
                 cls = "tensor" if fl / (pk["tflops"] * 1e12) >= by / (pk["gbs"] * 1e9) else "hbm"
                 c = split[cls]

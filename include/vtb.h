@@ -63,12 +63,14 @@ int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* w
  * torch.optim.SGD(fused=True) update parameters without bumping it), so the bf16 operands are always rebuilt from the
  * fp32 masters (reads 4 B + writes 2 x 2 B per weight: ~35 us for CSPDarknet-53).
  * jobs_device: njobs VtbPackJob records in DEVICE memory, first_block = running sum of vtb_pack_job_blocks() over the
- * preceding jobs (first job: 0); total_blocks = the sum over all jobs. */
+ * preceding jobs (first job: 0); total_blocks = the sum over all jobs; at most 256 jobs per launch. */
 typedef struct VtbPackJob {
   const float* w;        /* OIHW fp32 master, [cout][cin_real][kk] */
   void* wf;              /* bf16 [cout][kk][cin] */
-  void* wd;              /* bf16 [cin][kk][cout], may be NULL */
+  void* wd;              /* bf16 [cin][kk][wd_ld] written at columns [wd_co_off, wd_co_off + cout), may be NULL */
   int cout, cin_real, cin, kk;
+  int wd_ld, wd_co_off;  /* wd_ld >= cout: two convolutions that share their input can be packed side by side into ONE
+                            dgrad operand (CSP conv1 | conv2, darknet.py:52-53); plain case: wd_ld = cout, wd_co_off = 0 */
   long long first_block;
 } VtbPackJob;
 long long vtb_pack_job_blocks(int cout, int cin, int kk);
@@ -104,6 +106,15 @@ typedef struct VtbBnTrain {
   unsigned int* tickets;
   const struct VtbSyncBn* sync;    /* NULL: single-GPU statistics; else the last block also exchanges the sums with all
                                       ranks over NVLink peer memory before finalising (see vtb_bn_sync_* below) */
+  /* Two ConvNormAct units that read the SAME input (CSPDarknetStage conv1 | conv2, darknet.py:46-47,52-53) run as ONE
+   * convolution over side-by-side packed weights: output channels >= split belong to the second unit and use its
+   * parameter tensors below (indexed from 0).  split = 0: one unit.  mean/invstd/scale/shift stay [cout] arrays. */
+  int split;
+  const float* gamma2;
+  const float* beta2;
+  float* running_mean2;
+  float* running_var2;
+  long long* num_batches_tracked2;
 } VtbBnTrain;
 int vtb_conv_fprop_bn(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
                       const VtbBnTrain* bn, void* stream);
@@ -117,6 +128,10 @@ int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, v
  * workspace: vtb_conv_wgrad_workspace_bytes(c) bytes of scratch. Deterministic (no atomics). */
 int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,
                    float* dw_oihw, int cin_real, int accumulate, void* stream);
+/* wgrad of two side-by-side units (see VtbBnTrain.split): rows [0, split) of the weight gradient go to dw_a, rows
+ * [split, cout) to dw_b (both OIHW fp32, each indexed from its own channel 0). */
+int vtb_conv_wgrad_pair(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,
+                        float* dw_a, float* dw_b, int split, int cin_real, int accumulate, void* stream);
 
 /* ---- BatchNorm2d training forward: replaces aten::native_batch_norm at components.py:36 ----
  * The conv epilogue leaves per-CTA partial sums; these calls finish the job.

@@ -57,3 +57,34 @@ def test_fp32_plan_mirrors_bf16_plan(build):
     assert e16.fused_eval and not e32.fused_eval
     assert all(op.y is None for op in e16.ops if op.kind == "conv")
     assert all(op.y is not None for op in e32.ops if op.kind == "conv")
+
+
+def test_sibling_pair_plan():
+    """CSP conv1 | conv2 read the same tensor: training-mode tensor-core plans run them as ONE convolution whose raw
+    output, BatchNorm arrays and dy buffer hold both units side by side; every other plan keeps two ordinary units."""
+    m = Darknet(16, [(1, 32), (2, 64)], CSPDarknetStage)
+    m.train()
+    g = engine.Graph(True, True, False, pair_ok=True)
+    outs = m._emit(g, g.input_image(2, 3, 32, 32))
+    for t in outs:
+        g.mark_output(t)
+    g.finalize()
+    firsts = [op for op in g.ops if op.kind == "conv" and op.pair is not None]
+    assert len(firsts) == 2                                     # one pair per CSP stage
+    for a in firsts:
+        b = a.pair
+        assert b.pair_of is a and g.ops.index(b) == g.ops.index(a) + 1
+        assert a.x is b.x or (a.x.buf is b.x.buf and a.x.coff == b.x.coff)
+        assert a.y.buf is b.y.buf and a.y.coff == 0 and b.y.coff == a.geom.cout and a.y.ld == a.geom.cout + b.geom.cout
+        assert a.pair_geom.cout == a.geom.cout + b.geom.cout and a.pair_geom.cin == a.geom.cin
+        for name in ("mean", "invstd", "scale", "shift"):
+            assert b.st[name] == a.st[name] + a.geom.cout       # one finalised array, two slices
+        assert a.out.buf is not b.out.buf                       # concat slice vs. standalone tensor
+        assert g.dy_bytes >= a.out.pixels * a.pair_geom.cout * 2
+    # same module, plans that must NOT pair: eval, fp32 parity mode, pairing switched off
+    for args in ((False, False, False, True), (True, True, True, True), (True, True, False, False)):
+        gg = engine.Graph(*args)
+        m.train(args[0])
+        m._emit(gg, gg.input_image(2, 3, 32, 32))
+        assert all(op.pair is None and op.pair_of is None for op in gg.ops if op.kind == "conv")
+    m.train()

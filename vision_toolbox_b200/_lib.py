@@ -27,14 +27,16 @@ class VtbBnTrain(C.Structure):
     _fields_ = [("count", C.c_double), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
                 ("momentum", C.c_float), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
                 ("num_batches_tracked", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
-                ("scale", C.c_void_p), ("shift", C.c_void_p), ("tickets", C.c_void_p), ("sync", C.c_void_p)]
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("tickets", C.c_void_p), ("sync", C.c_void_p),
+                ("split", C.c_int), ("gamma2", C.c_void_p), ("beta2", C.c_void_p), ("running_mean2", C.c_void_p),
+                ("running_var2", C.c_void_p), ("num_batches_tracked2", C.c_void_p)]
 
 
 class VtbPackJob(C.Structure):
     """struct VtbPackJob of include/vtb.h (one convolution's weight re-pack inside the batched launch)."""
 
     _fields_ = [("w", C.c_void_p), ("wf", C.c_void_p), ("wd", C.c_void_p), ("cout", C.c_int), ("cin_real", C.c_int),
-                ("cin", C.c_int), ("kk", C.c_int), ("first_block", C.c_longlong)]
+                ("cin", C.c_int), ("kk", C.c_int), ("wd_ld", C.c_int), ("wd_co_off", C.c_int), ("first_block", C.c_longlong)]
 
 
 class VtbSyncBn(C.Structure):
@@ -66,6 +68,7 @@ SIGNATURES = {
     "vtb_conv_fprop_bn": (_i, [_cp, _p, _i, _p, _p, _i, _p, C.POINTER(VtbBnTrain), _p]),
     "vtb_conv_dgrad": (_i, [_cp, _p, _i, _p, _p, _i, _i, _p]),
     "vtb_conv_wgrad": (_i, [_cp, _p, _i, _p, _i, _p, _p, _i, _i, _p]),
+    "vtb_conv_wgrad_pair": (_i, [_cp, _p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _p]),
     "vtb_bn_stats_reduce": (_i, [_p, _i, _i, _p, _p]),
     "vtb_bn_finalize": (_i, [_p, _i, _p, _d, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vtb_bn_eval_affine": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _p]),

@@ -90,9 +90,10 @@ class CSPDarknetStage(_NativeMixin, nn.Module):
         out = self.conv._emit(g, x)
         half = self.conv1.conv.out_channels
         cat = g.new_buffer(out.n, out.h, out.w, 2 * half)
-        # torch.cat([conv1(out), blocks(conv2(out))], 1): both producers write their channel slice directly
-        self.conv1._emit(g, out, out=g.slice(cat, 0, half))
-        _emit_blocks(self.blocks, g, self.conv2._emit(g, out), out=g.slice(cat, half, half))
+        # torch.cat([conv1(out), blocks(conv2(out))], 1): both producers write their channel slice directly;
+        # conv1 and conv2 read the same tensor -> one side-by-side convolution in training plans (engine.Graph)
+        _, b = g.conv_norm_act_pair(self.conv1, self.conv2, out, out_a=g.slice(cat, 0, half))
+        _emit_blocks(self.blocks, g, b, out=g.slice(cat, half, half))
         return self.out_conv._emit(g, g.slice(cat, 0, 2 * half))
 
 

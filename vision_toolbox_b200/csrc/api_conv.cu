@@ -154,31 +154,70 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
 }
 
 // The same re-pack for EVERY convolution of a plan in one launch (VtbPackJob table in device memory): block b serves the
-// job with the largest first_block <= b and packs kPackPerBlock elements of it.
-constexpr int kPackPerBlock = 2048;
-__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const VtbPackJob* __restrict__ jobs, int njobs) {
-  pdl_wait();
-  pdl_trigger();
-  int lo = 0, hi = njobs - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].first_block <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
-  }
-  const VtbPackJob J = jobs[lo];
-  const long long total = (long long)J.cout * J.kk * J.cin;
-  const long long base = ((long long)blockIdx.x - J.first_block) * kPackPerBlock;
-  const long long end = (base + kPackPerBlock < total) ? base + kPackPerBlock : total;
+// job with the largest first_block <= b and, inside it, one tile of 32 output channels x CI_T input channels (all taps).
+// The fp32 master is read in its own order (for one output channel the CI_T x kk block is contiguous), staged in shared
+// memory, and written out twice with 64-byte runs: wf[co][tap][ci] (ci fastest) and wd[ci][tap][co] (co fastest).
+constexpr int kPackCoT = 32;
+__host__ __device__ inline int pack_ci_tile(int kk) { return kk <= 9 ? 32 : 8; }
+constexpr int kPackSmemElems = 36 * kPackCoT * 9;   // >= kk * 32 * (CI_T + 1) for kk <= 9 (CI_T 32) and kk <= 36 (CI_T 8)
+
+// one 32 x CI_T tile of one job; KK > 0: compile-time tap count (divisions become shifts / multiplies), 0: runtime
+template <int KK>
+__device__ __forceinline__ void pack_tile(const VtbPackJob& J, int b, __nv_bfloat16* tile) {
+  const int kk = KK > 0 ? KK : J.kk;
+  const int cit = pack_ci_tile(kk), pitch = cit + 1;
+  const int n_ci_tiles = (J.cin + cit - 1) / cit;
+  const int co0 = (b / n_ci_tiles) * kPackCoT, ci0 = (b % n_ci_tiles) * cit;
+  const int per_co = cit * kk;
   const float* __restrict__ w = J.w;
+  for (int e = threadIdx.x; e < kPackCoT * per_co; e += blockDim.x) {
+    const int co_l = e / per_co, r = e - co_l * per_co;
+    const int ci_l = r / kk, t = r - ci_l * kk;
+    const int co = co0 + co_l, ci = ci0 + ci_l;
+    const float v = (co < J.cout && ci < J.cin_real) ? __ldg(w + ((long long)co * J.cin_real + ci) * kk + t) : 0.f;
+    tile[(t * kPackCoT + co_l) * pitch + ci_l] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
   __nv_bfloat16* __restrict__ wf = reinterpret_cast<__nv_bfloat16*>(J.wf);
   __nv_bfloat16* __restrict__ wd = reinterpret_cast<__nv_bfloat16*>(J.wd);
-  for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
-    const int ci = (int)(i % J.cin);
-    const int t = (int)((i / J.cin) % J.kk);
-    const int co = (int)(i / ((long long)J.cin * J.kk));
-    const float v = (ci < J.cin_real) ? w[((long long)co * J.cin_real + ci) * J.kk + t] : 0.f;
-    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-    wf[i] = b;
-    if (wd) wd[((long long)ci * J.kk + t) * J.cout + co] = b;
+  for (int e = threadIdx.x; e < kPackCoT * per_co; e += blockDim.x) {
+    const int ci_l = e % cit, q = e / cit;
+    const int t = q % kk, co_l = q / kk;
+    const int co = co0 + co_l, ci = ci0 + ci_l;
+    if (co < J.cout && ci < J.cin) wf[((long long)co * kk + t) * J.cin + ci] = tile[(t * kPackCoT + co_l) * pitch + ci_l];
+  }
+  if (wd != nullptr) {
+    for (int e = threadIdx.x; e < kPackCoT * per_co; e += blockDim.x) {
+      const int co_l = e % kPackCoT, q = e / kPackCoT;
+      const int t = q % kk, ci_l = q / kk;
+      const int co = co0 + co_l, ci = ci0 + ci_l;
+      if (co < J.cout && ci < J.cin)
+        wd[((long long)ci * kk + t) * J.wd_ld + J.wd_co_off + co] = tile[(t * kPackCoT + co_l) * pitch + ci_l];
+    }
+  }
+  __syncthreads();   // the tile buffer is reused by this block's next tile
+}
+
+constexpr int kPackMaxJobs = 256;
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const VtbPackJob* __restrict__ jobs, int njobs,
+                                                                  long long total_tiles) {
+  __shared__ __nv_bfloat16 tile[kPackSmemElems];   // [tap][co_l][CI_T + 1]
+  __shared__ long long first[kPackMaxJobs];        // first tile of every job (the search below stays in shared memory)
+  pdl_wait();
+  pdl_trigger();
+  for (int j = threadIdx.x; j < njobs; j += blockDim.x) first[j] = jobs[j].first_block;
+  __syncthreads();
+  for (long long tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (first[mid] <= tix) lo = mid; else hi = mid - 1;
+    }
+    const VtbPackJob J = jobs[lo];
+    const int b = (int)(tix - first[lo]);
+    if (J.kk == 1) pack_tile<1>(J, b, tile);
+    else if (J.kk == 9) pack_tile<9>(J, b, tile);
+    else pack_tile<0>(J, b, tile);
   }
 }
 
@@ -190,7 +229,7 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const VtbPack
 template <int EW>
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, int cin_real, int kk,
-                    float* __restrict__ dw, int accumulate) {
+                    float* __restrict__ dw, int accumulate, float* __restrict__ dw2, int split) {
   constexpr int SG = 256 / EW;
   extern __shared__ float red_sm[];   // [SG][kk][EW + 1]
   const int co = blockIdx.x;
@@ -213,7 +252,9 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin,
     }
   }
   __syncthreads();
-  float* dst = dw + ((size_t)co * cin_real + c0) * kk;
+  // output channels >= split belong to the second weight tensor of a side-by-side pair (dw2, indexed from 0)
+  float* dst = (dw2 != nullptr && co >= split) ? dw2 + ((size_t)(co - split) * cin_real + c0) * kk
+                                               : dw + ((size_t)co * cin_real + c0) * kk;
   const int ngroups = min(SG, splits);
   for (int j = threadIdx.x; j < cr * kk; j += 256) {
     const int c = j / kk, t = j - c * kk;
@@ -330,16 +371,18 @@ int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* w
 
 long long vtb_pack_job_blocks(int cout, int cin, int kk) {
   if (cout <= 0 || cin <= 0 || kk <= 0) return fail(VTB_EINVAL, "vtb_pack_job_blocks: bad arguments");
-  const long long total = (long long)cout * kk * cin;
-  return (total + kPackPerBlock - 1) / kPackPerBlock;
+  if (kk > 36) return fail(VTB_EINVAL, "vtb_pack_job_blocks: kernels larger than 6x6 are not supported");
+  const int cit = pack_ci_tile(kk);
+  return (long long)((cout + kPackCoT - 1) / kPackCoT) * ((cin + cit - 1) / cit);
 }
 
 int vtb_pack_weights(const VtbPackJob* jobs_device, int njobs, long long total_blocks, void* stream) {
-  if (!jobs_device || njobs <= 0 || total_blocks <= 0 || total_blocks > 0x7fffffffLL)
-    return fail(VTB_EINVAL, "vtb_pack_weights: bad arguments");
+  if (!jobs_device || njobs <= 0 || njobs > kPackMaxJobs || total_blocks <= 0)
+    return fail(VTB_EINVAL, "vtb_pack_weights: bad arguments (at most 256 jobs per launch)");
   count_launch(1);
-  return check_cuda((int)launch_pdl(pack_weights_batched_kernel, dim3((unsigned)total_blocks), dim3(256), 0, (cudaStream_t)stream,
-                                    jobs_device, njobs),
+  const long long grid = std::min<long long>(total_blocks, (long long)std::max(1, num_sms()) * 8);
+  return check_cuda((int)launch_pdl(pack_weights_batched_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream,
+                                    jobs_device, njobs, total_blocks),
                     "pack_weights_batched_kernel");
 }
 
@@ -396,6 +439,17 @@ static int fprop_impl(const VtbConv* c, const void* x, int ldx, const void* wf, 
     p.bn_invstd = bn->invstd;
     p.bn_scale = bn->scale;
     p.bn_shift = bn->shift;
+    p.bn_split = bn->split;
+    if (bn->split > 0) {
+      if (bn->split >= c->cout || !bn->gamma2 || !bn->beta2 || ((bn->running_mean2 == nullptr) != (bn->running_var2 == nullptr)) ||
+          ((bn->running_mean == nullptr) != (bn->running_mean2 == nullptr)))
+        return fail(VTB_EINVAL, "vtb_conv_fprop_bn: bad side-by-side BatchNorm arguments");
+      p.bn_gamma2 = bn->gamma2;
+      p.bn_beta2 = bn->beta2;
+      p.bn_running_mean2 = bn->running_mean2;
+      p.bn_running_var2 = bn->running_var2;
+      p.bn_nbt2 = bn->num_batches_tracked2;
+    }
     if (bn->sync && !sync_args_ok(bn->sync, c->cout)) return fail(VTB_EINVAL, "vtb_conv_fprop_bn: bad SyncBN peers");
     p.sync = make_sync_peers(bn->sync);
   }
@@ -551,8 +605,8 @@ int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, v
   return VTB_OK;
 }
 
-int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,
-                   float* dw_oihw, int cin_real, int accumulate, void* stream) {
+static int wgrad_impl(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,
+                      float* dw_oihw, float* dw2, int split, int cin_real, int accumulate, void* stream) {
   if (!conv_ok(c) || !dy || !x || !workspace || !dw_oihw || cin_real <= 0 || cin_real > c->cin)
     return fail(VTB_EINVAL, "vtb_conv_wgrad: bad arguments");
   if (lddy < c->cout || ldx < c->cin || lddy % 8 || ldx % 8) return fail(VTB_EINVAL, "vtb_conv_wgrad: bad pitch");
@@ -610,12 +664,23 @@ int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, in
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t re;
   if (ew == 16)
-    re = launch_pdl(wgrad_reduce_kernel<16>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
+    re = launch_pdl(wgrad_reduce_kernel<16>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate, dw2, split);
   else if (ew == 32)
-    re = launch_pdl(wgrad_reduce_kernel<32>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
+    re = launch_pdl(wgrad_reduce_kernel<32>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate, dw2, split);
   else
-    re = launch_pdl(wgrad_reduce_kernel<64>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate);
+    re = launch_pdl(wgrad_reduce_kernel<64>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate, dw2, split);
   return check_cuda((int)re, "wgrad_reduce_kernel");
+}
+
+int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,
+                   float* dw_oihw, int cin_real, int accumulate, void* stream) {
+  return wgrad_impl(c, dy, lddy, x, ldx, workspace, dw_oihw, nullptr, 0, cin_real, accumulate, stream);
+}
+
+int vtb_conv_wgrad_pair(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,
+                        float* dw_a, float* dw_b, int split, int cin_real, int accumulate, void* stream) {
+  if (!c || !dw_b || split <= 0 || split >= c->cout) return fail(VTB_EINVAL, "vtb_conv_wgrad_pair: bad split");
+  return wgrad_impl(c, dy, lddy, x, ldx, workspace, dw_a, dw_b, split, cin_real, accumulate, stream);
 }
 
 }  // extern "C"

@@ -636,15 +636,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float invstd = (float)(1.0 / sqrt(var + (double)p.bn_eps));
             p.bn_mean[ch] = (float)mean;
             p.bn_invstd[ch] = invstd;
-            const float sc = p.bn_gamma[ch] * invstd;
+            // parameter tensors of the layer this channel belongs to (second layer of a side-by-side pair: bn_split)
+            const bool second = p.bn_split > 0 && ch >= p.bn_split;
+            const int pc = second ? ch - p.bn_split : ch;
+            const float* gam = second ? p.bn_gamma2 : p.bn_gamma;
+            const float* bet = second ? p.bn_beta2 : p.bn_beta;
+            float* rmean = second ? p.bn_running_mean2 : p.bn_running_mean;
+            float* rvar = second ? p.bn_running_var2 : p.bn_running_var;
+            long long* nbt = second ? p.bn_nbt2 : p.bn_nbt;
+            const float sc = gam[pc] * invstd;
             p.bn_scale[ch] = sc;
-            p.bn_shift[ch] = p.bn_beta[ch] - (float)mean * sc;
-            if (p.bn_running_mean != nullptr) {
+            p.bn_shift[ch] = bet[pc] - (float)mean * sc;
+            if (rmean != nullptr) {
               const double unbiased = p.bn_count > 1 ? var * (p.bn_count / (p.bn_count - 1.0)) : var;
-              p.bn_running_mean[ch] = (1.f - p.bn_momentum) * p.bn_running_mean[ch] + p.bn_momentum * (float)mean;
-              p.bn_running_var[ch] = (1.f - p.bn_momentum) * p.bn_running_var[ch] + p.bn_momentum * (float)unbiased;
+              rmean[pc] = (1.f - p.bn_momentum) * rmean[pc] + p.bn_momentum * (float)mean;
+              rvar[pc] = (1.f - p.bn_momentum) * rvar[pc] + p.bn_momentum * (float)unbiased;
             }
-            if (ch == 0 && p.bn_nbt != nullptr) *p.bn_nbt += 1;
+            if (pc == 0 && nbt != nullptr) *nbt += 1;
           }
           if (et == 0) p.tickets[n_blk] = 0u;       // self-cleaning: ready for the next launch
         }

@@ -81,6 +81,14 @@ struct ConvIgemmParams {
   float* bn_invstd;
   float* bn_scale;
   float* bn_shift;
+  // two BatchNorm layers side by side on the channel axis (two convolutions of the same input run as ONE launch: CSP
+  // conv1 | conv2): channels >= bn_split use the second set of parameter tensors (indexed from 0); 0 = single layer
+  int bn_split;
+  const float* bn_gamma2;
+  const float* bn_beta2;
+  float* bn_running_mean2;
+  float* bn_running_var2;
+  long long* bn_nbt2;
   // SyncBN: peer-mapped exchange buffers (world <= 1: single-GPU statistics); bn_count is then the GLOBAL count and
   // tickets[64] counts the finished n-block exchanges of the launch
   SyncPeers sync;

@@ -128,6 +128,10 @@ class ConvOp:
     pidx: int = -1  # index of (weight, gamma, beta) in the parameter list
     st: dict = field(default_factory=dict)  # float offsets into the stat arena
     kind: str = "conv"
+    # side-by-side pair (two units reading the same tensor, run as ONE convolution): set on the first / second op
+    pair: Any = None        # first op -> its partner
+    pair_of: Any = None     # second op -> the first
+    pair_geom: Any = None   # VtbConv with cout = both units (first op only)
 
 
 @dataclass
@@ -153,10 +157,13 @@ class EseOp:
 # graph builder
 # ----------------------------------------------------------------------------------------------------
 class Graph:
-    def __init__(self, training: bool, need_grad: bool, f32: bool = False):
+    def __init__(self, training: bool, need_grad: bool, f32: bool = False, pair_ok: bool = False):
         self.training = training
         self.need_grad = need_grad
         self.f32 = f32
+        # sibling ConvNormAct units (CSP conv1 | conv2) may run as one convolution: training-mode tensor-core plans whose
+        # BatchNorm finalisation happens inside the conv kernel (single GPU, or SyncBN over peer memory)
+        self.pair_ok = pair_ok and training and not f32
         self.esize = F32 if f32 else BF16
         # BN uses batch statistics only in training mode; the 1-kernel fused epilogue needs frozen statistics
         # (fp32 parity mode keeps conv and normalise separate: it mirrors the reference's op order)
@@ -214,7 +221,8 @@ class Graph:
         self.input, self.input_c = t, c
         return t
 
-    def conv_norm_act(self, mod, x: TView, residual: Optional[TView] = None, out: Optional[TView] = None) -> TView:
+    def conv_norm_act(self, mod, x: TView, residual: Optional[TView] = None, out: Optional[TView] = None,
+                      y: Optional[TView] = None) -> TView:
         conv, norm = mod.conv, mod.norm
         k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         cin_real, cout = conv.in_channels, conv.out_channels
@@ -231,7 +239,8 @@ class Graph:
         if out is None:
             out = self.new_tensor(x.n, ho, wo, cout)
         assert (out.n, out.h, out.w, out.c) == (x.n, ho, wo, cout)
-        y = None if self.fused_eval else self.new_tensor(x.n, ho, wo, cout, "raw")
+        if y is None:
+            y = None if self.fused_eval else self.new_tensor(x.n, ho, wo, cout, "raw")
         op = ConvOp(mod, x, y, out, residual, mod.act_is_relu(), geom, cin_real)
         idx = len(self.ops)
         x.consumers.append(idx)
@@ -269,6 +278,48 @@ class Graph:
         op.rows_f, op.rows_b = rows_f, rows_b
         self.ops.append(op)
         return out
+
+    def conv_norm_act_pair(self, mod_a, mod_b, x: TView, out_a: Optional[TView] = None,
+                           out_b: Optional[TView] = None) -> tuple[TView, TView]:
+        """Two ConvNormAct units applied to the SAME tensor (CSPDarknetStage conv1 / conv2, reference darknet.py:52-53).
+
+        In training-mode tensor-core plans they become one implicit GEMM over side-by-side packed weights: one fprop
+        (statistics + BatchNorm finalisation of both units in its epilogue), one dgrad without a read-modify-write
+        fan-in, one wgrad - `x` is read once instead of twice in each of the three.  The normalise / BatchNorm-backward
+        passes stay per unit (their outputs live in different buffers).  Elsewhere: two ordinary units."""
+        ca, cb, na, nb = mod_a.conv, mod_b.conv, mod_a.norm, mod_b.norm
+        compatible = (
+            self.pair_ok and mod_a.native_supported() and mod_b.native_supported()
+            and ca.kernel_size == cb.kernel_size and ca.stride == cb.stride and ca.padding == cb.padding
+            and ca.in_channels == cb.in_channels and na.eps == nb.eps and na.momentum == nb.momentum
+            and na.track_running_stats == nb.track_running_stats and (na.running_mean is None) == (nb.running_mean is None)
+        )
+        if not compatible:
+            return self.conv_norm_act(mod_a, x, out=out_a), self.conv_norm_act(mod_b, x, out=out_b)
+        k, s, p = ca.kernel_size[0], ca.stride[0], ca.padding[0]
+        ho, wo = (x.h + 2 * p - k) // s + 1, (x.w + 2 * p - k) // s + 1
+        c_a, c_b = ca.out_channels, cb.out_channels
+        tot = c_a + c_b
+        ybuf = self.new_buffer(x.n, ho, wo, tot, "raw")
+        first = len(self.ops)
+        o_a = self.conv_norm_act(mod_a, x, out=out_a, y=self.slice(ybuf, 0, c_a))
+        o_b = self.conv_norm_act(mod_b, x, out=out_b, y=self.slice(ybuf, c_a, c_b))
+        op_a, op_b = self.ops[first], self.ops[first + 1]
+        op_a.pair, op_b.pair_of = op_b, op_a
+        op_a.pair_geom = VtbConv(x.n, x.h, x.w, x.c, tot, k, s, p)
+        # the fused launch finalises BatchNorm for all `tot` channels into ONE set of arrays; each unit uses its slice
+        L = _lib.lib()
+        for name in ("mean", "invstd", "scale", "shift"):
+            self._stat(op_a, name, tot)
+            op_b.st[name] = op_a.st[name] + c_a
+        rows = L.vtb_conv_stats_rows(C.byref(op_a.pair_geom))
+        if rows <= 0:
+            check(-1, "vtb_conv_stats_rows")
+        self._stat(op_a, "pair_partial_f", rows * tot * 2)
+        if self.need_grad:
+            self.ws_bytes = max(self.ws_bytes, int(L.vtb_conv_wgrad_workspace_bytes(C.byref(op_a.pair_geom))))
+            self.dy_bytes = max(self.dy_bytes, o_a.pixels * tot * self.esize)
+        return o_a, o_b
 
     def maxpool(self, x: TView, out: Optional[TView] = None) -> TView:
         ho, wo = (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1
@@ -414,7 +465,7 @@ class Runner:
         L = self.L
         self.f32 = graph.f32
         self._conv_ops = [op for op in graph.ops if op.kind == "conv"]
-        self._pack_key, self._pack_jobs, self._pack_blocks, self._pack_srcs = None, None, 0, None
+        self._pack_key, self._pack_jobs, self._pack_launches, self._pack_srcs = None, None, [], None
         self.tdtype = torch.float32 if self.f32 else torch.bfloat16
         self.fn_grad_add = L.vtb_f32_grad_add if self.f32 else L.vtb_grad_add
         self.fn_to_nhwc = L.vtb_f32_nchw_to_nhwc if self.f32 else L.vtb_nchw_to_nhwc
@@ -447,26 +498,46 @@ class Runner:
         key = tuple(w.data_ptr() for w in srcs)
         if key != self._pack_key:
             jobs = (_lib.VtbPackJob * len(convs))()
-            blk = 0
+            blk, launches = 0, []
             for j, (op, w) in enumerate(zip(convs, srcs)):
                 g = op.geom
                 n = g.cout * g.k * g.k * g.cin
-                cache = op.mod.__dict__.get("_vtb_wpack")
-                if cache is None or cache[0].numel() != n or cache[0].device != w.device:
-                    cache = (torch.empty(n, dtype=torch.bfloat16, device=w.device),
-                             torch.empty(n, dtype=torch.bfloat16, device=w.device))
-                    op.mod.__dict__["_vtb_wpack"] = cache
-                jobs[j] = _lib.VtbPackJob(w.data_ptr(), cache[0].data_ptr(), cache[1].data_ptr(), g.cout, op.cin_real,
-                                          g.cin, g.k * g.k, blk)
+                first = op if op.pair is not None else op.pair_of
+                if first is not None:
+                    # side-by-side pair: both units pack into ONE [tot][tap][cin] / [cin][tap][tot] operand pair
+                    tot = first.pair_geom.cout
+                    npair = tot * g.k * g.k * g.cin
+                    cache = first.mod.__dict__.get("_vtb_wpack_pair")
+                    if cache is None or cache[0].numel() != npair or cache[0].device != w.device:
+                        cache = (torch.empty(npair, dtype=torch.bfloat16, device=w.device),
+                                 torch.empty(npair, dtype=torch.bfloat16, device=w.device))
+                        first.mod.__dict__["_vtb_wpack_pair"] = cache
+                    co_off = 0 if op is first else first.geom.cout
+                    wf_ptr = cache[0].data_ptr() + co_off * g.k * g.k * g.cin * BF16
+                    jobs[j] = _lib.VtbPackJob(w.data_ptr(), wf_ptr, cache[1].data_ptr(), g.cout, op.cin_real,
+                                              g.cin, g.k * g.k, tot, co_off, blk)
+                else:
+                    cache = op.mod.__dict__.get("_vtb_wpack")
+                    if cache is None or cache[0].numel() != n or cache[0].device != w.device:
+                        cache = (torch.empty(n, dtype=torch.bfloat16, device=w.device),
+                                 torch.empty(n, dtype=torch.bfloat16, device=w.device))
+                        op.mod.__dict__["_vtb_wpack"] = cache
+                    jobs[j] = _lib.VtbPackJob(w.data_ptr(), cache[0].data_ptr(), cache[1].data_ptr(), g.cout, op.cin_real,
+                                              g.cin, g.k * g.k, g.cout, 0, blk)
                 nb = int(L.vtb_pack_job_blocks(g.cout, g.cin, g.k * g.k))
                 if nb <= 0:
                     check(-1, "vtb_pack_job_blocks")
                 blk += nb
+                if (j + 1) % 256 == 0 or j == len(convs) - 1:   # a launch serves at most 256 jobs
+                    launches.append((j // 256 * 256, j % 256 + 1, blk))
+                    blk = 0
             table = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
             self._pack_jobs = table.to(self.device)
-            self._pack_blocks, self._pack_key = blk, key
+            self._pack_launches, self._pack_key = launches, key
         self._pack_srcs = srcs   # converted copies (non-fp32 masters) must outlive the launch
-        check(L.vtb_pack_weights(self._pack_jobs.data_ptr(), len(convs), self._pack_blocks, st), "vtb_pack_weights")
+        base, rec = self._pack_jobs.data_ptr(), C.sizeof(_lib.VtbPackJob)
+        for j0, n, blocks in self._pack_launches:
+            check(L.vtb_pack_weights(base + j0 * rec, n, blocks, st), "vtb_pack_weights")
 
     @staticmethod
     def _packed(op: ConvOp):
@@ -506,7 +577,9 @@ class Runner:
             if op.kind == "conv":
                 if self.f32:
                     self._conv_forward_f32(op, abase, sbase, run, st, world)
-                else:
+                elif op.pair is not None:
+                    self._conv_forward_pair(op, abase, sbase, run, st, world)
+                elif op.pair_of is None:    # the second unit of a pair ran together with the first
                     self._conv_forward(op, abase, sbase, run, st, world)
             elif op.kind == "pool":
                 xx, oo = op.x, op.out
@@ -584,6 +657,67 @@ class Runner:
             invstd.copy_(torch.rsqrt(norm.running_var + norm.eps))
         check(L.vtb_bn_act(abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"), f("shift"), int(op.relu),
                            res_p, res_ld, abase + out.byte_offset(), out.ld, st), "vtb_bn_act")
+
+    def _conv_forward_pair(self, op_a: ConvOp, abase: int, sbase: int, run: Run, st: int, world: int) -> None:
+        """Both units of a side-by-side pair: ONE conv + statistics + BatchNorm finalisation launch, then one
+        normalise+ReLU pass per unit (their destinations differ: a concat slice and a standalone tensor)."""
+        L = self.L
+        op_b, geom = op_a.pair, op_a.pair_geom
+        na, nb = op_a.mod.norm, op_b.mod.norm
+        peer_sync = self.dist.sync if (world > 1 and self.dist is not None) else None
+        if world > 1 and peer_sync is None:
+            raise RuntimeError("paired plan built for the in-kernel BatchNorm finalisation, but SyncBN runs over NCCL")
+        f = lambda name: sbase + 4 * op_a.st[name]
+        mom = na.momentum if na.momentum is not None else 0.1
+        track = na.track_running_stats and na.running_mean is not None
+        ptr = lambda t: t.data_ptr() if track else 0
+        bn = VtbBnTrain(float(op_a.out.pixels) * world, na.weight.data_ptr(), na.bias.data_ptr(), na.eps, mom,
+                        ptr(na.running_mean), ptr(na.running_var), ptr(na.num_batches_tracked),
+                        f("mean"), f("invstd"), f("scale"), f("shift"), self.tickets.data_ptr(),
+                        C.addressof(peer_sync) if peer_sync is not None else None)
+        bn.split = op_a.geom.cout
+        bn.gamma2, bn.beta2 = nb.weight.data_ptr(), nb.bias.data_ptr()
+        if track:
+            bn.running_mean2, bn.running_var2 = nb.running_mean.data_ptr(), nb.running_var.data_ptr()
+            bn.num_batches_tracked2 = nb.num_batches_tracked.data_ptr()
+        wf, _ = op_a.mod.__dict__["_vtb_wpack_pair"]
+        x, y = op_a.x, op_a.y   # y: slice 0 of the shared raw buffer, pitch = both units
+        check(L.vtb_conv_fprop_bn(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(), abase + y.byte_offset(),
+                                  y.ld, f("pair_partial_f"), C.byref(bn), st), "vtb_conv_fprop_bn(pair)")
+        for op in (op_a, op_b):
+            fo = lambda name, op=op: sbase + 4 * op.st[name]
+            yy, out, res = op.y, op.out, op.residual
+            check(L.vtb_bn_act(abase + yy.byte_offset(), yy.ld, out.pixels, op.geom.cout, fo("scale"), fo("shift"),
+                               int(op.relu), 0 if res is None else abase + res.byte_offset(),
+                               0 if res is None else res.ld, abase + out.byte_offset(), out.ld, st), "vtb_bn_act")
+
+    def _conv_backward_pair(self, op_a: ConvOp, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world):
+        """Backward of a side-by-side pair: BatchNorm+ReLU backward per unit into the two column ranges of ONE dy
+        buffer, then one dgrad (plain store: no fan-in accumulate) and one wgrad (rows split over the two weights)."""
+        L = self.L
+        op_b, geom = op_a.pair, op_a.pair_geom
+        tot = geom.cout
+        peer_sync = self.dist.sync if (world > 1 and self.dist is not None) else None
+        for op, off in ((op_b, op_a.geom.cout), (op_a, 0)):
+            fo = lambda name, op=op: sbase + 4 * op.st[name]
+            out, yy = op.out, op.y
+            check(L.vtb_bn_bwd_fused(gp(out), gld(out), abase + yy.byte_offset(), yy.ld, out.pixels, op.geom.cout,
+                                     fo("scale"), fo("shift"), fo("mean"), fo("invstd"), int(op.relu),
+                                     float(out.pixels) * world, fo("partial_b"), pgrads[op.pidx + 1].data_ptr(),
+                                     pgrads[op.pidx + 2].data_ptr(), 0, self.tickets.data_ptr() + 1024,
+                                     dybase + off * BF16, tot, C.byref(peer_sync) if peer_sync is not None else None, st),
+                  "vtb_bn_bwd_fused(pair)")
+        _, wd = op_a.mod.__dict__["_vtb_wpack_pair"]
+        x = op_a.x
+        if not (x.is_input and not run.x_requires_grad):
+            check(L.vtb_conv_dgrad(C.byref(geom), dybase, tot, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
+                  "vtb_conv_dgrad(pair)")
+            mark(x)
+        check(L.vtb_conv_wgrad_pair(C.byref(geom), dybase, tot, abase + x.byte_offset(), x.ld, wsbase,
+                                    pgrads[op_a.pidx].data_ptr(), pgrads[op_b.pidx].data_ptr(), op_a.geom.cout,
+                                    op_a.cin_real, 0, st), "vtb_conv_wgrad_pair")
+        for op in (op_a, op_b):
+            self._residual_grad(op, gp, gld, is_init, mark, st)
 
     def _conv_forward_f32(self, op: ConvOp, abase: int, sbase: int, run: Run, st: int, world: int) -> None:
         """fp32 parity mode of one ConvNormAct (reference components.py:26-39 without autocast): conv -> fp64 statistics
@@ -752,6 +886,29 @@ class Runner:
 
         for i in range(len(g.ops) - 1, -1, -1):
             op = g.ops[i]
+            if op.kind == "conv" and op.pair is not None:
+                continue   # handled together with its partner (visited just before, in reverse order)
+            if op.kind == "conv" and op.pair_of is not None:
+                op_a = op.pair_of
+                flush_pending(op.out)
+                flush_pending(op_a.out)
+                have = [is_init(o.out) for o in (op_a, op)]
+                if any(have):
+                    for o, h in zip((op_a, op), have):
+                        if not h:   # one branch without gradient: it contributes zeros to the shared dy buffer
+                            tg = gview(o.out)
+                            self.view_tensor(gact, tg).zero_()
+                            mark(o.out)
+                    self._conv_backward_pair(op_a, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world)
+                else:
+                    for o in (op_a, op):
+                        for j in range(3):
+                            pgrads[o.pidx + j].zero_()
+                if ready_cb is not None:
+                    ready_cb(g.params[op.pidx : op.pidx + 3])
+                    ready_cb(g.params[op_a.pidx : op_a.pidx + 3])
+                flush_pending(False)
+                continue
             flush_pending(op.out)
             if not is_init(op.out):
                 # no gradient reaches this op: its parameters get zero gradient
@@ -904,12 +1061,16 @@ def run_native(module: nn.Module, x: torch.Tensor) -> list[torch.Tensor]:
         x.requires_grad or any(p.requires_grad for p in module.parameters())
     )
     f32 = _resolve_f32()
-    key = (tuple(x.shape), module.training, need_grad, x.device.index, f32)
+    dcfg = module.__dict__.get("_vtb_dist")
+    # sibling units run as one convolution when BatchNorm is finalised inside the conv kernel (VTB_PAIR=0: A/B switch)
+    pair_ok = (_os.environ.get("VTB_PAIR", "1") == "1" and module.training and not f32
+               and (dcfg is None or not dcfg.sync_bn or dcfg.world == 1 or dcfg.sync is not None))
+    key = (tuple(x.shape), module.training, need_grad, x.device.index, f32, pair_ok)
     plans = module.__dict__.setdefault("_vtb_plans", {})
     runner = plans.get(key)
     if runner is None:
         with torch.cuda.device(x.device):
-            g = Graph(module.training, need_grad, f32)
+            g = Graph(module.training, need_grad, f32, pair_ok)
             t_in = g.input_image(*x.shape)
             outs = module._emit(g, t_in)
             if isinstance(outs, TView):
