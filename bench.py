@@ -367,6 +367,9 @@ def main() -> None:
     # every rank runs the extra step (it contains the SyncBN / gradient collectives); rank 0 instruments it
     prof = ProfilingLib(_lib.lib())
     runners = list(model.__dict__.get("_vtb_plans", {}).values())
+    sides = [getattr(r, "_side", None) for r in runners]
+    for r in runners:
+        r._side = None          # instrumented step: one stream, so that every event pair brackets exactly one kernel family
     if rank == 0:
         for r in runners:
             r.L = prof
@@ -374,8 +377,9 @@ def main() -> None:
     torch.cuda._sleep(30_000_000)  # let the host run ahead so event intervals contain no launch gaps
     trainer._step_eager(dev_x[0], dev_y[0])   # eager on purpose: per-call events cannot be recorded inside a graph replay
     barrier()
-    for r in runners:
+    for r, sd_ in zip(runners, sides):
         r.L = _lib.lib()
+        r._side = sd_
     if rank == 0:
         agg = {}
         pk = peaks()

@@ -37,6 +37,7 @@ prof = ProfilingLib(_lib.lib())
 runners = list(model.__dict__.get("_vtb_plans", {}).values())
 for r in runners:
     r.L = prof
+    r._side = None   # single stream: every event pair brackets exactly one call
 torch.cuda.synchronize()
 torch.cuda._sleep(60_000_000)
 tr.step(x, y)

@@ -158,8 +158,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
 // The fp32 master is read in its own order (for one output channel the CI_T x kk block is contiguous), staged in shared
 // memory, and written out twice with 64-byte runs: wf[co][tap][ci] (ci fastest) and wd[ci][tap][co] (co fastest).
 constexpr int kPackCoT = 32;
-__host__ __device__ inline int pack_ci_tile(int kk) { return kk <= 9 ? 32 : 8; }
-constexpr int kPackSmemElems = 36 * kPackCoT * 9;   // >= kk * 32 * (CI_T + 1) for kk <= 9 (CI_T 32) and kk <= 36 (CI_T 8)
+__host__ __device__ inline int pack_ci_tile(int kk) { return kk == 1 ? 256 : (kk <= 9 ? 32 : 8); }
+constexpr int kPackSmemElems = 36 * kPackCoT * 9;   // >= kk * 32 * (CI_T + 1): kk 1 (CI_T 256), kk <= 9 (CI_T 32), kk <= 36 (CI_T 8)
 
 // one 32 x CI_T tile of one job; KK > 0: compile-time tap count (divisions become shifts / multiplies), 0: runtime
 template <int KK>

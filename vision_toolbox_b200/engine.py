@@ -453,11 +453,11 @@ def _ptr(t: Optional[torch.Tensor]) -> int:
 
 
 class Runner:
-    def __init__(self, graph: Graph, device: torch.device):
+    def __init__(self, graph: Graph, device: torch.device, dist_cfg: Optional["DistConfig"] = None):
         self.g = graph
         self.device = device
         self.L = _lib.lib()
-        self.dist: Optional[DistConfig] = None
+        self.dist: Optional[DistConfig] = dist_cfg
         self.grad_sink = False
         # ticket counters of the fused conv + BatchNorm-finalize kernels (self-cleaning, shared by all layers)
         self.tickets = torch.zeros(512, dtype=torch.int32, device=device)   # [0,256): conv kernels, [256,512): BN bwd
@@ -465,6 +465,18 @@ class Runner:
         L = self.L
         self.f32 = graph.f32
         self._conv_ops = [op for op in graph.ops if op.kind == "conv"]
+        # Weight-gradient GEMMs on a second stream (VTB_WGRAD_STREAM=0 switches it off): wgrad(i) only needs dy(i) and
+        # x(i), so it fills the ramp-up / tail bubbles of the dependent chain bn_bwd -> dgrad -> bn_bwd ... on the main
+        # stream (15.47 -> 15.16 ms per CSPDarknet-53 step).  Single-process plans only: with more than one rank the
+        # SyncBN exchange kernels spin on their peers while holding SM resources, NCCL kernels wait on theirs, and a
+        # third stream that both depend on closes a cross-rank wait cycle (observed: exchange timeout at 2 GPUs).
+        self._side = None
+        multi_rank = dist_cfg is not None and dist_cfg.world > 1
+        if (_os.environ.get("VTB_WGRAD_STREAM", "1") == "1" and not graph.f32 and device.type == "cuda"
+                and not multi_rank):
+            self._side = torch.cuda.Stream(device)
+        self._dy_slots = 3 if self._side is not None else 1
+        self._dy_free: list = []
         self._pack_key, self._pack_jobs, self._pack_launches, self._pack_srcs = None, None, [], None
         self.tdtype = torch.float32 if self.f32 else torch.bfloat16
         self.fn_grad_add = L.vtb_f32_grad_add if self.f32 else L.vtb_grad_add
@@ -709,13 +721,14 @@ class Runner:
                   "vtb_bn_bwd_fused(pair)")
         _, wd = op_a.mod.__dict__["_vtb_wpack_pair"]
         x = op_a.x
+        self._launch_wgrad(lambda s_: check(L.vtb_conv_wgrad_pair(C.byref(geom), dybase, tot, abase + x.byte_offset(), x.ld,
+                                                                  wsbase, pgrads[op_a.pidx].data_ptr(),
+                                                                  pgrads[op_b.pidx].data_ptr(), op_a.geom.cout,
+                                                                  op_a.cin_real, 0, s_), "vtb_conv_wgrad_pair"), st)
         if not (x.is_input and not run.x_requires_grad):
             check(L.vtb_conv_dgrad(C.byref(geom), dybase, tot, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
                   "vtb_conv_dgrad(pair)")
             mark(x)
-        check(L.vtb_conv_wgrad_pair(C.byref(geom), dybase, tot, abase + x.byte_offset(), x.ld, wsbase,
-                                    pgrads[op_a.pidx].data_ptr(), pgrads[op_b.pidx].data_ptr(), op_a.geom.cout,
-                                    op_a.cin_real, 0, st), "vtb_conv_wgrad_pair")
         for op in (op_a, op_b):
             self._residual_grad(op, gp, gld, is_init, mark, st)
 
@@ -794,6 +807,27 @@ class Runner:
                                    pgrads[op.pidx].data_ptr(), op.cin_real, 0, st), "vtb_f32_conv_wgrad")
         self._residual_grad(op, gp, gld, is_init, mark, st)
 
+    def _grad_stream_ctx(self):
+        """Stream whose completion implies "the gradients reported so far are final" (side stream when wgrads run there)."""
+        import contextlib
+
+        return torch.cuda.stream(self._side) if self._side is not None else contextlib.nullcontext()
+
+    def _launch_wgrad(self, launch, st: int) -> None:
+        """Enqueue a weight-gradient GEMM (`launch(stream_handle)`) for the dy that the main stream has just produced:
+        on the main stream, or - two-stream mode - on the side stream, ordered after the dy producer; the dy buffer is
+        handed back to the rotation once this wgrad has read it."""
+        if self._side is None:
+            launch(st)
+            return
+        ready = torch.cuda.Event()
+        ready.record()
+        self._side.wait_event(ready)
+        launch(self._side.cuda_stream)
+        done = torch.cuda.Event()
+        done.record(self._side)
+        self._dy_free[self._dy_slot] = done
+
     def _residual_grad(self, op: ConvOp, gp, gld, is_init, mark, st) -> None:
         """Gradient of the post-activation residual add (darknet.py:28): identity into `res` unless it is aliased."""
         out, res = op.out, op.residual
@@ -821,8 +855,12 @@ class Runner:
         abase, sbase = run.act.data_ptr(), (run.stat.data_ptr() + 255) // 256 * 256
         gact = torch.empty(g.grad_bytes, dtype=torch.uint8, device=dev)  # mirrors the "act" prefix of the arena
         gbase = gact.data_ptr()
-        dyraw = torch.empty(g.dy_bytes + 1024, dtype=torch.uint8, device=dev)
-        dybase = (dyraw.data_ptr() + 1023) // 1024 * 1024
+        dy_stride = _round_up(g.dy_bytes, 1024)
+        dyraw = torch.empty(self._dy_slots * dy_stride + 1024, dtype=torch.uint8, device=dev)
+        dybase0 = (dyraw.data_ptr() + 1023) // 1024 * 1024
+        dybase = dybase0
+        self._dy_free = [None] * self._dy_slots   # per dy buffer: event after which its last wgrad reader is done
+        dy_turn = 0
         ws = torch.empty(g.ws_bytes + 1024, dtype=torch.uint8, device=dev)
         wsbase = (ws.data_ptr() + 1023) // 1024 * 1024
         # parameter gradients: fresh fp32 tensors handed to autograd, or (grad_sink mode, used by parallel.Trainer)
@@ -871,6 +909,18 @@ class Runner:
             check(self.fn_grad_add(gp(t), gld(t), go.data_ptr(), t.c, t.pixels, t.c, int(is_init(t)), st), "vtb_grad_add")
             mark(t)
 
+        def next_dy() -> int:
+            """dy buffer for the next BatchNorm backward (round robin; waits for the side-stream wgrad that read it last)."""
+            nonlocal dy_turn
+            slot = dy_turn % self._dy_slots
+            dy_turn += 1
+            self._dy_slot = slot
+            ev = self._dy_free[slot]
+            if ev is not None:
+                torch.cuda.current_stream(dev).wait_event(ev)
+                self._dy_free[slot] = None
+            return dybase0 + slot * dy_stride
+
         pending: list[tuple[TView, TView]] = []
         # gradient all-reduce overlap: only meaningful when gradients land directly in the caller's flat buffer
         ready_cb = self.dist.on_grads_ready if (self.dist is not None and self.grad_sink and all(direct)) else None
@@ -899,14 +949,15 @@ class Runner:
                             tg = gview(o.out)
                             self.view_tensor(gact, tg).zero_()
                             mark(o.out)
-                    self._conv_backward_pair(op_a, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world)
+                    self._conv_backward_pair(op_a, abase, sbase, gp, gld, is_init, mark, next_dy(), wsbase, pgrads, run, st, world)
                 else:
                     for o in (op_a, op):
                         for j in range(3):
                             pgrads[o.pidx + j].zero_()
                 if ready_cb is not None:
-                    ready_cb(g.params[op.pidx : op.pidx + 3])
-                    ready_cb(g.params[op_a.pidx : op_a.pidx + 3])
+                    with self._grad_stream_ctx():
+                        ready_cb(g.params[op.pidx : op.pidx + 3])
+                        ready_cb(g.params[op_a.pidx : op_a.pidx + 3])
                 flush_pending(False)
                 continue
             flush_pending(op.out)
@@ -921,9 +972,10 @@ class Runner:
                 continue
             if op.kind == "conv":
                 bwd = self._conv_backward_f32 if self.f32 else self._conv_backward
-                bwd(op, abase, sbase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, world)
+                bwd(op, abase, sbase, gp, gld, is_init, mark, next_dy(), wsbase, pgrads, run, st, world)
                 if ready_cb is not None:
-                    ready_cb(g.params[op.pidx : op.pidx + 3])
+                    with self._grad_stream_ctx():   # the all-reduce must also wait for the side-stream wgrad
+                        ready_cb(g.params[op.pidx : op.pidx + 3])
             elif op.kind == "pool":
                 xx, oo = op.x, op.out
                 if not (xx.is_input and not run.x_requires_grad):
@@ -949,6 +1001,8 @@ class Runner:
                     pending.append((rr, oo))
             flush_pending(False)
 
+        if self._side is not None:
+            torch.cuda.current_stream(dev).wait_stream(self._side)   # every weight gradient is final past this point
         gx = None
         if run.x_requires_grad:
             t = g.input
@@ -1009,12 +1063,13 @@ class Runner:
         x, out, res = op.x, op.out, op.residual
         dout_p, dout_ld = gp(out), gld(out)
         _, wd = self._packed(op)
+        self._launch_wgrad(lambda s_: check(L.vtb_conv_wgrad(C.byref(geom), dybase, cout, abase + x.byte_offset(), x.ld,
+                                                             wsbase, pgrads[op.pidx].data_ptr(), op.cin_real, 0, s_),
+                                            "vtb_conv_wgrad"), st)
         if not (x.is_input and not run.x_requires_grad):
             check(L.vtb_conv_dgrad(C.byref(geom), dybase, cout, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
                   "vtb_conv_dgrad")
             mark(x)
-        check(L.vtb_conv_wgrad(C.byref(geom), dybase, cout, abase + x.byte_offset(), x.ld, wsbase,
-                               pgrads[op.pidx].data_ptr(), op.cin_real, 0, st), "vtb_conv_wgrad")
         self._residual_grad(op, gp, gld, is_init, mark, st)
 
 
@@ -1065,7 +1120,8 @@ def run_native(module: nn.Module, x: torch.Tensor) -> list[torch.Tensor]:
     # sibling units run as one convolution when BatchNorm is finalised inside the conv kernel (VTB_PAIR=0: A/B switch)
     pair_ok = (_os.environ.get("VTB_PAIR", "1") == "1" and module.training and not f32
                and (dcfg is None or not dcfg.sync_bn or dcfg.world == 1 or dcfg.sync is not None))
-    key = (tuple(x.shape), module.training, need_grad, x.device.index, f32, pair_ok)
+    key = (tuple(x.shape), module.training, need_grad, x.device.index, f32, pair_ok,
+           dcfg is not None and dcfg.world > 1)
     plans = module.__dict__.setdefault("_vtb_plans", {})
     runner = plans.get(key)
     if runner is None:
@@ -1078,7 +1134,7 @@ def run_native(module: nn.Module, x: torch.Tensor) -> list[torch.Tensor]:
             for t in outs:
                 g.mark_output(t)
             g.finalize()
-            runner = Runner(g, x.device)
+            runner = Runner(g, x.device, dcfg)
         plans[key] = runner
         if len(plans) > 8:  # bound the cache (each plan only holds metadata)
             plans.pop(next(iter(plans)))
