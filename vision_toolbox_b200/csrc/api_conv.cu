@@ -243,19 +243,36 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin,
   constexpr int pitch = EW + 1;
   const size_t split_stride = (size_t)cout * kk * cin;
   if (e < cw) {
+    // the (tap, split) pairs are dealt round-robin to the SG split groups (fixed mapping -> deterministic), so every
+    // group has loads to issue even when the layer needed a single split (the big 3x3 layers: a pure transpose)
     const float* src = ws + (size_t)co * kk * cin + c0 + e;
-    for (int t = 0; t < kk; ++t) {
-      float acc = 0.f;
-#pragma unroll 4
-      for (int s = sg; s < splits; s += SG) acc += __ldg(src + (size_t)s * split_stride + (size_t)t * cin);
-      red_sm[(sg * kk + t) * pitch + e] = acc;
+    float* mine = red_sm + (size_t)sg * kk * pitch + e;
+    for (int t = 0; t < kk; ++t) mine[t * pitch] = 0.f;
+    const int total = kk * splits;
+    int q = sg;
+    for (; q + 3 * SG < total; q += 4 * SG) {   // 4 independent loads in flight
+      float v[4];
+      int tt[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int qq = q + u * SG;
+        const int t = qq / splits, sp = qq - t * splits;
+        tt[u] = t;
+        v[u] = __ldg(src + (size_t)sp * split_stride + (size_t)t * cin);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mine[tt[u] * pitch] += v[u];
+    }
+    for (; q < total; q += SG) {
+      const int t = q / splits, sp = q - t * splits;
+      mine[t * pitch] += __ldg(src + (size_t)sp * split_stride + (size_t)t * cin);
     }
   }
   __syncthreads();
   // output channels >= split belong to the second weight tensor of a side-by-side pair (dw2, indexed from 0)
   float* dst = (dw2 != nullptr && co >= split) ? dw2 + ((size_t)(co - split) * cin_real + c0) * kk
                                                : dw + ((size_t)co * cin_real + c0) * kk;
-  const int ngroups = min(SG, splits);
+  constexpr int ngroups = SG;
   for (int j = threadIdx.x; j < cr * kk; j += 256) {
     const int c = j / kk, t = j - c * kk;
     float v = 0.f;

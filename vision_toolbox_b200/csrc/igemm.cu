@@ -57,6 +57,16 @@ __device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloa
   float S[8], Q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) S[j] = Q[j] = 0.f;
+  // read-modify-write epilogue: issue every global read of this lane before the first dependent add, so the ROWS
+  // round trips overlap instead of serialising (the drain is latency-bound per warp)
+  uint4 old[ADD ? ROWS : 1];
+  if (ADD) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int rr = rg * ROWS + r;
+      old[r] = (rr < rows_valid) ? *reinterpret_cast<const uint4*>(gdst + (size_t)rr * ld + chunk * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
     const int rr = rg * ROWS + r;
@@ -66,7 +76,7 @@ __device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloa
     if (rr < rows_valid) {
       uint4* gp = reinterpret_cast<uint4*>(gdst + (size_t)rr * ld + chunk * 8);
       if (ADD) {
-        const uint4 ov = *gp;
+        const uint4 ov = old[r];
         const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(bf16lo(w[j]) + bf16lo(oo[j]), bf16hi(w[j]) + bf16hi(oo[j]));
