@@ -143,3 +143,34 @@ def test_training_steps_use_updated_weights(graph):
     for o, a, b in zip(outs, o_now, o_old):
         assert rel_err(o.float(), a) < BF16_TOL, rel_err(o.float(), a)
         assert rel_err(b, a) > 5 * BF16_TOL, "weights barely moved: the test would not see stale packs"
+
+
+def test_short_loss_curve_matches_cpu_reference_semantics():
+    """a short training run agrees with the reference semantics.  The same Trainer drives the
+    CPU composition (plain torch Conv2d / BatchNorm2d / ReLU modules = what the reference executes) in fp32 and the
+    native bf16 path on the GPU from identical weights and data: SGD momentum, weight decay on conv / linear weights only,
+    label smoothing, BatchNorm running statistics - every step's loss within 3 %, final running statistics within 5 %."""
+    from vision_toolbox_b200.parallel import Trainer
+
+    name = "model_cspdarknet"
+    g = load_golden(name)
+    torch.manual_seed(0)
+    head0 = torch.nn.Linear(32, 10)
+    x = torch.rand(8, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    y = torch.randint(0, 10, (8,), generator=torch.Generator().manual_seed(6))
+    curves, stats = [], []
+    for dev in ("cpu", "cuda"):
+        m = BUILDERS[name]()
+        m.load_state_dict(g["state_dict"])
+        head = torch.nn.Linear(32, 10)
+        head.load_state_dict(head0.state_dict())
+        m, head = m.to(dev).train(), head.to(dev)
+        tr = Trainer(m, head, lr=0.05, momentum=0.9, weight_decay=1e-3, label_smoothing=0.1)
+        curves.append([float(tr.step(x.to(dev), y.to(dev))) for _ in range(8)])
+        stats.append({k: v.detach().float().cpu() for k, v in m.state_dict().items() if "running" in k})
+    cpu, gpu = curves
+    assert cpu[-1] < 0.8 * cpu[0]                      # the run actually learns
+    for a, b in zip(cpu, gpu):
+        assert abs(a - b) < 0.03 * abs(a), (cpu, gpu)
+    for k in stats[0]:
+        assert rel_err(stats[1][k], stats[0][k]) < 5e-2, k
