@@ -2,6 +2,7 @@
 // materialisation, BatchNorm/ReLU backward (reduce + apply), gradient fan-in adds, layout conversion.
 // All activations are NHWC bf16 views (pointer + pixel pitch); one thread handles 8 channels (16 bytes).
 #include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 
 #include <cuda_bf16.h>
@@ -821,6 +822,23 @@ int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long lo
   void* args[] = {&dout_p, &lddo, &y_p, &ldy, &pixels, &c8, &cv, &scale, &shift, &mean, &invstd, &partial, &c, &count,
                   &dgamma, &dbeta, &accumulate, &sync, &dy_p, &lddy, &sp};
   count_launch(1);
+  // Single-GPU: an ordinary launch with programmatic stream serialization.  The grid is at most one 512-thread block per
+  // SM, every kernel that can still be running when these blocks are scheduled (the previous launch of this stream, a
+  // weight-gradient GEMM on the side stream) finishes without waiting for this one, so every block becomes resident and
+  // the hand-rolled grid barrier cannot deadlock - while the launch itself is cheaper than a cooperative one and its
+  // blocks may take SMs as the previous kernel drains.  With SyncBN peers (cross-rank spin inside the kernel, NCCL
+  // kernels on another stream) the co-residency GUARANTEE of the cooperative launch is kept.  VTB_BWD_COOP=1 forces it.
+  static const bool force_coop = getenv("VTB_BWD_COOP") != nullptr && atoi(getenv("VTB_BWD_COOP")) != 0;
+  if (peers == nullptr && !force_coop) {
+    cudaError_t e;
+    if (relu)
+      e = launch_pdl(bn_bwd_fused_kernel<true>, grid, block, sm, (cudaStream_t)stream, dout_p, lddo, y_p, ldy, pixels, c8, cv,
+                     scale, shift, mean, invstd, partial, c, count, dgamma, dbeta, accumulate, sync, dy_p, lddy, sp);
+    else
+      e = launch_pdl(bn_bwd_fused_kernel<false>, grid, block, sm, (cudaStream_t)stream, dout_p, lddo, y_p, ldy, pixels, c8, cv,
+                     scale, shift, mean, invstd, partial, c, count, dgamma, dbeta, accumulate, sync, dy_p, lddy, sp);
+    return check_cuda((int)e, "bn_bwd_fused_kernel");
+  }
   return check_cuda((int)cudaLaunchCooperativeKernel(fn, grid, block, args, sm, (cudaStream_t)stream),
                     "bn_bwd_fused_kernel");
 }
