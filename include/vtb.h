@@ -233,6 +233,19 @@ int vtb_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weigh
                 const float* gate, const void* dout, int lddo, void* dx, int lddx, int accumulate_dx, float* dweight,
                 float* dbias, int accumulate_dw, float* scratch, void* stream);
 
+/* ---- classifier head + loss of the training step (reference classifier.py:59-64, 92: nn.AdaptiveAvgPool2d(1), nn.Flatten,
+ * nn.Linear(C, K), F.cross_entropy(label_smoothing)) on the last feature map f (NHWC bf16 view, hw pixels per image).
+ * fwd: pooled [n][c] fp32 (spatial mean), logits [n][k] = pooled . weight^T + bias (fp32), row_loss [n], loss[0] = mean,
+ *      dlogits [n][k] = d loss / d logits (saved for backward).  labels: int64 class indices.  4 launches.
+ * bwd: dweight [k][c] (+)=, dbias [k] (+)=, df (NHWC bf16 view, may be NULL) = d loss / d f, all scaled by *gscale (the
+ *      upstream gradient of the scalar loss; NULL = 1).  scratch: n*k + n*c floats.  5 launches. */
+int vtb_head_ce_fwd(const void* f, int ldf, int n, int hw, int c, const float* weight, const float* bias, int k,
+                    const long long* labels, float label_smoothing, float* pooled, float* logits, float* dlogits,
+                    float* row_loss, float* loss, void* stream);
+int vtb_head_ce_bwd(const float* pooled, const float* dlogits, const float* weight, int n, int hw, int c, int k,
+                    const float* gscale, float* dweight, float* dbias, int accumulate, void* df, int lddf, float* scratch,
+                    void* stream);
+
 /* ---- fp32 parity mode ------------------------------------------------------------------------------------------------
  * BASELINE north_star: "forward feature maps and gradients within 1e-4 relative in fp32 mode" - the reference run WITHOUT
  * autocast (components.py:26-39 in fp32).  Same dataflow and view conventions as above, but every activation / gradient

@@ -88,6 +88,8 @@ SIGNATURES = {
     "vtb_maxpool3s2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p]),
     "vtb_ese_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),
     "vtb_ese_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i, _i, _p, _p, _i, _p, _p]),
+    "vtb_head_ce_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _f, _p, _p, _p, _p, _p, _p]),
+    "vtb_head_ce_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p]),
     # fp32 parity mode (csrc/parity_f32.cu)
     "vtb_f32_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),
     "vtb_f32_conv_fprop": (_i, [_cp, _p, _i, _p, _i, _p, _i, _p]),

@@ -186,7 +186,8 @@ __global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, in
 // ------------------------------------------------------------------ small fp32 GEMM for the eSE 1x1 "conv" on (N,C,1,1)
 // C[i][j] = sum_k A(i,k) * B(k,j), A(i,k) = a[i*sai + k*sak], B(k,j) = b[k*sbk + j*sbj]; operands optionally rounded to
 // bf16 first (autocast runs nn.Conv2d in bf16).  32x32 tiles, 16-deep k steps, 256 threads x (2x2) results.
-// EPI 0: plain store (scaled by alpha); 1: z / gate epilogue of the eSE forward; 2: accumulate-or-store (dW)
+// EPI 0: plain store (scaled by alpha); 1: z / gate epilogue of the eSE forward; 2: accumulate-or-store (dW);
+// 3: acc * alpha + bias[j] (the classifier head's nn.Linear)
 template <bool RA, bool RB, int EPI>
 __global__ void __launch_bounds__(256)
 small_gemm_kernel(const float* __restrict__ a, long long sai, long long sak, const float* __restrict__ b, long long sbk,
@@ -235,6 +236,8 @@ small_gemm_kernel(const float* __restrict__ a, long long sai, long long sak, con
         const float zz = v_rbf(acc[u][w] + v_rbf(bias[gj]));
         *dst = zz;
         out2[gi * ldc + gj] = v_rbf(fminf(fmaxf(zz * (1.f / 6.f) + 0.5f, 0.f), 1.f));
+      } else if (EPI == 3) {
+        *dst = fmaf(acc[u][w], alpha, bias[gj]);
       } else {
         *dst = accumulate ? *dst + acc[u][w] : acc[u][w];
       }
@@ -411,6 +414,91 @@ __global__ void ese_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, int ld
   }
 }
 
+// ------------------------------------------------------------------ classifier head (reference classifier.py:59-64, 92)
+// AdaptiveAvgPool2d(1) + Flatten + Linear(C, K) + cross_entropy(label_smoothing) on the last feature map.
+// One block per sample: log-sum-exp over the K logits (fixed reduction tree -> deterministic), the sample's loss
+//   (1 - eps) * (lse - z_y) + eps * (lse - mean_j z_j)          [torch.nn.functional.cross_entropy, label_smoothing = eps]
+// and d(mean loss) / d logits = (softmax - (1 - eps) * onehot - eps / K) / N.
+__device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, u) : v + u;
+  }
+  __syncthreads();   // sh may still be read by the previous reduction
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int w = 1; w < nw; ++w) r = is_max ? fmaxf(r, sh[w]) : r + sh[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+head_ce_kernel(const float* __restrict__ logits, int k, const long long* __restrict__ labels, float eps, float inv_n,
+               float* __restrict__ dlogits, float* __restrict__ row_loss) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float sh[8];
+  const int i = blockIdx.x;
+  const float* z = logits + (long long)i * k;
+  float m = -INFINITY, sz = 0.f;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const float v = z[j];
+    m = fmaxf(m, v);
+    sz += v;
+  }
+  m = block_reduce(m, sh, true);
+  sz = block_reduce(sz, sh, false);
+  float se = 0.f;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) se += expf(z[j] - m);
+  se = block_reduce(se, sh, false);
+  const float lse = m + logf(se);
+  const int y = (int)labels[i];
+  const float on = 1.f - eps, off = eps / (float)k;
+  for (int j = threadIdx.x; j < k; j += blockDim.x)
+    dlogits[(long long)i * k + j] = (expf(z[j] - lse) - (j == y ? on : 0.f) - off) * inv_n;
+  if (threadIdx.x == 0) row_loss[i] = on * (lse - z[y]) + eps * (lse - sz / (float)k);
+}
+
+// loss = mean of the per-sample losses (one block, fixed order)
+__global__ void __launch_bounds__(256) head_loss_mean_kernel(const float* __restrict__ row_loss, int n, float* __restrict__ loss) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += row_loss[i];
+  s = block_reduce(s, sh, false);
+  if (threadIdx.x == 0) *loss = s / (float)n;
+}
+
+// out = in * (*gscale)   (upstream gradient of the scalar loss; gscale == nullptr: 1)
+__global__ void head_scale_kernel(const float* __restrict__ in, const float* __restrict__ gscale, long long total,
+                                  float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const float g = gscale ? *gscale : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    out[i] = in[i] * g;
+}
+
+// df[n][pixel][c] = dpooled[n][c]   (gradient of the spatial mean; dpooled already carries the 1/hw factor)
+__global__ void head_broadcast_kernel(const float* __restrict__ dpooled, int hw, long long pixels, int c8,
+                                      __nv_bfloat16* __restrict__ df, int lddf) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = pixels * c8;
+  const int c = c8 * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / c8;
+    const int ch = (int)(i - pix * c8) * 8;
+    const long long img = pix / hw;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(dpooled + img * c + ch));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(dpooled + img * c + ch) + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    *reinterpret_cast<uint4*>(df + pix * lddf + ch) = v_pack8(f);
+  }
+}
+
 }  // namespace vtb
 
 using namespace vtb;
@@ -513,6 +601,57 @@ int vtb_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weigh
                                                                       pixels, c8, (__nv_bfloat16*)dx, lddx);
   count_launch(6);
   return check_cuda((int)cudaGetLastError(), "ese backward kernels");
+}
+
+int vtb_head_ce_fwd(const void* f, int ldf, int n, int hw, int c, const float* weight, const float* bias, int k,
+                    const long long* labels, float label_smoothing, float* pooled, float* logits, float* dlogits,
+                    float* row_loss, float* loss, void* stream) {
+  if (!VVIEW_OK(f, ldf, c) || c % 8 || n <= 0 || hw <= 0 || k <= 0 || !weight || !bias || !labels || !pooled || !logits ||
+      !dlogits || !row_loss || !loss || label_smoothing < 0.f || label_smoothing >= 1.f)
+    return fail(VTB_EINVAL, "vtb_head_ce_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int c8 = c / 8;
+  launch_pdl(hw_reduce_kernel<false>, dim3((c8 + 31) / 32, n), dim3(256), 0, st, (const __nv_bfloat16*)f, ldf,
+             (const __nv_bfloat16*)nullptr, 0, hw, c8, pooled, c, 1.f / (float)hw);
+  // logits[n][k] = pooled[n][:] . weight[k][:] + bias[k]
+  launch_pdl(small_gemm_kernel<false, false, 3>, dim3((k + 31) / 32, (n + 31) / 32), dim3(256), 0, st, (const float*)pooled,
+             (long long)c, 1LL, weight, 1LL, (long long)c, n, k, c, 1.f, logits, (long long)k, bias, (float*)nullptr, 0);
+  launch_pdl(head_ce_kernel, dim3(n), dim3(256), 0, st, (const float*)logits, k, labels, label_smoothing, 1.f / (float)n, dlogits,
+             row_loss);
+  launch_pdl(head_loss_mean_kernel, dim3(1), dim3(256), 0, st, (const float*)row_loss, n, loss);
+  count_launch(4);
+  return check_cuda((int)cudaGetLastError(), "vtb_head_ce_fwd");
+}
+
+int vtb_head_ce_bwd(const float* pooled, const float* dlogits, const float* weight, int n, int hw, int c, int k,
+                    const float* gscale, float* dweight, float* dbias, int accumulate, void* df, int lddf, float* scratch,
+                    void* stream) {
+  if (!pooled || !dlogits || !weight || n <= 0 || hw <= 0 || c <= 0 || c % 8 || k <= 0 || !dweight || !dbias || !scratch ||
+      (df && !VVIEW_OK(df, lddf, c)))
+    return fail(VTB_EINVAL, "vtb_head_ce_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nk = (long long)n * k;
+  float* dl = scratch;                 // [n][k]  dlogits * upstream gradient
+  float* dpooled = scratch + nk;       // [n][c]
+  launch_pdl(head_scale_kernel, dim3(vgrid(nk, 256)), dim3(256), 0, st, dlogits, gscale, nk, dl);
+  // dweight[k][c] (+)= sum_n dl[n][k] * pooled[n][c]
+  launch_pdl(small_gemm_kernel<false, false, 2>, dim3((c + 31) / 32, (k + 31) / 32), dim3(256), 0, st, (const float*)dl, 1LL,
+             (long long)k, pooled, (long long)c, 1LL, k, c, n, 1.f, dweight, (long long)c, (const float*)nullptr, (float*)nullptr,
+             accumulate);
+  launch_pdl(ese_dbias_kernel, dim3((k + 255) / 256), dim3(256), 0, st, (const float*)dl, n, k, dbias, accumulate);
+  int launches = 3;
+  if (df != nullptr) {
+    // dpooled[n][c] = (1/hw) * sum_k dl[n][k] * weight[k][c]
+    launch_pdl(small_gemm_kernel<false, false, 0>, dim3((c + 31) / 32, (n + 31) / 32), dim3(256), 0, st, (const float*)dl,
+               (long long)k, 1LL, weight, (long long)c, 1LL, n, c, k, 1.f / (float)hw, dpooled, (long long)c,
+               (const float*)nullptr, (float*)nullptr, 0);
+    const long long pixels = (long long)n * hw;
+    launch_pdl(head_broadcast_kernel, dim3(vgrid(pixels * (c / 8), 256)), dim3(256), 0, st, (const float*)dpooled, hw, pixels,
+               c / 8, (__nv_bfloat16*)df, lddf);
+    launches += 2;
+  }
+  count_launch(launches);
+  return check_cuda((int)cudaGetLastError(), "vtb_head_ce_bwd");
 }
 
 }  // extern "C"

@@ -19,6 +19,69 @@ from torch import nn
 from .engine import DistConfig
 
 
+class _HeadCEFn(torch.autograd.Function):
+    """Pooling + linear head + label-smoothed cross entropy of the reference trainer (classifier.py:59-64, 92) as two
+    C-ABI calls (``vtb_head_ce_fwd`` / ``vtb_head_ce_bwd``, 9 kernel launches per step instead of ~35 torch ones).
+
+    `f`: the backbone's last feature map - a logical (N, C, H, W) bf16 tensor with NHWC strides (what the native backbone
+    returns).  `sink`: write the head's parameter gradients straight into the existing fp32 ``.grad`` tensors (Trainer's
+    flat all-reduce buffer, overwriting) instead of handing fresh tensors to autograd."""
+
+    @staticmethod
+    def forward(ctx, f, weight, bias, labels, label_smoothing: float, sink: bool):
+        import ctypes as C
+
+        from . import _lib
+        from ._lib import check
+
+        L = _lib.lib()
+        n, c, h, w = f.shape
+        k = weight.shape[0]
+        assert f.dtype == torch.bfloat16 and f.stride(1) == 1 and f.stride(2) == w * f.stride(3), "NHWC bf16 view expected"
+        assert weight.dtype == torch.float32 and weight.is_contiguous() and bias.dtype == torch.float32
+        dev = f.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        pooled = torch.empty(n, c, dtype=torch.float32, device=dev)
+        logits = torch.empty(n, k, dtype=torch.float32, device=dev)
+        dlogits = torch.empty(n, k, dtype=torch.float32, device=dev)
+        row_loss = torch.empty(n, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        labels = labels.to(torch.int64).contiguous()
+        check(L.vtb_head_ce_fwd(f.data_ptr(), f.stride(3), n, h * w, c, weight.data_ptr(), bias.data_ptr(), k,
+                                labels.data_ptr(), float(label_smoothing), pooled.data_ptr(), logits.data_ptr(),
+                                dlogits.data_ptr(), row_loss.data_ptr(), loss.data_ptr(), st), "vtb_head_ce_fwd")
+        ctx.save_for_backward(pooled, dlogits, weight, bias)
+        ctx.geom = (n, c, h, w, k)
+        ctx.sink = sink
+        ctx.need_df = f.requires_grad
+        ctx.logits = logits
+        return loss.view(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gloss):
+        from . import _lib
+        from ._lib import check
+
+        L = _lib.lib()
+        pooled, dlogits, weight, bias = ctx.saved_tensors
+        n, c, h, w, k = ctx.geom
+        dev = pooled.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        g = gloss.detach().to(torch.float32).contiguous()
+        direct = (ctx.sink and weight.grad is not None and bias.grad is not None and weight.grad.dtype == torch.float32
+                  and weight.grad.is_contiguous() and bias.grad.is_contiguous())
+        dW = weight.grad if direct else torch.empty_like(weight)
+        db = bias.grad if direct else torch.empty_like(bias)
+        df = torch.empty((n, c, h, w), dtype=torch.bfloat16, device=dev,
+                         memory_format=torch.channels_last) if ctx.need_df else None
+        scratch = torch.empty(n * k + n * c, dtype=torch.float32, device=dev)
+        check(L.vtb_head_ce_bwd(pooled.data_ptr(), dlogits.data_ptr(), weight.data_ptr(), n, h * w, c, k, g.data_ptr(),
+                                dW.data_ptr(), db.data_ptr(), 0, 0 if df is None else df.data_ptr(), c,
+                                scratch.data_ptr(), st), "vtb_head_ce_bwd")
+        return df, (None if direct else dW), (None if direct else db), None, None, None
+
+
 def split_decay_groups(modules: list[nn.Module]):
     """classifier.py:141-169 — weight decay on conv / linear weights only, none on norm parameters and biases."""
     decay, no_decay = [], []
@@ -67,6 +130,13 @@ class Trainer:
         self.avg_in_collective = False
         self._graph = None
         self.graph_launches = 0
+        import os
+
+        # classifier head + loss through the C ABI (vtb_head_ce_*): correct (tests/test_gpu_parity.py) and 9 launches instead
+        # of ~35, but its fp32 SIMT GEMMs lose to cuBLAS on the 256 x 1000 x 1024 head: 15.10 vs 15.00 ms per step on the
+        # same box.  Off by default (VTB_NATIVE_HEAD=1 enables it) until the head GEMM runs on the tensor-core kernels.
+        self.native_head = (os.environ.get("VTB_NATIVE_HEAD", "0") == "1" and isinstance(head, nn.Linear)
+                            and head.bias is not None and head.weight.dtype == torch.float32)
         if process_group is not None:
             import torch.distributed as dist
 
@@ -148,6 +218,9 @@ class Trainer:
 
     def forward_loss(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         f = self.backbone(x)  # (N, C, H, W) bf16 on CUDA
+        if self.native_head and f.is_cuda and f.dtype == torch.bfloat16 and f.shape[1] % 8 == 0:
+            # pooling + linear + label-smoothed CE in the native library (head gradients land in the flat buffer)
+            return _HeadCEFn.apply(f, self.head.weight, self.head.bias, y, self.label_smoothing, True)
         pooled = f.float().mean(dim=(2, 3))  # AdaptiveAvgPool2d + Flatten (classifier.py:61-62)
         logits = self.head(pooled)
         return F.cross_entropy(logits, y, label_smoothing=self.label_smoothing)
