@@ -71,6 +71,8 @@ typedef struct VtbPackJob {
   int cout, cin_real, cin, kk;
   int wd_ld, wd_co_off;  /* wd_ld >= cout: two convolutions that share their input can be packed side by side into ONE
                             dgrad operand (CSP conv1 | conv2, darknet.py:52-53); plain case: wd_ld = cout, wd_co_off = 0 */
+  int wf_ld;             /* row pitch of wf in elements: kk * cin, or more (rows of the gathered-operand stem are padded
+                            to a multiple of 16 columns; the pad columns are never written - keep them zero) */
   long long first_block;
 } VtbPackJob;
 long long vtb_pack_job_blocks(int cout, int cin, int kk);
@@ -212,6 +214,15 @@ int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long lo
 /* dst (+)= src on bf16 NHWC views: gradient fan-out of the residual add (darknet.py:28) when it cannot be
  * aliased, and injection of incoming feature-map gradients. */
 int vtb_grad_add(void* dst, int ldd, const void* src, int lds, long long pixels, int c, int accumulate, void* stream);
+
+/* The image's FIRST convolution (stems: darknet.py:74,109, vovnet.py:85) as a 1x1 GEMM over a gathered operand:
+ * vtb_im2col_input writes out[n][ho][wo][kp] bf16, column t*c + ci = x[n][ci][ho*s-p+kh][wo*s-p+kw] (t = kh*k + kw, zero
+ * padding, columns >= k*k*c zero); the convolution is then called with VtbConv{n, ho, wo, cin = kp, cout, 1, 1, 0} and a
+ * weight packed by a VtbPackJob{cin_real = cin = c, kk = k*k, wf_ld = kp}.  Its weight gradient comes out in the same
+ * (tap, ci) column order, [cout][k*k*c]; vtb_dw_from_col permutes it to OIHW.  Used when the image needs no gradient. */
+int vtb_im2col_input(const float* x, int n, int c, int h, int w, int k, int stride, int pad, void* out, int kp,
+                     void* stream);
+int vtb_dw_from_col(const float* dw_col, int cout, int c, int kk, float* dw_oihw, int accumulate, void* stream);
 
 /* NCHW fp32 (the layout model(x) receives, tests/test_backbones.py:21) -> NHWC bf16, channels zero-padded
  * to cpad (the 3-channel image is stored with 16 channels for the tensor-core stem). */

@@ -88,3 +88,32 @@ def test_sibling_pair_plan():
         m._emit(gg, gg.input_image(2, 3, 32, 32))
         assert all(op.pair is None and op.pair_of is None for op in gg.ops if op.kind == "conv")
     m.train()
+
+
+def test_gathered_operand_stem_plan():
+    """The image's first convolution runs as a 1x1 GEMM over a gathered operand (k*k*3 taps -> columns, padded to 16) in
+    tensor-core plans whose input needs no gradient; the padded NHWC image buffer disappears from the arena."""
+    from vision_toolbox_b200.backbones import DarknetYOLOv5
+
+    cases = [(Darknet(16, [(1, 32)], CSPDarknetStage), (9, 3), 32, (32, 32)),
+             (DarknetYOLOv5(16, [(1, 32)]), (36, 3), 112, (16, 16)),
+             (VoVNet(32, [(1, 16, 2, 32)], ese=False), (9, 3), 32, (16, 16))]
+    for m, col, kp, hw in cases:
+        m.train()
+        g = engine.Graph(True, True, False, True, col_stem=True)
+        t_in = g.input_image(2, 3, 32, 32)
+        outs = m._emit(g, t_in)
+        for t in outs:
+            g.mark_output(t)
+        g.finalize()
+        stem = next(op for op in g.ops if op.kind == "conv")
+        assert stem.col == col and stem.x is g.input_col and stem.x.is_input
+        assert (stem.geom.k, stem.geom.stride, stem.geom.pad, stem.geom.cin) == (1, 1, 0, kp)
+        assert (stem.x.h, stem.x.w, stem.x.c) == (hw[0], hw[1], kp) and stem.cin_real == col[0] * col[1]
+        assert "dw_col" in stem.st and t_in.buf not in g.buffers and g.input_unused
+        assert sum(op.col is not None for op in g.ops if op.kind == "conv") == 1
+        # the same model with an image that needs a gradient, or in fp32 parity mode: the ordinary stem
+        for args in ((True, True, False, True, False), (True, True, True, True, True)):
+            gg = engine.Graph(*args)
+            m._emit(gg, gg.input_image(2, 3, 32, 32))
+            assert all(op.col is None for op in gg.ops if op.kind == "conv") and gg.input_col is None

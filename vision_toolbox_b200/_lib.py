@@ -36,7 +36,8 @@ class VtbPackJob(C.Structure):
     """struct VtbPackJob of include/vtb.h (one convolution's weight re-pack inside the batched launch)."""
 
     _fields_ = [("w", C.c_void_p), ("wf", C.c_void_p), ("wd", C.c_void_p), ("cout", C.c_int), ("cin_real", C.c_int),
-                ("cin", C.c_int), ("kk", C.c_int), ("wd_ld", C.c_int), ("wd_co_off", C.c_int), ("first_block", C.c_longlong)]
+                ("cin", C.c_int), ("kk", C.c_int), ("wd_ld", C.c_int), ("wd_co_off", C.c_int), ("wf_ld", C.c_int),
+                ("first_block", C.c_longlong)]
 
 
 class VtbSyncBn(C.Structure):
@@ -84,6 +85,8 @@ SIGNATURES = {
     "vtb_bn_bwd_fused": (_i, [_p, _i, _p, _i, _ll, _i, _p, _p, _p, _p, _i, _d, _p, _p, _p, _i, _p, _p, _i, _p, _p]),
     "vtb_grad_add": (_i, [_p, _i, _p, _i, _ll, _i, _i, _p]),
     "vtb_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),
+    "vtb_im2col_input": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "vtb_dw_from_col": (_i, [_p, _i, _i, _i, _p, _i, _p]),
     "vtb_maxpool3s2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
     "vtb_maxpool3s2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p]),
     "vtb_ese_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),

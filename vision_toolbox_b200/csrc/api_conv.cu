@@ -184,7 +184,7 @@ __device__ __forceinline__ void pack_tile(const VtbPackJob& J, int b, __nv_bfloa
     const int ci_l = e % cit, q = e / cit;
     const int t = q % kk, co_l = q / kk;
     const int co = co0 + co_l, ci = ci0 + ci_l;
-    if (co < J.cout && ci < J.cin) wf[((long long)co * kk + t) * J.cin + ci] = tile[(t * kPackCoT + co_l) * pitch + ci_l];
+    if (co < J.cout && ci < J.cin) wf[(long long)co * J.wf_ld + t * J.cin + ci] = tile[(t * kPackCoT + co_l) * pitch + ci_l];
   }
   if (wd != nullptr) {
     for (int e = threadIdx.x; e < kPackCoT * per_co; e += blockDim.x) {

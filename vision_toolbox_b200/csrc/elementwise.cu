@@ -653,6 +653,84 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, l
   }
 }
 
+// Image (NCHW fp32, c <= 4 channels) -> the GATHERED operand of its first convolution:
+//   out[n][ho][wo][t * c + ci] = x[n][ci][ho * s - p + kh][wo * s - p + kw],  t = kh * k + kw   (bf16; zero outside the
+// image and for columns >= k * k * c).  The first convolution then is a 1x1 GEMM over kp = round_up(k*k*c, 16) columns:
+// ONE TMA request per tile instead of one per tap - the few-channel stem is bound by the per-SM im2col request cadence
+// (~450 cycles per request whatever its size), not by bytes.  One thread per output pixel, 16-byte stores.
+// KS > 0: compile-time kernel size with 3 image channels (fully unrolled: the k*k*3 loads of a pixel are independent and
+// all in flight together); KS == 0: runtime k / c.
+template <int KS>
+__global__ void __launch_bounds__(256)
+im2col_input_kernel(const float* __restrict__ x, int n, int c, int h, int w, int k, int stride, int pad, int ho, int wo,
+                    __nv_bfloat16* __restrict__ out, int kp) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = (long long)n * ho * wo;
+  const long long hw = (long long)h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % wo);
+    const long long t0 = i / wo;
+    const int oh = (int)(t0 % ho);
+    const long long img = t0 / ho;
+    const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
+    if (KS > 0) {
+      constexpr int KR = (KS > 0 ? KS * KS * 3 : 1), KP = (KR + 15) / 16 * 16;
+      const float* xi = x + img * 3 * hw;
+      float f[KP];
+#pragma unroll
+      for (int q = 0; q < KP; ++q) f[q] = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < KS; ++kh) {
+        const int ih = ih0 + kh;
+        const bool rok = ih >= 0 && ih < h;
+#pragma unroll
+        for (int kw = 0; kw < KS; ++kw) {
+          const int iw = iw0 + kw;
+          if (rok && iw >= 0 && iw < w) {
+            const float* src = xi + (long long)ih * w + iw;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) f[(kh * KS + kw) * 3 + ci] = __ldg(src + ci * hw);
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < KP / 8; ++v) *reinterpret_cast<uint4*>(out + i * KP + v * 8) = pack8(f + v * 8);
+    } else {
+      const int kreal = k * k * c;
+      const float* xi = x + img * c * hw;
+      int ci = 0, kw = 0, kh = 0;
+      for (int v = 0; v < kp / 8; ++v) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float val = 0.f;
+          if (v * 8 + j < kreal) {
+            const int ih = ih0 + kh, iw = iw0 + kw;
+            if (ih >= 0 && ih < h && iw >= 0 && iw < w) val = __ldg(xi + ci * hw + (long long)ih * w + iw);
+            if (++ci == c) { ci = 0; if (++kw == k) { kw = 0; ++kh; } }
+          }
+          f[j] = val;
+        }
+        *reinterpret_cast<uint4*>(out + i * kp + v * 8) = pack8(f);
+      }
+    }
+  }
+}
+
+// weight gradient of the gathered-operand convolution, [cout][k*k*c] in (tap, ci) column order -> OIHW
+__global__ void dw_from_col_kernel(const float* __restrict__ dw_col, int cout, int c, int kk, float* __restrict__ dw,
+                                   int accumulate) {
+  pdl_wait();
+  pdl_trigger();
+  const int total = cout * c * kk;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i % kk, ci = (i / kk) % c, co = i / (kk * c);
+    const float v = dw_col[(long long)co * kk * c + t * c + ci];
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
 }  // namespace vtb
 
 using namespace vtb;
@@ -866,6 +944,32 @@ int vtb_nchw_to_nhwc(const float* x, int n, int c, int h, int w, void* out, int 
                                                                              (__nv_bfloat16*)out, cpad);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "nchw_to_nhwc_kernel");
+}
+
+int vtb_im2col_input(const float* x, int n, int c, int h, int w, int k, int stride, int pad, void* out, int kp,
+                     void* stream) {
+  if (!x || !out || n <= 0 || c <= 0 || c > 4 || h <= 0 || w <= 0 || k <= 0 || stride <= 0 || pad < 0 || kp % 8 ||
+      kp < k * k * c || (reinterpret_cast<uintptr_t>(out) & 15) || h + 2 * pad < k || w + 2 * pad < k)
+    return fail(VTB_EINVAL, "vtb_im2col_input: bad arguments");
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  const long long total = (long long)n * ho * wo;
+  const dim3 grid(ew_grid(total, 256));
+  if (c == 3 && k == 3 && kp == 32)
+    launch_pdl(im2col_input_kernel<3>, grid, dim3(256), 0, (cudaStream_t)stream, x, n, c, h, w, k, stride, pad, ho, wo,
+               (__nv_bfloat16*)out, kp);
+  else
+    launch_pdl(im2col_input_kernel<0>, grid, dim3(256), 0, (cudaStream_t)stream, x, n, c, h, w, k, stride, pad, ho, wo,
+               (__nv_bfloat16*)out, kp);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "im2col_input_kernel");
+}
+
+int vtb_dw_from_col(const float* dw_col, int cout, int c, int kk, float* dw_oihw, int accumulate, void* stream) {
+  if (!dw_col || !dw_oihw || cout <= 0 || c <= 0 || kk <= 0) return fail(VTB_EINVAL, "vtb_dw_from_col: bad arguments");
+  launch_pdl(dw_from_col_kernel, dim3((cout * c * kk + 255) / 256), dim3(256), 0, (cudaStream_t)stream, dw_col, cout, c, kk,
+             dw_oihw, accumulate);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "dw_from_col_kernel");
 }
 
 }  // extern "C"

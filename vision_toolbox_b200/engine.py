@@ -132,6 +132,8 @@ class ConvOp:
     pair: Any = None        # first op -> its partner
     pair_of: Any = None     # second op -> the first
     pair_geom: Any = None   # VtbConv with cout = both units (first op only)
+    # gathered-operand stem: (taps, image channels) when this op is the image's first convolution run as a 1x1 GEMM
+    col: Any = None
 
 
 @dataclass
@@ -157,7 +159,12 @@ class EseOp:
 # graph builder
 # ----------------------------------------------------------------------------------------------------
 class Graph:
-    def __init__(self, training: bool, need_grad: bool, f32: bool = False, pair_ok: bool = False):
+    def __init__(self, training: bool, need_grad: bool, f32: bool = False, pair_ok: bool = False,
+                 col_stem: bool = False):
+        # the image's first convolution as a 1x1 GEMM over a gathered operand (vtb_im2col_input): tensor-core plans whose
+        # input needs no gradient
+        self.col_stem = col_stem and not f32
+        self.input_col: Optional[TView] = None
         self.training = training
         self.need_grad = need_grad
         self.f32 = f32
@@ -236,12 +243,25 @@ class Graph:
         geom = VtbConv(x.n, x.h, x.w, x.c, cout, k, s, p)
         ho = (x.h + 2 * p - k) // s + 1
         wo = (x.w + 2 * p - k) // s + 1
+        col = None
+        if self.col_stem and x.is_input and x is self.input and cin_real <= 4 and self.input_col is None:
+            # stems (darknet.py:74,109; vovnet.py:85): gather the k*k*cin_real taps of every output pixel once
+            # (vtb_im2col_input) and run the convolution as a 1x1 GEMM: one TMA request per tile instead of one per tap
+            kcols = k * k * cin_real
+            xc = self.new_tensor(x.n, ho, wo, _round_up(kcols, 16))
+            xc.is_input = True
+            xc.col_of = (k, s, p, cin_real)
+            self.input_col = xc
+            col = (k * k, cin_real)
+            x, cin_real = xc, kcols
+            geom = VtbConv(xc.n, ho, wo, xc.c, cout, 1, 1, 0)
         if out is None:
             out = self.new_tensor(x.n, ho, wo, cout)
         assert (out.n, out.h, out.w, out.c) == (x.n, ho, wo, cout)
         if y is None:
             y = None if self.fused_eval else self.new_tensor(x.n, ho, wo, cout, "raw")
         op = ConvOp(mod, x, y, out, residual, mod.act_is_relu(), geom, cin_real)
+        op.col = col
         idx = len(self.ops)
         x.consumers.append(idx)
         if residual is not None:
@@ -272,6 +292,8 @@ class Graph:
             self._stat(op, "coef", cout * 2)
             self._stat(op, "sums_b", cout * 4)
             self._stat(op, "lsums_b", cout * 4)
+            if col is not None:
+                self._stat(op, "dw_col", cout * cin_real)   # weight gradient in (tap, ci) column order
             wsq = L.vtb_f32_conv_wgrad_workspace_bytes if self.f32 else L.vtb_conv_wgrad_workspace_bytes
             self.ws_bytes = max(self.ws_bytes, int(wsq(C.byref(geom))))
             self.dy_bytes = max(self.dy_bytes, out.pixels * cout * self.esize)
@@ -356,6 +378,11 @@ class Graph:
         self.outputs.append(t)
 
     def finalize(self) -> None:
+        if self.input_col is not None and self.input is not None and not self.input.consumers and not self.input.is_output:
+            self.buffers.remove(self.input.buf)   # the padded NHWC image is not needed: the stem reads the gathered operand
+            for i, b in enumerate(self.buffers):
+                b.idx = i
+            self.input_unused = True
         # materialised activations first (the gradient arena mirrors exactly this prefix), raw conv outputs after
         off = 0
         for b in self.buffers:
@@ -515,7 +542,17 @@ class Runner:
                 g = op.geom
                 n = g.cout * g.k * g.k * g.cin
                 first = op if op.pair is not None else op.pair_of
-                if first is not None:
+                if op.col is not None:
+                    # gathered-operand stem: rows of k*k*c columns in (tap, ci) order, padded to g.cin (pads stay zero)
+                    taps, creal = op.col
+                    cache = op.mod.__dict__.get("_vtb_wpack_col")
+                    if cache is None or cache[0].numel() != g.cout * g.cin or cache[0].device != w.device:
+                        cache = (torch.zeros(g.cout * g.cin, dtype=torch.bfloat16, device=w.device), None)
+                        op.mod.__dict__["_vtb_wpack_col"] = cache
+                    jobs[j] = _lib.VtbPackJob(w.data_ptr(), cache[0].data_ptr(), None, g.cout, creal, creal, taps, g.cout, 0,
+                                              g.cin, blk)
+                    nb = int(L.vtb_pack_job_blocks(g.cout, creal, taps))
+                elif first is not None:
                     # side-by-side pair: both units pack into ONE [tot][tap][cin] / [cin][tap][tot] operand pair
                     tot = first.pair_geom.cout
                     npair = tot * g.k * g.k * g.cin
@@ -527,7 +564,8 @@ class Runner:
                     co_off = 0 if op is first else first.geom.cout
                     wf_ptr = cache[0].data_ptr() + co_off * g.k * g.k * g.cin * BF16
                     jobs[j] = _lib.VtbPackJob(w.data_ptr(), wf_ptr, cache[1].data_ptr(), g.cout, op.cin_real,
-                                              g.cin, g.k * g.k, tot, co_off, blk)
+                                              g.cin, g.k * g.k, tot, co_off, g.k * g.k * g.cin, blk)
+                    nb = int(L.vtb_pack_job_blocks(g.cout, g.cin, g.k * g.k))
                 else:
                     cache = op.mod.__dict__.get("_vtb_wpack")
                     if cache is None or cache[0].numel() != n or cache[0].device != w.device:
@@ -535,8 +573,8 @@ class Runner:
                                  torch.empty(n, dtype=torch.bfloat16, device=w.device))
                         op.mod.__dict__["_vtb_wpack"] = cache
                     jobs[j] = _lib.VtbPackJob(w.data_ptr(), cache[0].data_ptr(), cache[1].data_ptr(), g.cout, op.cin_real,
-                                              g.cin, g.k * g.k, g.cout, 0, blk)
-                nb = int(L.vtb_pack_job_blocks(g.cout, g.cin, g.k * g.k))
+                                              g.cin, g.k * g.k, g.cout, 0, g.k * g.k * g.cin, blk)
+                    nb = int(L.vtb_pack_job_blocks(g.cout, g.cin, g.k * g.k))
                 if nb <= 0:
                     check(-1, "vtb_pack_job_blocks")
                 blk += nb
@@ -554,7 +592,7 @@ class Runner:
     @staticmethod
     def _packed(op: ConvOp):
         """(wf, wd) bf16 packs of this convolution, current as of the last forward of its module."""
-        return op.mod.__dict__["_vtb_wpack"]
+        return op.mod.__dict__["_vtb_wpack_col" if op.col is not None else "_vtb_wpack"]
 
     def view_tensor(self, arena: torch.Tensor, t: TView) -> torch.Tensor:
         """Zero-copy logical-NCHW (channels_last strided) tensor over a view of the arena."""
@@ -580,7 +618,13 @@ class Runner:
             xin = xin.float().contiguous()
         n, c, h, w = xin.shape
         t_in = g.input
-        check(self.fn_to_nhwc(xin.data_ptr(), n, c, h, w, abase + t_in.byte_offset(), t_in.c, st), "vtb_nchw_to_nhwc")
+        if g.input_col is not None:
+            xc = g.input_col
+            kk_, ss_, pp_, _ = xc.col_of
+            check(L.vtb_im2col_input(xin.data_ptr(), n, c, h, w, kk_, ss_, pp_, abase + xc.byte_offset(), xc.c, st),
+                  "vtb_im2col_input")
+        if not getattr(g, "input_unused", False):
+            check(self.fn_to_nhwc(xin.data_ptr(), n, c, h, w, abase + t_in.byte_offset(), t_in.c, st), "vtb_nchw_to_nhwc")
 
         if not self.f32:
             self._refresh_packs(st)
@@ -1063,9 +1107,21 @@ class Runner:
         x, out, res = op.x, op.out, op.residual
         dout_p, dout_ld = gp(out), gld(out)
         _, wd = self._packed(op)
-        self._launch_wgrad(lambda s_: check(L.vtb_conv_wgrad(C.byref(geom), dybase, cout, abase + x.byte_offset(), x.ld,
-                                                             wsbase, pgrads[op.pidx].data_ptr(), op.cin_real, 0, s_),
-                                            "vtb_conv_wgrad"), st)
+        if op.col is not None:
+            # gathered-operand stem: the GEMM yields [cout][taps * c] in (tap, ci) column order; permute to OIHW
+            taps, creal = op.col
+            dw_col = (run.stat.data_ptr() + 255) // 256 * 256 + 4 * op.st["dw_col"]
+
+            def launch(s_):
+                check(L.vtb_conv_wgrad(C.byref(geom), dybase, cout, abase + x.byte_offset(), x.ld, wsbase, dw_col,
+                                       op.cin_real, 0, s_), "vtb_conv_wgrad(stem)")
+                check(L.vtb_dw_from_col(dw_col, cout, creal, taps, pgrads[op.pidx].data_ptr(), 0, s_), "vtb_dw_from_col")
+
+            self._launch_wgrad(launch, st)
+        else:
+            self._launch_wgrad(lambda s_: check(L.vtb_conv_wgrad(C.byref(geom), dybase, cout, abase + x.byte_offset(), x.ld,
+                                                                 wsbase, pgrads[op.pidx].data_ptr(), op.cin_real, 0, s_),
+                                                "vtb_conv_wgrad"), st)
         if not (x.is_input and not run.x_requires_grad):
             check(L.vtb_conv_dgrad(C.byref(geom), dybase, cout, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
                   "vtb_conv_dgrad")
@@ -1120,13 +1176,16 @@ def run_native(module: nn.Module, x: torch.Tensor) -> list[torch.Tensor]:
     # sibling units run as one convolution when BatchNorm is finalised inside the conv kernel (VTB_PAIR=0: A/B switch)
     pair_ok = (_os.environ.get("VTB_PAIR", "1") == "1" and module.training and not f32
                and (dcfg is None or not dcfg.sync_bn or dcfg.world == 1 or dcfg.sync is not None))
+    # the image's first convolution as a 1x1 GEMM over a gathered operand, unless the image itself needs a gradient
+    col_stem = (_os.environ.get("VTB_COL_STEM", "1") == "1" and not f32
+                and not (torch.is_grad_enabled() and x.requires_grad))
     key = (tuple(x.shape), module.training, need_grad, x.device.index, f32, pair_ok,
-           dcfg is not None and dcfg.world > 1)
+           dcfg is not None and dcfg.world > 1, col_stem)
     plans = module.__dict__.setdefault("_vtb_plans", {})
     runner = plans.get(key)
     if runner is None:
         with torch.cuda.device(x.device):
-            g = Graph(module.training, need_grad, f32, pair_ok)
+            g = Graph(module.training, need_grad, f32, pair_ok, col_stem)
             t_in = g.input_image(*x.shape)
             outs = module._emit(g, t_in)
             if isinstance(outs, TView):
