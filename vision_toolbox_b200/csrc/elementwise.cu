@@ -664,6 +664,7 @@ template <int KS>
 __global__ void __launch_bounds__(256)
 im2col_input_kernel(const float* __restrict__ x, int n, int c, int h, int w, int k, int stride, int pad, int ho, int wo,
                     __nv_bfloat16* __restrict__ out, int kp) {
+  __shared__ uint4 stage[KS > 0 ? 8 * 128 : 1];
   pdl_wait();
   pdl_trigger();
   const long long total = (long long)n * ho * wo;
@@ -694,8 +695,27 @@ im2col_input_kernel(const float* __restrict__ x, int n, int c, int h, int w, int
           }
         }
       }
+      // a warp's 32 pixels are 32 * KP * 2 contiguous bytes of the output: stage the rows in shared memory (XOR-swizzled
+      // 16-byte chunks) and write them back with fully coalesced 512-byte store instructions
+      constexpr int CH = KP / 8;   // 16-byte chunks per pixel
+      const int ln = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+      const long long warp_base = i - ln;
+      if (CH == 4 && warp_base + 31 < total) {
+        uint4* st = stage + wrp * 128;
 #pragma unroll
-      for (int v = 0; v < KP / 8; ++v) *reinterpret_cast<uint4*>(out + i * KP + v * 8) = pack8(f + v * 8);
+        for (int v = 0; v < CH; ++v) st[ln * 4 + (v ^ ((ln >> 1) & 3))] = pack8(f + v * 8);
+        __syncwarp();
+        uint4* o16 = reinterpret_cast<uint4*>(out + warp_base * KP);
+#pragma unroll
+        for (int v = 0; v < CH; ++v) {
+          const int q = v * 32 + ln, pix = q >> 2, chunk = q & 3;
+          o16[q] = st[pix * 4 + (chunk ^ ((pix >> 1) & 3))];
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int v = 0; v < CH; ++v) *reinterpret_cast<uint4*>(out + i * KP + v * 8) = pack8(f + v * 8);
+      }
     } else {
       const int kreal = k * k * c;
       const float* xi = x + img * c * hw;
