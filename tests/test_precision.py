@@ -96,8 +96,11 @@ def test_gathered_operand_stem_plan():
     from vision_toolbox_b200.backbones import DarknetYOLOv5
 
     cases = [(Darknet(16, [(1, 32)], CSPDarknetStage), (9, 3), 32, (32, 32)),
-             (DarknetYOLOv5(16, [(1, 32)]), (36, 3), 112, (16, 16)),
              (VoVNet(32, [(1, 16, 2, 32)], ese=False), (9, 3), 32, (16, 16))]
+    # the 6x6 stride-2 YOLOv5 stem (108 taps) keeps the im2col descriptors
+    gy = engine.Graph(True, True, False, True, col_stem=True)
+    DarknetYOLOv5(16, [(1, 32)]).train()._emit(gy, gy.input_image(2, 3, 32, 32))
+    assert gy.input_col is None and all(op.col is None for op in gy.ops if op.kind == "conv")
     for m, col, kp, hw in cases:
         m.train()
         g = engine.Graph(True, True, False, True, col_stem=True)

@@ -32,7 +32,10 @@ def main(path: str, tag: str) -> None:
                  "Gbyte": 1e9, "nsecond": 1e-3}.get(u, 1.0)
         d[r[mi]] = v * scale
     ids = list(launches)
-    starts = [i for i, k in enumerate(ids) if "nchw_to_nhwc" in launches[k]["kernel"]]
+    # first kernel of a training step: the batched weight re-pack (older captures: the layout conversion)
+    starts = [i for i, k in enumerate(ids) if "pack_weights_batched" in launches[k]["kernel"]]
+    if not starts:
+        starts = [i for i, k in enumerate(ids) if "nchw_to_nhwc" in launches[k]["kernel"]]
     step = ids[starts[-1]:] if starts else ids
     agg, tot = collections.OrderedDict(), 0.0
     conv_bytes, conv_n = 0.0, 0
