@@ -120,3 +120,18 @@ def test_gathered_operand_stem_plan():
             gg = engine.Graph(*args)
             m._emit(gg, gg.input_image(2, 3, 32, 32))
             assert all(op.col is None for op in gg.ops if op.kind == "conv") and gg.input_col is None
+
+
+def test_channel_mismatch_raises_like_the_reference():
+    """A 4-channel image into the 3-channel stem: aten::convolution raises RuntimeError for the reference
+    (components.py:26); the planner must not silently read the first three channels of its padded NHWC buffer."""
+    m = Darknet(16, [(1, 32)], CSPDarknetStage).train()
+    for col in (False, True):
+        g = engine.Graph(True, True, False, True, col_stem=col)
+        with pytest.raises(RuntimeError, match="expected input to have 3 channels, but got 4"):
+            m._emit(g, g.input_image(2, 4, 32, 32))
+    from vision_toolbox_b200.components import ConvNormAct
+    unit = ConvNormAct(32, 64, 1)
+    g = engine.Graph(True, True)
+    with pytest.raises(RuntimeError, match="expected input to have 32 channels, but got 16"):
+        unit._emit(g, g.new_tensor(2, 8, 8, 16))

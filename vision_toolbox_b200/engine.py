@@ -238,6 +238,11 @@ class Graph:
                 "ConvNormAct options outside the Darknet/VoVNet hot path (groups/dilation/norm='none'/act other than "
                 "relu|none) have no sm_100a kernel; run that module on its own"
             )
+        have = self.input_c if (x.is_input and x is self.input) else x.c
+        if have != cin_real:
+            # what aten::convolution raises for the reference (components.py:26): the module tree decides, not the data
+            raise RuntimeError(f"Given groups=1, weight of size {list(conv.weight.shape)}, expected input to have "
+                               f"{cin_real} channels, but got {have} channels instead")
         if cout % 16 or x.c < cin_real or x.c % 16:
             raise NotImplementedError(f"channel counts must be multiples of 16 (got {cin_real}->{cout})")
         geom = VtbConv(x.n, x.h, x.w, x.c, cout, k, s, p)
