@@ -526,10 +526,12 @@ bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv
           sync_push(sp, sq, gc, a[0], a[1]);
           sync_push(sp, sq, gc + 1, a[2], a[3]);
         }
-        __threadfence_system();
-        __syncthreads();
-        if (t < sp.world) sync_signal_wait(sp, kSyncFlagsBwd, blockIdx.y, sq, t);
-        __syncthreads();
+        if (!sp.tagged) {
+          __threadfence_system();
+          __syncthreads();
+          if (t < sp.world) sync_signal_wait(sp, kSyncFlagsBwd, blockIdx.y, sq, t);
+          __syncthreads();
+        }
         if (t < pairs) {
           const int gc = blockIdx.y * cv * 8 + t * 2;
           const double2 v0 = sync_gather(sp, sq, gc), v1 = sync_gather(sp, sq, gc + 1);

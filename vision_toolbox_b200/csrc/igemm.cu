@@ -622,10 +622,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             named_bar_sync(1, kEpiWarps * 32);
             const unsigned int seq = *reinterpret_cast<volatile unsigned int*>(slots);
             if (et < p.block_n) sync_push(p.sync, seq, ch, sx, sq);
-            __threadfence_system();
-            named_bar_sync(1, kEpiWarps * 32);
-            if (et < p.sync.world) sync_signal_wait(p.sync, kSyncFlagsConv, n_blk, seq, et);
-            named_bar_sync(1, kEpiWarps * 32);
+            if (!p.sync.tagged) {   // flag protocol: make the pushes visible, publish / await the per-rank flags
+              __threadfence_system();
+              named_bar_sync(1, kEpiWarps * 32);
+              if (et < p.sync.world) sync_signal_wait(p.sync, kSyncFlagsConv, n_blk, seq, et);
+              named_bar_sync(1, kEpiWarps * 32);
+            }
             if (et < p.block_n) {
               const double2 v = sync_gather(p.sync, seq, ch);
               sx = v.x;

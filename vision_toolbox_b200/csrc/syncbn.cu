@@ -65,9 +65,11 @@ __device__ __forceinline__ void exchange_and_finalize(const float* __restrict__ 
     }
     __syncthreads();
   }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < peers.world) sync_signal_wait(peers, kSyncFlagsStd, 0, seq, threadIdx.x);
+  if (!peers.tagged) {
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < peers.world) sync_signal_wait(peers, kSyncFlagsStd, 0, seq, threadIdx.x);
+  }
   __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     const double2 v = sync_gather(peers, seq, ch);
