@@ -46,8 +46,8 @@ struct SyncPeers {
 
 inline SyncPeers make_sync_peers(const VtbSyncBn* s) {
   SyncPeers p;
-  static const int tagged_env = [] { const char* v = getenv("VTB_SYNC_TAGGED"); return v ? atoi(v) : 1; }();
-  p.tagged = tagged_env ? 1 : 0;
+  const char* tv = getenv("VTB_SYNC_TAGGED");   // read per call: tools/dp_check.py compares both protocols in one process
+  p.tagged = (tv == nullptr || atoi(tv) != 0) ? 1 : 0;
   for (int r = 0; r < kSyncMaxRanks; ++r) p.base[r] = (s && r < s->world) ? (unsigned char*)s->peer_buffers[r] : nullptr;
   p.rank = s ? s->rank : 0;
   p.world = s ? s->world : 1;
