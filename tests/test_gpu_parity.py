@@ -200,3 +200,39 @@ def test_native_head_and_loss_match_torch(shape):
     assert rel_err(ours[1], head.weight.grad) < 1e-4
     assert rel_err(ours[2], head.bias.grad) < 1e-4
     assert rel_err(ours[3], f2.grad) < 4e-3
+
+
+@pytest.mark.parametrize("name", ["stage_csp_2_16_32", "model_darknet", "model_vovnet_ese"])
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_frozen_statistics_backward(name, mode):
+    """eval() with gradients (fine-tuning with frozen BatchNorm): running statistics normalise, nothing updates them, and
+    the gradients are those of an affine layer - against the oracle run in eval mode.  Image with and without gradient
+    (the second uses the gathered-operand stem)."""
+    import vision_toolbox_b200 as vtb
+    from helpers import oracle_outputs
+
+    g = load_golden(name)
+    sd = g["state_dict"]
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    full = dict(sd)
+    full.update(params)
+    xo = g["x"].clone().requires_grad_(True)
+    outs_o = oracle_outputs(name, full, xo, False, mode)
+    grads_o = torch.autograd.grad(sum((o * c).sum() for o, c in zip(outs_o, g["cotangents"])), [xo] + list(params.values()))
+    ref = dict(zip(["__dx__"] + list(params), grads_o))
+    tol_f, tol_g = (2e-2, 6e-2) if mode == "bf16" else (1e-4, 1e-3)
+    for x_grad in (True, False):
+        m = _native(name, g, train=False)
+        x = g["x"].cuda().requires_grad_(x_grad)
+        with vtb.precision(mode):
+            outs = module_outputs(m, x)
+            sum((o.float() * c.cuda()).sum() for o, c in zip(outs, g["cotangents"])).backward()
+        torch.cuda.synchronize()
+        for o, r in zip(outs, outs_o):
+            assert rel_err(o.float(), r) < tol_f
+        for k, p in m.named_parameters():
+            assert rel_err(p.grad, ref[k]) < tol_g, (k, mode, x_grad, rel_err(p.grad, ref[k]))
+        if x_grad:
+            assert rel_err(x.grad, ref["__dx__"]) < tol_g
+        for k, v in sd.items():          # frozen: parameters and buffers untouched
+            assert torch.equal(m.state_dict()[k].cpu(), v), k
