@@ -236,3 +236,47 @@ def test_frozen_statistics_backward(name, mode):
             assert rel_err(x.grad, ref["__dx__"]) < tol_g
         for k, v in sd.items():          # frozen: parameters and buffers untouched
             assert torch.equal(m.state_dict()[k].cpu(), v), k
+
+
+@pytest.mark.parametrize("mode", ["fp32"])   # bf16 on 63 output pixels is ReLU-flip noise (a 3x3 stride-2 stem unit measured
+def test_unit_without_activation_batch_one_and_odd_inputs(mode):   # 1e-1 on dW against fp32 truth); fp32 mode is the sharp check
+    """ConvNormAct(act="none") (components.py:37-44), batch 1, odd sizes, an fp16 channels_last image: the CPU composition
+    of the same module (plain torch Conv2d / BatchNorm2d = the reference's arithmetic) on the same values is the yardstick."""
+    import copy
+
+    import vision_toolbox_b200 as vtb
+    from vision_toolbox_b200.components import ConvNormAct
+
+    # bf16 gradients of a unit on 63 output pixels sit at the mercy of a few ReLU-mask flips (SURVEY.md Appendix B: the
+    # reference's own autocast run is 5e-2 off on a much larger unit); the fp32 mode is the sharp check of these shapes
+    tol_f, tol_g = (2e-2, 2e-1) if mode == "bf16" else (1e-4, 1e-4)
+    torch.manual_seed(3)
+    for make, shape in ((lambda: ConvNormAct(32, 48, 3, act="none"), (1, 32, 7, 9)),
+                        (lambda: ConvNormAct(3, 32, 3, 2), (1, 3, 17, 13)),
+                        (lambda: ConvNormAct(16, 16, 1, act="none"), (3, 16, 5, 5))):
+        ref_mod = make().train()
+        with torch.no_grad():
+            ref_mod.norm.weight.uniform_(0.5, 1.5)
+            ref_mod.norm.bias.uniform_(-0.2, 0.2)
+        gpu = copy.deepcopy(ref_mod).cuda().train()
+        xh = torch.rand(shape).half().contiguous(memory_format=torch.channels_last)
+        xr = xh.float().contiguous().requires_grad_(True)
+        yr = ref_mod(xr)
+        cot = torch.randn(yr.shape)
+        (yr * cot).sum().backward()
+        with vtb.precision(mode):
+            xg = xh.cuda().requires_grad_(True)
+            yg = gpu(xg)
+            (yg.float() * cot.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        assert tuple(yg.shape) == tuple(yr.shape)
+        assert rel_err(yg.float(), yr) < tol_f, (mode, shape, rel_err(yg.float(), yr))
+        for (k, p), (_, q) in zip(gpu.named_parameters(), ref_mod.named_parameters()):
+            assert rel_err(p.grad, q.grad) < tol_g, (mode, shape, k, rel_err(p.grad, q.grad))
+        # image gradient: returned in the image's dtype (fp16 here: 2^-11 rounding); in bf16 mode the reference's own
+        # autocast run is ~5e-2 from fp32 truth on a unit's dX (SURVEY.md Appendix B: BatchNorm cancels most of it)
+        e_dx = rel_err(xg.grad.float(), xr.grad)
+        assert xg.grad.dtype == torch.float16 and e_dx < (2e-1 if mode == "bf16" else 1e-3), (mode, shape, e_dx)
+        for k, v in ref_mod.state_dict().items():
+            if "running" in k:
+                assert rel_err(gpu.state_dict()[k].cpu(), v) < (2e-3 if mode == "bf16" else 1e-5), k
