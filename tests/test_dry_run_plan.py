@@ -76,7 +76,10 @@ def _views(name, a, es):
     if base in ("vtb_conv_fprop", "vtb_conv_fprop_bn"):
         g, pin, pout = _geom(a[0])
         y = (a[5], a[6]) if f32 else (a[4], a[5])
-        return [(a[1], a[2], pin, g.cin, "r"), (y[0], y[1], pout, g.cout, "w")]
+        v = [(a[1], a[2], pin, g.cin, "r"), (y[0], y[1], pout, g.cout, "w")]
+        if base == "vtb_conv_fprop" and not f32 and a[10]:      # eval-mode fused epilogue: + residual
+            v.append((a[10], a[11], pout, g.cout, "r"))
+        return v
     if base == "vtb_conv_dgrad":
         g, pin, pout = _geom(a[0])
         dx, ld, acc = (a[5], a[6], a[7]) if f32 else (a[4], a[5], a[6])
@@ -126,9 +129,9 @@ class FakeDist:
         self.reduced += 1
 
 
-def _dry_run(model, shape, f32, need_input_grad=False, dist=None):
-    model.train()
-    g = engine.Graph(True, True, f32, pair_ok=dist is None, col_stem=not need_input_grad)
+def _dry_run(model, shape, f32, need_input_grad=False, dist=None, training=True, need_grad=True):
+    model.train(training)
+    g = engine.Graph(training, need_grad, f32, pair_ok=dist is None, col_stem=not need_input_grad)
     outs = model._emit(g, g.input_image(*shape))
     for t in ([outs] if isinstance(outs, engine.TView) else outs):
         g.mark_output(t)
@@ -153,6 +156,11 @@ def _dry_run(model, shape, f32, need_input_grad=False, dist=None):
     with mock.patch.object(engine.torch, "empty", rec(real_empty)), mock.patch.object(engine.torch, "zeros", rec(real_zeros)):
         outs_t, run = runner.forward(x)
         n_fwd = len(lib.calls)
+        if not need_grad:
+            for i, (name, a) in enumerate(lib.calls):
+                for ptr, ld, pixels, c, mode in _views(name, a, 4 if f32 else 2):
+                    assert allocs.inside(ptr, ptr + ((pixels - 1) * ld + c) * (4 if f32 else 2)), (i, name)
+            return g, lib.calls, n_fwd
         tdt = torch.float32 if f32 else torch.bfloat16
         gouts = [torch.ones(o.shape, dtype=tdt).contiguous(memory_format=torch.channels_last) for o in outs_t]
         for t in gouts:
@@ -222,6 +230,28 @@ def test_launch_list_with_all_reduce_syncbn(f32):
     names = Counter(n for n, _ in calls)
     assert names["vtb_bn_finalize"] == units and names["vtb_bn_bwd_finalize"] == (units if f32 else 2 * units)
     assert names["vtb_conv_fprop_bn"] == 0 and names["vtb_bn_bwd_fused"] == 0
+
+
+@pytest.mark.parametrize("f32", [False, True], ids=["bf16", "fp32"])
+def test_eval_and_frozen_statistics_plans(f32):
+    """eval() without gradients: one fused conv + affine + ReLU (+ residual) launch per unit in bf16 mode, conv + normalise
+    in fp32 mode; eval() with gradients (frozen BatchNorm): the unfused backward."""
+    m = backbones.Darknet(16, [(1, 32), (2, 64)], CSPDarknetStage)
+    g, calls, _ = _dry_run(m, (2, 3, 32, 32), f32, training=False, need_grad=False)
+    units = sum(op.kind == "conv" for op in g.ops)
+    names = Counter(n for n, _ in calls)
+    if f32:
+        assert names["vtb_f32_conv_fprop"] == units == names["vtb_f32_bn_act"] and g.fused_eval is False
+    else:
+        assert names["vtb_conv_fprop"] == units == names["vtb_bn_eval_affine"] and names["vtb_bn_act"] == 0
+        assert all(op.pair is None for op in g.ops if op.kind == "conv")        # no pairing outside training plans
+    g, calls, n_fwd = _dry_run(m, (2, 3, 32, 32), f32, training=False, need_grad=True)
+    bwd = Counter(n for n, _ in calls[n_fwd:])
+    pre = "vtb_f32_" if f32 else "vtb_"
+    assert bwd[pre + "bn_bwd_apply"] == units and bwd["vtb_bn_bwd_finalize"] == units and bwd["vtb_bn_bwd_fused"] == 0
+    vov = backbones.VoVNet(32, [(1, 16, 2, 32), (2, 16, 3, 32)], ese=True)
+    _dry_run(vov, (2, 3, 32, 32), f32, training=False, need_grad=False)
+    _dry_run(vov, (2, 3, 32, 32), f32, training=False, need_grad=True)
 
 
 def test_launch_counts_cspdarknet53():
