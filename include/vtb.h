@@ -219,7 +219,8 @@ int vtb_grad_add(void* dst, int ldd, const void* src, int lds, long long pixels,
  * vtb_im2col_input writes out[n][ho][wo][kp] bf16, column t*c + ci = x[n][ci][ho*s-p+kh][wo*s-p+kw] (t = kh*k + kw, zero
  * padding, columns >= k*k*c zero); the convolution is then called with VtbConv{n, ho, wo, cin = kp, cout, 1, 1, 0} and a
  * weight packed by a VtbPackJob{cin_real = cin = c, kk = k*k, wf_ld = kp}.  Its weight gradient comes out in the same
- * (tap, ci) column order, [cout][k*k*c]; vtb_dw_from_col permutes it to OIHW.  Used when the image needs no gradient. */
+ * (tap, ci) column order, [cout][k*k*c]; vtb_dw_from_col permutes it to OIHW.  Used when the image needs no gradient.
+ * The host side uses it for k = 3, c = 3 (kp = 32), the case every stem of the path has and the one the parity tests cover. */
 int vtb_im2col_input(const float* x, int n, int c, int h, int w, int k, int stride, int pad, void* out, int kp,
                      void* stream);
 int vtb_dw_from_col(const float* dw_col, int cout, int c, int kk, float* dw_oihw, int accumulate, void* stream);

@@ -249,9 +249,9 @@ class Graph:
         ho = (x.h + 2 * p - k) // s + 1
         wo = (x.w + 2 * p - k) // s + 1
         col = None
-        if (self.col_stem and x.is_input and x is self.input and cin_real <= 4 and k * k * cin_real <= 32
+        if (self.col_stem and x.is_input and x is self.input and cin_real == 3 and k == 3
                 and self.input_col is None):
-            # 3x3 stems (darknet.py:74; vovnet.py:85): gather the k*k*cin_real <= 32 taps of every output pixel once
+            # 3x3 RGB stems (darknet.py:74; vovnet.py:85): gather the 27 taps of every output pixel once
             # (vtb_im2col_input) and run the convolution as a 1x1 GEMM: one TMA request per tile instead of one per tap
             # (the 6x6 YOLOv5 stem keeps the im2col descriptors: 108 gathered columns cost more than they save, 4.38 ->
             # 4.62 ms per 32 x 640^2 forward)
