@@ -175,7 +175,7 @@ def reference_arm(args, rank: int, world: int) -> None:
                 p.add_(m, alpha=-0.05)
             for k, v in new_stats.items():
                 sd[k] = v
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(args.warmup):
         step()
