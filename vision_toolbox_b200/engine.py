@@ -1,10 +1,16 @@
 """Graph planner + executor behind the drop-in modules.
 
 A module tree (ConvNormAct, DarknetBlock, CSPDarknetStage, OSABlock, Darknet, VoVNet ...) *emits* itself into
-a :class:`Graph` once per (input shape, mode).  The graph is a static list of ops over NHWC bf16 views that
-live in one activation arena (concatenations are channel slices of one buffer, so ``torch.cat`` of reference
-darknet.py:53 / vovnet.py:55 never runs).  :class:`Runner` replays that list through the C ABI
+a :class:`Graph` once per (input shape, mode, precision).  The graph is a static list of ops over NHWC views
+(bf16, or fp32 in parity mode) that live in one activation arena (concatenations are channel slices of one buffer, so
+``torch.cat`` of reference darknet.py:53 / vovnet.py:55 never runs).  :class:`Runner` replays that list through the C ABI
 (``include/vtb.h``) on the current CUDA stream, forward and backward; autograd sees ONE node per call.
+
+Plan-level transformations (all decided when the graph is built, all covered by tests/test_precision.py and the CPU dry
+run of tests/test_dry_run_plan.py): sibling units that read the same tensor run as one convolution
+(``conv_norm_act_pair``), 3x3 RGB stems run as a 1x1 GEMM over a gathered operand, residual gradients alias the block
+output's gradient memory, weight-gradient GEMMs go to a second stream in single-process plans, every convolution's bf16
+operand packs are rebuilt by one launch per forward.
 
 No op here has a torch/cuDNN implementation: if libvtb_b200.so is missing, loading it raises.
 """
@@ -377,9 +383,6 @@ class Graph:
             self._stat(op, "scratch", 3 * x.n * x.c)
         self.ops.append(op)
         return out
-
-    def add_residual(self, a: TView, b: TView) -> TView:
-        raise NotImplementedError("bare adds are fused into the producing ConvNormAct / ESE op")
 
     def mark_output(self, t: TView) -> None:
         t.is_output = True
