@@ -171,6 +171,7 @@ class Graph:
         # input needs no gradient
         self.col_stem = col_stem and not f32
         self.input_col: Optional[TView] = None
+        self.input_unused = False   # set by finalize(): the padded NHWC image left the arena (gathered-operand stem)
         self.training = training
         self.need_grad = need_grad
         self.f32 = f32
@@ -634,7 +635,7 @@ class Runner:
             kk_, ss_, pp_, _ = xc.col_of
             check(L.vtb_im2col_input(xin.data_ptr(), n, c, h, w, kk_, ss_, pp_, abase + xc.byte_offset(), xc.c, st),
                   "vtb_im2col_input")
-        if not getattr(g, "input_unused", False):
+        if not g.input_unused:
             check(self.fn_to_nhwc(xin.data_ptr(), n, c, h, w, abase + t_in.byte_offset(), t_in.c, st), "vtb_nchw_to_nhwc")
 
         if not self.f32:

@@ -29,8 +29,6 @@ class _HeadCEFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, f, weight, bias, labels, label_smoothing: float, sink: bool):
-        import ctypes as C
-
         from . import _lib
         from ._lib import check
 
