@@ -1,0 +1,101 @@
+"""The executor on the CPU against the reference's golden vectors, through tests/fake_vtb.InterpreterLib (a torch-CPU
+implementation of the C ABI's documented semantics).  Verifies the HOST side of the product - plans, buffer slicing,
+gradient routing, sibling pairing, the gathered-operand stem, the pack job table - with real numbers and no GPU; the CUDA
+kernels meet the same goldens in tests/test_gpu_parity.py."""
+from unittest import mock
+
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden, rel_err
+from fake_vtb import InterpreterLib
+from helpers import BUILDERS
+from vision_toolbox_b200 import engine
+from vision_toolbox_b200.backbones.base import BaseBackbone
+
+
+def _run(name, g, training, need_grad, x_grad, pair=True, col=True):
+    m = BUILDERS[name]()
+    m.load_state_dict(g["state_dict"])
+    m.train(training)
+    graph = engine.Graph(training, need_grad, False, pair_ok=pair, col_stem=col and not x_grad)
+    t_in = graph.input_image(*g["x"].shape)
+    outs = m._emit(graph, t_in) if not isinstance(m, BaseBackbone) else m._emit(graph, t_in)
+    for t in ([outs] if isinstance(outs, engine.TView) else outs):
+        graph.mark_output(t)
+    graph.finalize()
+    lib = InterpreterLib()
+    with mock.patch.object(engine._lib, "lib", return_value=lib):
+        runner = engine.Runner(graph, torch.device("cpu"))
+    runner._stream = lambda: 0
+    x = g["x"].clone().requires_grad_(x_grad)
+    outs_t, run = runner.forward(x)
+    outs_f = [o.float().clone() for o in outs_t]
+    if not need_grad:
+        return m, graph, outs_f, None, None
+    gouts = [c.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for c in g["cotangents"]]
+    gx, pgrads = runner.backward(run, gouts)
+    grads = {}
+    names = {id(p): k for k, p in m.named_parameters()}
+    for p, gr in zip(graph.params, pgrads):
+        grads[names[id(p)]] = gr.clone()
+    return m, graph, outs_f, grads, gx
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_train_forward_and_statistics(name):
+    g = load_golden(name)
+    with torch.no_grad():
+        m, graph, outs, _, _ = _run(name, g, True, False, False)
+    for o, ref in zip(outs, g["train_bf16_outs"]):
+        assert tuple(o.shape) == tuple(ref.shape) and rel_err(o, ref) < 2e-2, (name, rel_err(o, ref))
+    sd = m.state_dict()
+    for k, ref in g["buffers_after_bf16_step"].items():
+        assert rel_err(sd[k].float(), ref) < 2e-3, k
+    for k, ref in g["buffers_after_step"].items():
+        if "num_batches" in k:
+            assert int(sd[k]) == int(ref), k
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_eval_forward(name):
+    g = load_golden(name)
+    with torch.no_grad():
+        m, graph, outs, _, _ = _run(name, g, False, False, False)
+    assert graph.fused_eval
+    for o, ref in zip(outs, g["eval_fp32_outs"]):
+        assert rel_err(o, ref) < 2e-2
+    for k, v in g["state_dict"].items():
+        assert torch.equal(m.state_dict()[k], v), k
+
+
+@pytest.mark.parametrize("x_grad", [False, True], ids=["stem-gathered", "image-gradient"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_train_backward(name, x_grad):
+    g = load_golden(name)
+    m, graph, outs, grads, gx = _run(name, g, True, True, x_grad)
+    ref16, ref32 = dict(g["train_bf16_dparams"]), dict(g["train_fp32_dparams"])
+    if x_grad:
+        grads["__dx__"], ref16["__dx__"], ref32["__dx__"] = gx, g["train_bf16_dx"], g["train_fp32_dx"]
+    else:
+        assert gx is None
+    assert set(grads) == set(ref32)
+    for k in ref32:
+        assert grads[k].shape == ref32[k].shape and torch.isfinite(grads[k]).all(), k
+        e_ours, e_ref = rel_err(grads[k], ref32[k]), rel_err(ref16[k], ref32[k])
+        assert e_ours < 2.0 * e_ref + 1e-2, (name, k, e_ours, e_ref)     # SURVEY.md Appendix B criterion
+
+
+def test_pairing_and_gathered_stem_do_not_change_the_result():
+    """The plan-level transformations are exact rewrites: same numbers with and without them (up to the summation order of
+    the torch kernels the interpreter uses)."""
+    name = "model_cspdarknet"
+    g = load_golden(name)
+    _, g1, o1, gr1, _ = _run(name, g, True, True, False, pair=True, col=True)
+    _, g0, o0, gr0, _ = _run(name, g, True, True, False, pair=False, col=False)
+    assert any(op.pair is not None for op in g1.ops if op.kind == "conv") and g1.input_col is not None
+    assert all(op.pair is None for op in g0.ops if op.kind == "conv") and g0.input_col is None
+    for a, b in zip(o1, o0):
+        assert rel_err(a, b) < 1e-2
+    for k in gr0:
+        assert rel_err(gr1[k], gr0[k]) < 2e-2, k
