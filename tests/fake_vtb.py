@@ -311,3 +311,156 @@ class InterpreterLib:
         new = (g * gt[:, None, :] + dpool[:, None, :]).reshape(n * hw, c)
         dst = _view(dx, lddx, n * hw, c)
         dst.copy_(((_r(new) + dst.float()) if acc_dx else new).to(BF16))
+
+    # ---------------------------------------------------------------- fp32 parity mode (vtb_f32_*)
+    def _vtb_f32_nchw_to_nhwc(self, x, n, c, h, w, out, cpad, st):
+        src = _flat(x, n * c * h * w, torch.float32).view(n, c, h, w)
+        dst = _view(out, cpad, n * h * w, cpad, torch.float32)
+        dst.zero_()
+        dst[:, :c] = src.permute(0, 2, 3, 1).reshape(-1, c)
+
+    @staticmethod
+    def _w32(g, w, cin_real):
+        """OIHW fp32 master, zero-extended to the padded channel count of the operand view."""
+        src = _flat(w, g.cout * cin_real * g.k * g.k, torch.float32).view(g.cout, cin_real, g.k, g.k)
+        full = torch.zeros(g.cout, g.cin, g.k, g.k)
+        full[:, :cin_real] = src
+        return full
+
+    def _vtb_f32_conv_fprop(self, geom, x, ldx, w, cin_real, y, ldy, st):
+        g = _obj(geom)
+        ho, wo = self._hw(g)
+        xi = _view(x, ldx, g.n * g.h * g.w, g.cin, torch.float32).view(g.n, g.h, g.w, g.cin).permute(0, 3, 1, 2)
+        out = F.conv2d(xi, self._w32(g, w, cin_real), None, g.stride, g.pad)
+        _view(y, ldy, g.n * ho * wo, g.cout, torch.float32).copy_(out.permute(0, 2, 3, 1).reshape(-1, g.cout))
+
+    def _vtb_f32_conv_dgrad(self, geom, dy, lddy, w, cin_real, dx, lddx, accumulate, st):
+        g = _obj(geom)
+        ho, wo = self._hw(g)
+        gy = _view(dy, lddy, g.n * ho * wo, g.cout, torch.float32).view(g.n, ho, wo, g.cout).permute(0, 3, 1, 2)
+        gx = torch.nn.grad.conv2d_input((g.n, g.cin, g.h, g.w), self._w32(g, w, cin_real), gy, g.stride, g.pad)
+        gx = gx.permute(0, 2, 3, 1).reshape(g.n * g.h * g.w, g.cin)
+        dst = _view(dx, lddx, gx.shape[0], g.cin, torch.float32)
+        dst.copy_(dst + gx if accumulate else gx)
+
+    def _vtb_f32_conv_wgrad(self, geom, dy, lddy, x, ldx, ws, dw, cin_real, accumulate, st):
+        g = _obj(geom)
+        ho, wo = self._hw(g)
+        gy = _view(dy, lddy, g.n * ho * wo, g.cout, torch.float32).view(g.n, ho, wo, g.cout).permute(0, 3, 1, 2)
+        xi = _view(x, ldx, g.n * g.h * g.w, g.cin, torch.float32).view(g.n, g.h, g.w, g.cin).permute(0, 3, 1, 2)
+        new = torch.nn.grad.conv2d_weight(xi, (g.cout, g.cin, g.k, g.k), gy, g.stride, g.pad)[:, :cin_real].reshape(-1)
+        dst = _flat(dw, new.numel(), torch.float32)
+        dst.copy_(dst + new if accumulate else new)
+
+    def _vtb_f32_bn_stats(self, y, ldy, pixels, c, partial, sums, st):
+        yv = _view(y, ldy, pixels, c, torch.float32).double()
+        _flat(sums, 2 * c, torch.float64).copy_(torch.stack([yv.sum(0), (yv * yv).sum(0)], 1).reshape(-1))
+
+    def _vtb_bn_finalize(self, partial, rows, sums, count, c, gamma, beta, eps, momentum, rm, rv, nbt, mean, invstd, scale,
+                         shift, st):
+        if sums:
+            s = _flat(sums, 2 * c, torch.float64).view(c, 2)
+        else:
+            s = _flat(partial, rows * c * 2, torch.float32).view(rows, c, 2).double().sum(0)
+        mu = s[:, 0] / count
+        var = (s[:, 1] / count - mu * mu).clamp_min(0)
+        istd = (1.0 / torch.sqrt(var + eps)).float()
+        sc = _flat(gamma, c, torch.float32) * istd
+        _flat(mean, c, torch.float32).copy_(mu.float())
+        _flat(invstd, c, torch.float32).copy_(istd)
+        _flat(scale, c, torch.float32).copy_(sc)
+        _flat(shift, c, torch.float32).copy_(_flat(beta, c, torch.float32) - mu.float() * sc)
+        if rm:
+            unbiased = var * (count / (count - 1.0)) if count > 1 else var
+            _flat(rm, c, torch.float32).mul_(1 - momentum).add_(momentum * mu.float())
+            _flat(rv, c, torch.float32).mul_(1 - momentum).add_(momentum * unbiased.float())
+        if nbt:
+            _flat(nbt, 1, torch.int64).add_(1)
+
+    def _vtb_bn_stats_reduce(self, partial, rows, c, sums, st):
+        _flat(sums, 2 * c, torch.float64).copy_(
+            _flat(partial, rows * c * 2, torch.float32).view(rows, c, 2).double().sum(0).reshape(-1))
+
+    @staticmethod
+    def _bn32(yv, mean, invstd, gamma, beta, c):
+        f = lambda p: _flat(p, c, torch.float32)
+        return (yv - f(mean)) * f(invstd) * f(gamma) + f(beta)
+
+    def _vtb_f32_bn_act(self, y, ldy, pixels, c, mean, invstd, gamma, beta, relu, res, ldr, out, ldo, st):
+        z = self._bn32(_view(y, ldy, pixels, c, torch.float32), mean, invstd, gamma, beta, c)
+        if relu:
+            z = z.clamp_min(0)
+        if res:
+            z = z + _view(res, ldr, pixels, c, torch.float32)
+        _view(out, ldo, pixels, c, torch.float32).copy_(z)
+
+    def _dz32(self, dout, lddo, y, ldy, pixels, c, mean, invstd, gamma, beta, relu):
+        yv = _view(y, ldy, pixels, c, torch.float32)
+        dz = _view(dout, lddo, pixels, c, torch.float32).clone()
+        if relu:
+            dz = torch.where(self._bn32(yv, mean, invstd, gamma, beta, c) > 0, dz, torch.zeros_like(dz))
+        return dz, (yv - _flat(mean, c, torch.float32)) * _flat(invstd, c, torch.float32)
+
+    def _vtb_f32_bn_bwd_reduce(self, dout, lddo, y, ldy, pixels, c, mean, invstd, gamma, beta, relu, partial, sums, st):
+        dz, xhat = self._dz32(dout, lddo, y, ldy, pixels, c, mean, invstd, gamma, beta, relu)
+        _flat(sums, 2 * c, torch.float64).copy_(
+            torch.stack([dz.double().sum(0), (dz.double() * xhat.double()).sum(0)], 1).reshape(-1))
+
+    def _vtb_f32_bn_bwd_apply(self, dout, lddo, y, ldy, pixels, c, mean, invstd, gamma, beta, relu, coef, dy, lddy, st):
+        dz, xhat = self._dz32(dout, lddo, y, ldy, pixels, c, mean, invstd, gamma, beta, relu)
+        k = _flat(coef, 2 * c, torch.float32).view(c, 2)
+        out = _flat(gamma, c, torch.float32) * _flat(invstd, c, torch.float32) * (dz - k[:, 0] - xhat * k[:, 1])
+        _view(dy, lddy, pixels, c, torch.float32).copy_(out)
+
+    def _vtb_f32_grad_add(self, dst, ldd, src, lds, pixels, c, accumulate, st):
+        d, s = _view(dst, ldd, pixels, c, torch.float32), _view(src, lds, pixels, c, torch.float32)
+        d.copy_(d + s if accumulate else s)
+
+    def _vtb_f32_maxpool3s2_fwd(self, x, ldx, n, h, w, c, out, ldo, idx, st):
+        xi = _view(x, ldx, n * h * w, c, torch.float32).view(n, h, w, c).permute(0, 3, 1, 2)
+        y, ind = F.max_pool2d(xi, 3, 2, 1, return_indices=True)
+        ho, wo = y.shape[2:]
+        _view(out, ldo, n * ho * wo, c, torch.float32).copy_(y.permute(0, 2, 3, 1).reshape(-1, c))
+        if idx:
+            oh, ow = torch.arange(ho).view(1, 1, ho, 1), torch.arange(wo).view(1, 1, 1, wo)
+            code = (ind // w - (oh * 2 - 1)) * 3 + (ind % w - (ow * 2 - 1))
+            _flat(idx, n * ho * wo * c, torch.uint8).copy_(code.permute(0, 2, 3, 1).reshape(-1).to(torch.uint8))
+
+    def _vtb_f32_maxpool3s2_bwd(self, x, ldx, n, h, w, c, dout, lddo, dx, lddx, accumulate, idx, st):
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        code = _flat(idx, n * ho * wo * c, torch.uint8).view(n, ho, wo, c).long()
+        g = _view(dout, lddo, n * ho * wo, c, torch.float32).view(n, ho, wo, c)
+        oh, ow = torch.arange(ho).view(1, ho, 1, 1), torch.arange(wo).view(1, 1, wo, 1)
+        pos = (oh * 2 - 1 + code // 3) * w + (ow * 2 - 1 + code % 3)
+        acc = torch.zeros(n, h * w, c)
+        acc.scatter_add_(1, pos.view(n, ho * wo, c), g.reshape(n, ho * wo, c))
+        dst = _view(dx, lddx, n * h * w, c, torch.float32)
+        dst.copy_(dst + acc.view(-1, c) if accumulate else acc.view(-1, c))
+
+    def _vtb_f32_ese_fwd(self, x, ldx, n, hw, c, weight, bias, res, ldr, out, ldo, pool, z, gate, st):
+        xv = _view(x, ldx, n * hw, c, torch.float32).view(n, hw, c)
+        p = xv.sum(1) / hw
+        zz = p @ _flat(weight, c * c, torch.float32).view(c, c).t() + _flat(bias, c, torch.float32)
+        gt = (zz / 6 + 0.5).clamp(0, 1)
+        for ptr, val in ((pool, p), (z, zz), (gate, gt)):
+            _flat(ptr, n * c, torch.float32).copy_(val.reshape(-1))
+        o = xv * gt[:, None, :]
+        if res:
+            o = o + _view(res, ldr, n * hw, c, torch.float32).view(n, hw, c)
+        _view(out, ldo, n * hw, c, torch.float32).copy_(o.reshape(n * hw, c))
+
+    def _vtb_f32_ese_bwd(self, x, ldx, n, hw, c, weight, pool, z, gate, dout, lddo, dx, lddx, acc_dx, dweight, dbias,
+                         acc_dw, scratch, st):
+        xv = _view(x, ldx, n * hw, c, torch.float32).view(n, hw, c)
+        g = _view(dout, lddo, n * hw, c, torch.float32).view(n, hw, c)
+        W = _flat(weight, c * c, torch.float32).view(c, c)
+        p, zz, gt = (_flat(t, n * c, torch.float32).view(n, c) for t in (pool, z, gate))
+        dgate = (g * xv).sum(1)
+        dz = torch.where((zz > -3) & (zz < 3), dgate / 6, torch.zeros_like(dgate))
+        dpool = (dz @ W) / hw
+        for ptr, val in ((dweight, dz.t() @ p), (dbias, dz.sum(0))):
+            d = _flat(ptr, val.numel(), torch.float32)
+            d.copy_(d + val.reshape(-1) if acc_dw else val.reshape(-1))
+        new = (g * gt[:, None, :] + dpool[:, None, :]).reshape(n * hw, c)
+        dst = _view(dx, lddx, n * hw, c, torch.float32)
+        dst.copy_(dst + new if acc_dx else new)

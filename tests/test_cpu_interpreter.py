@@ -14,11 +14,25 @@ from vision_toolbox_b200 import engine
 from vision_toolbox_b200.backbones.base import BaseBackbone
 
 
-def _run(name, g, training, need_grad, x_grad, pair=True, col=True):
+class TwinRankDist:
+    """A second rank that holds the SAME batch: all-reducing a statistic doubles it.  Global mean / biased variance / the
+    dx formula are then those of the single batch, so the multi-rank code path must reproduce the single-process numbers
+    (only the unbiased running-variance factor differs: 2M / (2M - 1))."""
+
+    def __init__(self):
+        self.world, self.rank, self.sync_bn, self.sync, self.on_grads_ready = 2, 0, True, None, None
+        self.calls = 0
+
+    def all_reduce_(self, t):
+        t.mul_(2)
+        self.calls += 1
+
+
+def _run(name, g, training, need_grad, x_grad, pair=True, col=True, f32=False, dist=None):
     m = BUILDERS[name]()
     m.load_state_dict(g["state_dict"])
     m.train(training)
-    graph = engine.Graph(training, need_grad, False, pair_ok=pair, col_stem=col and not x_grad)
+    graph = engine.Graph(training, need_grad, f32, pair_ok=pair, col_stem=col and not x_grad)
     t_in = graph.input_image(*g["x"].shape)
     outs = m._emit(graph, t_in) if not isinstance(m, BaseBackbone) else m._emit(graph, t_in)
     for t in ([outs] if isinstance(outs, engine.TView) else outs):
@@ -28,12 +42,14 @@ def _run(name, g, training, need_grad, x_grad, pair=True, col=True):
     with mock.patch.object(engine._lib, "lib", return_value=lib):
         runner = engine.Runner(graph, torch.device("cpu"))
     runner._stream = lambda: 0
+    runner.dist = dist
     x = g["x"].clone().requires_grad_(x_grad)
     outs_t, run = runner.forward(x)
     outs_f = [o.float().clone() for o in outs_t]
     if not need_grad:
         return m, graph, outs_f, None, None
-    gouts = [c.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for c in g["cotangents"]]
+    gouts = [c.to(torch.float32 if f32 else torch.bfloat16).contiguous(memory_format=torch.channels_last)
+             for c in g["cotangents"]]
     gx, pgrads = runner.backward(run, gouts)
     grads = {}
     names = {id(p): k for k, p in m.named_parameters()}
@@ -99,3 +115,53 @@ def test_pairing_and_gathered_stem_do_not_change_the_result():
         assert rel_err(a, b) < 1e-2
     for k in gr0:
         assert rel_err(gr1[k], gr0[k]) < 2e-2, k
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fp32_mode_plans(name):
+    """The fp32 parity-mode plan (separate statistics / finalise / normalise launches, fp32 arenas) through the interpreter:
+    1e-5 on feature maps and running statistics, 1e-4 on gradients, against the reference's fp32 run."""
+    g = load_golden(name)
+    m, graph, outs, grads, gx = _run(name, g, True, True, True, f32=True)
+    assert not any(op.pair is not None or op.col is not None for op in graph.ops if op.kind == "conv")
+    for o, ref in zip(outs, g["train_fp32_outs"]):
+        assert rel_err(o, ref) < 1e-5, (name, rel_err(o, ref))
+    sd = m.state_dict()
+    for k, ref in g["buffers_after_step"].items():
+        if "num_batches" in k:
+            assert int(sd[k]) == int(ref)
+        else:
+            assert rel_err(sd[k], ref) < 1e-5, k
+    ref = dict(g["train_fp32_dparams"])
+    grads["__dx__"], ref["__dx__"] = gx, g["train_fp32_dx"]
+    for k in ref:
+        assert rel_err(grads[k], ref[k]) < 1e-4, (name, k, rel_err(grads[k], ref[k]))
+    with torch.no_grad():
+        m2, graph2, outs2, _, _ = _run(name, g, False, False, False, f32=True)
+    assert not graph2.fused_eval
+    for o, r in zip(outs2, g["eval_fp32_outs"]):
+        assert rel_err(o, r) < 1e-5
+
+
+@pytest.mark.parametrize("f32", [False, True], ids=["bf16", "fp32"])
+@pytest.mark.parametrize("name", ["stage_csp_2_16_32", "model_cspdarknet", "model_vovnet_ese"])
+def test_all_reduce_syncbn_path_with_a_twin_rank(name, f32):
+    """SyncBN through one all-reduce per exchange (the NCCL fallback of bf16 plans, the only multi-rank path of fp32
+    plans), fed by a twin rank: same feature maps and gradients as the single process."""
+    g = load_golden(name)
+    dist = TwinRankDist()
+    m, graph, outs, grads, _ = _run(name, g, True, True, False, pair=False, f32=f32, dist=dist)
+    units = sum(op.kind == "conv" for op in graph.ops)
+    assert dist.calls == 2 * units
+    for o, ref in zip(outs, g["train_fp32_outs" if f32 else "train_bf16_outs"]):
+        assert rel_err(o, ref) < (1e-5 if f32 else 2e-2)
+    ref32, ref16 = g["train_fp32_dparams"], g["train_bf16_dparams"]
+    for k in ref32:
+        if f32:
+            assert rel_err(grads[k], ref32[k]) < 1e-4, k
+        else:
+            assert rel_err(grads[k], ref32[k]) < 2.0 * rel_err(ref16[k], ref32[k]) + 1e-2, k
+    sd = m.state_dict()
+    for k, ref in g["buffers_after_step" if f32 else "buffers_after_bf16_step"].items():
+        if "running_mean" in k:
+            assert rel_err(sd[k], ref) < (1e-5 if f32 else 2e-3), k
