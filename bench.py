@@ -35,7 +35,20 @@ MODELS = {
     "darknet53": ("darknet", 27.16, 176, 256),
     "darknet19": ("darknet", 16.36, 224, 256),
     "vovnet99_ese": ("vovnet", 103.09, 224, 128),
+    "darknet_yolov5l": ("yolov5", 67.27 * 3, 640, 32),   # forward 67.27 GFLOP/img (BASELINE config C5 is inference)
 }
+# BASELINE.json `configs`, in order: --config C1..C5 reproduces each as a driver-style line.
+CONFIGS = {
+    "C1": dict(model="darknet19", batch=8, res=224, precision="fp32"),     # the reference's own CPU-runnable case
+    "C2": dict(model="darknet53", batch=256, res=176),
+    "C3": dict(model="cspdarknet53", batch=128, res=176),                  # global 1024 at 8 GPUs, as written
+    "C4": dict(model="vovnet99_ese", batch=128, res=224),
+    "C5": dict(model="darknet_yolov5l", batch=32, res=640, eval=True),
+}
+
+
+# element-wise BatchNorm entry points reported in roofline.split: full-tensor passes (reads + writes) per call
+EW_PASSES = {"vtb_bn_act": 2, "vtb_bn_bwd_fused": 5, "vtb_bn_bwd_apply": 3, "vtb_bn_bwd_reduce": 2}
 
 
 def build_model(name: str):
@@ -151,6 +164,8 @@ def reference_arm(args, rank: int, world: int) -> None:
         return
     from oracle import vt_oracle as O
 
+    # all host cores, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    torch.set_num_threads(os.cpu_count() or 1)
     fam, gflop, res, _ = MODELS[args.model]
     res = args.res or res
     nb = args.cpu_batch
@@ -166,6 +181,9 @@ def reference_arm(args, rank: int, world: int) -> None:
     y = torch.randint(0, 1000, (nb,))
 
     def step():
+        if args.eval:
+            with torch.no_grad():
+                return float(O.features(fam, sd, x, False, "fp32")[-1].mean())
         new_stats = {}
         loss = O.classifier_loss(fam, sd, head_w, head_b, x, y, "fp32", 0.1, new_stats)
         grads = torch.autograd.grad(loss, plist)
@@ -186,10 +204,12 @@ def reference_arm(args, rank: int, world: int) -> None:
     val = nb / dt
     cores = torch.get_num_threads()
     line = {
-        "impl": "reference", "metric": "train images/sec", "value": val, "unit": "img/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "inference images/sec" if args.eval else "train images/sec", "value": val, "unit": "img/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} train step {res}px, CPU sample batch {nb}", "model": args.model},
+        "config": {"workload": f"{args.model} {'get_feature_maps (eval)' if args.eval else 'train step'} {res}px, CPU sample "
+                               f"batch {nb}", "model": args.model, "preset": args.config or None,
+                   "threads": f"torch.set_num_threads(os.cpu_count()) = {cores}"},
         "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps of batch {nb} @ {res}px through oracle/vt_oracle.py (torch CPU fp32)"},
         "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -200,6 +220,7 @@ def reference_arm(args, rank: int, world: int) -> None:
 def cpu_baseline(model_name: str, res: int, seconds: float = 15.0) -> dict:
     from oracle import vt_oracle as O
 
+    torch.set_num_threads(os.cpu_count() or 1)
     fam = MODELS[model_name][0]
     torch.manual_seed(0)
     model = build_model(model_name)
@@ -225,6 +246,105 @@ def cpu_baseline(model_name: str, res: int, seconds: float = 15.0) -> dict:
             "sample": f"{n} fwd+bwd steps of batch {nb} @ {res}px, oracle/vt_oracle.py on torch CPU fp32"}
 
 
+def eval_arm(args, rank: int, world: int, local_rank: int) -> None:
+    """Inference arm (BASELINE config C5): model.get_feature_maps(x) under no_grad, eval mode (BatchNorm folded into the
+    conv epilogue: one launch per ConvNormAct).  N > 1: independent replicas, one per GPU (no exchange step exists)."""
+    import torch.distributed as dist
+
+    from vision_toolbox_b200 import _lib
+
+    fam, gflop_img, dres, dbatch = MODELS[args.model]
+    res, nb = args.res or dres, args.batch or dbatch
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W, K = max(args.warmup, 3), args.steps
+    torch.manual_seed(0)
+    model = build_model(args.model).to(dev).eval()
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host_x = [torch.rand(nb, 3, res, res, generator=g).pin_memory() for _ in range(2)]
+    dev_x = [h.to(dev) for h in host_x]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(x):
+        with torch.no_grad():
+            return model.get_feature_maps(x)
+
+    for i in range(W):
+        step(dev_x[i % 2])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        outs = step(dev_x[i % 2])
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    value = nb * world * K / (float(ms) / 1e3)
+    # end to end: pinned host -> device copy of every batch, a scalar of the last map read back
+    buf = torch.empty_like(dev_x[0])
+    barrier()
+    e0.record()
+    for i in range(K):
+        buf.copy_(host_x[i % 2], non_blocking=True)
+        last = float(step(buf)[-1].float().mean())
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    roofline = None
+    if rank == 0:
+        prof = ProfilingLib(_lib.lib())
+        runners = list(model.__dict__.get("_vtb_plans", {}).values())
+        for r in runners:
+            r.L = prof
+        torch.cuda._sleep(30_000_000)
+        step(dev_x[0])
+        torch.cuda.synchronize()
+        for r in runners:
+            r.L = _lib.lib()
+        pk = peaks()
+        t = fl = n = 0
+        for name, geom, a, b, _ in prof.records:
+            if name == "vtb_conv_fprop":
+                t += a.elapsed_time(b); fl += conv_flops(geom); n += 1
+        ach = fl / (t / 1e3) / 1e12 if t else 0.0
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (eval fprop, fused BN+ReLU epilogue)", "achieved": ach,
+                    "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                    "peak_source": pk["source"] + ", sustained cuBLAS bf16", "launches": n, "avg_launch_ms": t / max(n, 1)}
+        line = {"metric": "inference images/sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": float(ms) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{args.model} get_feature_maps (eval, no_grad), {res}px, batch {nb}/GPU, bf16",
+                           "model": args.model, "global_batch": nb * world, "resolution": res,
+                           "parallelism": f"replicas x{world}", "preset": args.config or None,
+                           "l2_policy": "activations >> L2"},
+                "clocks": clocks,
+                "e2e": {"value": nb * world * K / (float(ms2) / 1e3), "unit": "img/s",
+                        "h2d_bytes_per_step": host_x[0].numel() * 4, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
+                "model_tflops": value * gflop_img / 3 / 1e3, "last": last}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,13 +358,28 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph (single GPU)")
+    ap.add_argument("--config", default="", choices=[""] + list(CONFIGS), help="BASELINE.json config preset (C1..C5)")
+    ap.add_argument("--eval", action="store_true", help="inference: get_feature_maps under no_grad (config C5)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
+    if args.config:
+        preset = CONFIGS[args.config]
+        args.model = preset["model"]
+        args.batch = args.batch or preset["batch"]
+        args.res = args.res or preset["res"]
+        args.eval = args.eval or preset.get("eval", False)
+        args.precision = preset.get("precision", args.precision)
+        if args.impl == "reference":
+            args.cpu_batch = min(args.cpu_batch, args.batch)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.eval:
+        eval_arm(args, rank, world, local_rank)
         return
 
     import torch.distributed as dist
@@ -262,6 +397,10 @@ def main() -> None:
     K = args.steps
 
     torch.manual_seed(0)
+    if args.precision == "fp32":
+        import vision_toolbox_b200
+
+        vision_toolbox_b200.set_precision("fp32")   # config C1: the fp32 parity kernels (CUDA cores), not the fast path
     model = build_model(args.model).to(dev).train()
     head = torch.nn.Linear(model.out_channels_list[-1], 1000).to(dev)
     trainer = parallel.Trainer(model, head, lr=0.05, momentum=0.9, weight_decay=2e-5, label_smoothing=0.1,
@@ -387,8 +526,20 @@ def main() -> None:
         # against the measured peaks): the 3x3 layers with >= 128 channels are tensor-bound, stems / 1x1 / narrow
         # layers are HBM-bound; "roofline" below is the kernel as a whole, "roofline.split" the two classes apart
         split = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}   # ms, flops, bytes, launches
-        for name, geom, a, b, _ in prof.records:
+        ew = {}   # element-wise BatchNorm passes: entry point -> [ms, algorithmic bytes, launches]
+        for name, geom, a, b, cargs in prof.records:
             t = a.elapsed_time(b)
+            if name in EW_PASSES:
+                # (pixels, channels) sit at the same argument positions in all of them; passes = algorithmic full-tensor
+                # reads + writes of the call
+                pix, ch = cargs[4], cargs[5]
+                if name == "vtb_bn_act":
+                    pix, ch = cargs[2], cargs[3]
+                    passes = 3 if cargs[7] else 2
+                else:
+                    passes = EW_PASSES[name]
+                e = ew.setdefault(name, [0.0, 0.0, 0])
+                e[0] += t; e[1] += float(pix) * ch * 2.0 * passes; e[2] += 1
             is_conv = geom is not None and name in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_wgrad", "vtb_conv_wgrad_pair")
             fl = conv_flops(geom) if is_conv else 0.0
             d = agg.setdefault(name, [0.0, 0.0, 0])
@@ -417,6 +568,9 @@ def main() -> None:
                              "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tb[1] / max(tb[0], 1e-9) / 1e9 / pk["tflops"]},
             "hbm_bound": {"launches": hb[3], "ms": round(hb[0], 3), "achieved": hb[2] / max(hb[0], 1e-9) / 1e6,
                           "peak": pk["gbs"], "unit": "GB/s", "frac": hb[2] / max(hb[0], 1e-9) / 1e6 / pk["gbs"]}}
+        for nm, (ms_, by_, n_) in ew.items():
+            roofline["split"][nm] = {"launches": n_, "ms": round(ms_, 3), "achieved": by_ / max(ms_, 1e-9) / 1e6,
+                                     "peak": pk["gbs"], "unit": "GB/s", "frac": by_ / max(ms_, 1e-9) / 1e6 / pk["gbs"]}
         tot = sum(v[0] for v in agg.values())
         breakdown = {k: {"ms": round(v[0], 3), "share": round(v[0] / tot, 3), "calls": v[2],
                          **({"tflops": round(v[1] / (v[0] / 1e3) / 1e12, 1)} if v[1] else {})}
@@ -431,8 +585,8 @@ def main() -> None:
         line = {
             "metric": "train images/sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.model} train step (fwd+loss+bwd+SGD), {res}px, batch {nb}/GPU, bf16, "
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model} train step (fwd+loss+bwd+SGD), {res}px, batch {nb}/GPU, {args.precision}, "
                                    f"{'SyncBN+DDP' if world > 1 else 'single GPU'}",
                        "model": args.model, "global_batch": nb * world, "resolution": res,
                        "parallelism": f"dp{world}", "l2_policy": "inputs+activations >> L2 (multi-GB working set per step)",

@@ -52,6 +52,11 @@ int vtb_conv_out_hw(const VtbConv* c, int* ho, int* wo);
 /* rows of the per-CTA statistics scratch written by vtb_conv_fprop (one per thread block): floats = rows * cout * 2 */
 int vtb_conv_stats_rows(const VtbConv* c);
 size_t vtb_conv_wgrad_workspace_bytes(const VtbConv* c);
+/* The tiling the library will use for this geometry (introspection for tests / benchmarks: "did this case really run
+ * multi-tile CTAs, two TMEM sets, K-split chains, split-K wgrad?").  op: 0 fprop, 1 dgrad (stride 2: the largest phase),
+ * 2 wgrad.  info[8] = fprop/dgrad: {block_m, block_n, grid, tiles, max tiles per CTA, TMEM sets, ksplit, stages};
+ * wgrad: {pixels per stage, columns per tile, CTAs per split, splits, pixel blocks, ksplit, stages, 0}. */
+int vtb_conv_tiling_info(const VtbConv* c, int op, int* info);
 
 /* ---- weights ----
  * Re-pack an OIHW fp32 master weight (nn.Conv2d.weight, components.py:26) into the two bf16 matrices the

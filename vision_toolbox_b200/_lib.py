@@ -62,6 +62,7 @@ SIGNATURES = {
     "vtb_conv_out_hw": (_i, [_cp, C.POINTER(_i), C.POINTER(_i)]),
     "vtb_conv_stats_rows": (_i, [_cp]),
     "vtb_conv_wgrad_workspace_bytes": (C.c_size_t, [_cp]),
+    "vtb_conv_tiling_info": (_i, [_cp, _i, C.POINTER(_i)]),
     "vtb_pack_weight": (_i, [_cp, _p, _i, _p, _p, _p]),
     "vtb_pack_job_blocks": (_ll, [_i, _i, _i]),
     "vtb_pack_weights": (_i, [_p, _i, _ll, _p]),

@@ -375,6 +375,40 @@ size_t vtb_conv_wgrad_workspace_bytes(const VtbConv* c) {
   return (size_t)w.splits * c->cout * c->k * c->k * c->cin * sizeof(float);
 }
 
+int vtb_conv_tiling_info(const VtbConv* c, int op, int* info) {
+  if (!conv_ok(c) || !info || op < 0 || op > 2) return fail(VTB_EINVAL, "vtb_conv_tiling_info: bad arguments");
+  int ho, wo;
+  out_hw(c, &ho, &wo);
+  if (op == 2) {
+    const WgradPlan w = plan_wgrad(c);
+    const int v[8] = {w.kpix, w.n_cols, w.n_tiles * w.m_tiles, w.splits, w.kblocks, w.ksplit, w.stages, 0};
+    for (int i = 0; i < 8; ++i) info[i] = v[i];
+    return VTB_OK;
+  }
+  long long M = (long long)c->n * ho * wo;
+  int ncols = c->cout, k16 = c->k * c->k * c->cin / 16;
+  if (op == 1) {
+    ncols = c->cin;
+    if (c->stride == 1) {
+      M = (long long)c->n * c->h * c->w;
+      k16 = c->k * c->k * c->cout / 16;
+    } else {   // phase (1,1): the most taps
+      M = (long long)c->n * (c->h / 2) * (c->w / 2);
+      int nr = 0;
+      for (int r = 0; r < c->k; ++r) nr += (((1 + c->pad - r) % 2 + 2) % 2 == 0);
+      k16 = nr * nr * c->cout / 16;
+      if (M <= 0) M = 1;
+    }
+  }
+  const ConvTiling t = plan_conv_tiling(M, ncols, k16);
+  const int halves = t.block_m / kBlockM, acc_stride = (t.block_n + 31) & ~31;
+  const long long tiles = ((M + t.block_m - 1) / t.block_m) * t.n_blocks;
+  const int v[8] = {t.block_m, t.block_n, t.grid, (int)tiles, (int)((tiles + t.grid - 1) / t.grid),
+                    (2 * halves * t.ksplit * acc_stride <= 512) ? 2 : 1, t.ksplit, t.stages};
+  for (int i = 0; i < 8; ++i) info[i] = v[i];
+  return VTB_OK;
+}
+
 int vtb_pack_weight(const VtbConv* c, const float* w_oihw, int cin_real, void* wf, void* wd, void* stream) {
   if (!conv_ok(c) || !w_oihw || !wf || cin_real <= 0 || cin_real > c->cin)
     return fail(VTB_EINVAL, "vtb_pack_weight: bad arguments");
