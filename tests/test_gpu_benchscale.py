@@ -222,4 +222,4 @@ def test_benchmark_regime_is_what_ran():
     assert fp["c3x3s2_512_1024_11"][2] // max(1, 1024 // fp["c3x3s2_512_1024_11"][1]) >= 1
     assert fp["c3x3s2_512_1024_11"][1] < 1024                                      # several n-blocks
     wg = {n: v[2] for n, v in info.items()}
-    assert any(v[3] > 1 for v in wg.values()) and any(v[3] == 1 and v[4] > 100 for v in wg.values())   # split-K and long-K
+    assert any(v[3] > 1 for v in wg.values()) and any(v[3] == 1 and v[4] >= 64 for v in wg.values())   # split-K and one long-K split

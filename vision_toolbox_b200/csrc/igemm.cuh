@@ -27,10 +27,10 @@ constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 232448;
 constexpr int kMaxPanels = 8;      // staged output panels per accumulator (block_n / panel_w)
 
-enum StoreMode : int {
-  kStoreTma = 0,        // bf16 tile via TMA store
-  kStoreTmaAdd = 1,     // bf16 tile via TMA reduce-add (gradient fan-in)
-  kStoreScatter = 2,    // bf16 rows written by threads to a strided pixel lattice (stride-2 dgrad phases)
+enum StoreMode : int {   // every mode stages the bf16 tile in shared memory and writes 16-byte row segments
+  kStoreTma = 0,        // dense rows
+  kStoreTmaAdd = 1,     // dense rows, read-modify-write (gradient fan-in)
+  kStoreScatter = 2,    // rows go to a strided pixel lattice (stride-2 dgrad phases)
   kStoreScatterAdd = 3,
 };
 
@@ -92,6 +92,26 @@ struct ConvIgemmParams {
   // SyncBN: peer-mapped exchange buffers (world <= 1: single-GPU statistics); bn_count is then the GLOBAL count and
   // tickets[64] counts the finished n-block exchanges of the launch
   SyncPeers sync;
+  // BatchNorm(+ReLU) BACKWARD statistics (dgrad launches, bwd_y[0] != nullptr): this launch completes the gradient `g` of
+  // a tensor that was produced by one ConvNormAct (or two, side by side on the channel axis: channels >= bwd_split belong
+  // to the second, indexed from 0).  The epilogue reads the producer's raw conv output y at the pixels it stores and
+  // accumulates, per channel, sum(dz) and sum(dz * (y - mean)) with dz = g * (y*scale + shift > 0) into stats_partial
+  // rows [stats_row0, stats_row0 + m_step); with `tickets` the last CTA of each n-block reduces rows [0, fin_rows)
+  // (a stride-2 dgrad is four launches: only the last one finalises), exchanges them under SyncBN and writes
+  // coef[c][2] = (mean dz, mean dz*xhat), dgamma = sum dz*xhat, dbeta = sum dz (local sums): the standalone BatchNorm
+  // backward of that layer then is a single apply pass (vtb_bn_bwd_apply).
+  int bwd_split;
+  const __nv_bfloat16* bwd_y[2];
+  int bwd_ldy[2];
+  const float* bwd_scale[2];
+  const float* bwd_shift[2];
+  const float* bwd_mean[2];
+  const float* bwd_invstd[2];
+  int bwd_relu[2];
+  float* bwd_dgamma[2];
+  float* bwd_dbeta[2];
+  float* bwd_coef[2];
+  int stats_row0, fin_rows;
   // optional fused per-channel affine + ReLU (+ residual) epilogue (eval-mode folded BN)
   const float* scale;
   const float* shift;
