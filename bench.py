@@ -124,7 +124,8 @@ class ProfilingLib:
     def __getattr__(self, name):
         fn = getattr(self._real, name)
         if not name.startswith("vtb_") or name in ("vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows",
-                                                   "vtb_conv_wgrad_workspace_bytes", "vtb_launch_count", "vtb_pack_job_blocks"):
+                                                   "vtb_conv_wgrad_workspace_bytes", "vtb_launch_count", "vtb_pack_job_blocks", "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w",
+                                                   "vtb_conv_tiling_info", "vtb_bn_bwd_fused_rows"):
             return fn
 
         def wrapped(*args):
@@ -540,7 +541,7 @@ def main() -> None:
                     passes = EW_PASSES[name]
                 e = ew.setdefault(name, [0.0, 0.0, 0])
                 e[0] += t; e[1] += float(pix) * ch * 2.0 * passes; e[2] += 1
-            is_conv = geom is not None and name in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_wgrad", "vtb_conv_wgrad_pair")
+            is_conv = geom is not None and name in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_dgrad_bn", "vtb_conv_wgrad", "vtb_conv_wgrad_pair")
             fl = conv_flops(geom) if is_conv else 0.0
             d = agg.setdefault(name, [0.0, 0.0, 0])
             d[0] += t; d[1] += fl; d[2] += 1
@@ -549,7 +550,7 @@ def main() -> None:
                 cls = "tensor" if fl / (pk["tflops"] * 1e12) >= by / (pk["gbs"] * 1e9) else "hbm"
                 c = split[cls]
                 c[0] += t; c[1] += fl; c[2] += by; c[3] += 1
-        conv_calls = [agg.get(k, [0, 0, 0]) for k in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad")]
+        conv_calls = [agg.get(k, [0, 0, 0]) for k in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_dgrad_bn")]
         igemm_ms = sum(v[0] for v in conv_calls)
         igemm_fl = sum(v[1] for v in conv_calls)
         igemm_n = sum(v[2] for v in conv_calls)

@@ -131,6 +131,40 @@ int vtb_conv_fprop_bn(const VtbConv* c, const void* x, int ldx, const void* wf, 
  * OSA branches: darknet.py:28,53 ; vovnet.py:55,61) with bf16 rounding of each addend like autograd. */
 int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
                    void* stream);
+/* dgrad that ALSO starts the BatchNorm(+ReLU) backward of the layer(s) that produced x (autograd chain
+ * ConvolutionBackward0 -> ReluBackward0 -> NativeBatchNormBackward0 of components.py:26-39): when this call is the
+ * LAST contribution to dx, dx is the complete gradient `g` of the producer's output.  The epilogue then reads the
+ * producer's raw conv output y at the pixels it stores and reduces, per channel, sum(dz) and sum(dz * xhat) with
+ * dz = g * (y*scale + shift > 0), xhat = (y - mean) * invstd; the last thread block finalises (and exchanges the sums
+ * under SyncBN): dgamma, dbeta (overwritten, local sums) and coef[c][2] = (mean dz, mean dz*xhat) over `count`.
+ * BatchNorm's backward for that layer is then ONE apply pass (vtb_bn_bwd_apply with this coef) - no reduction pass,
+ * no grid barrier.  x may be the concatenation of two producers' outputs (CSPDarknetStage, darknet.py:53):
+ * channels [0, split) belong to layer[0], [split, cin) to layer[1] (split = 0: one producer); split must be a multiple of
+ * vtb_conv_dgrad_panel_w(c).  partial: vtb_conv_dgrad_stats_rows(c) * cin * 2 floats of scratch. */
+typedef struct VtbBnBwdLayer {
+  const void* y;          /* raw conv output of the producer, bf16 NHWC view on x's pixel lattice */
+  int ldy;
+  const float* scale;     /* gamma * invstd  (vtb_bn_finalize / vtb_conv_fprop_bn) */
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  int relu;               /* the producer's activation: 1 = ReLU (mask recomputed from y), 0 = none */
+  float* dgamma;          /* out [c], may be NULL */
+  float* dbeta;           /* out [c], may be NULL */
+  float* coef;            /* out [c][2] */
+} VtbBnBwdLayer;
+typedef struct VtbDgradBn {
+  int split;
+  VtbBnBwdLayer layer[2];
+  double count;           /* elements per channel of the producer's output (GLOBAL count under SyncBN) */
+  float* partial;
+  unsigned int* tickets;  /* as in VtbBnTrain */
+  const struct VtbSyncBn* sync;
+} VtbDgradBn;
+int vtb_conv_dgrad_stats_rows(const VtbConv* c);
+int vtb_conv_dgrad_panel_w(const VtbConv* c);
+int vtb_conv_dgrad_bn(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
+                      const VtbDgradBn* bn, void* stream);
 /* wgrad: dw_oihw (fp32, [cout][cin_real][k][k]) (+)= sum over pixels dy * im2col(x).
  * workspace: vtb_conv_wgrad_workspace_bytes(c) bytes of scratch. Deterministic (no atomics). */
 int vtb_conv_wgrad(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,

@@ -21,7 +21,8 @@ from vision_toolbox_b200 import _lib
 BF16 = torch.bfloat16
 HOST_ONLY = {"vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows", "vtb_bn_bwd_fused_rows", "vtb_conv_out_hw",
              "vtb_conv_wgrad_workspace_bytes", "vtb_f32_conv_wgrad_workspace_bytes", "vtb_f32_bn_rows",
-             "vtb_pack_job_blocks", "vtb_launch_count", "vtb_version", "vtb_num_sms", "vtb_bn_sync_buffer_bytes"}
+             "vtb_pack_job_blocks", "vtb_launch_count", "vtb_version", "vtb_num_sms", "vtb_bn_sync_buffer_bytes",
+             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info"}
 
 
 def _flat(ptr: int, n: int, dt: torch.dtype) -> torch.Tensor:
@@ -161,6 +162,24 @@ class InterpreterLib:
         gx = gx.permute(0, 2, 3, 1).reshape(g.n * g.h * g.w, g.cin)
         dst = _view(dx, lddx, gx.shape[0], g.cin)
         dst.copy_(((_r(gx) + dst.float()) if accumulate else gx).to(BF16))
+
+    def _vtb_conv_dgrad_bn(self, geom, dy, lddy, wd, dx, lddx, accumulate, bn, st):
+        """dgrad, then the BatchNorm(+ReLU) backward sums of the producer layer(s) against the COMPLETED dx (vtb.h)."""
+        g, b = _obj(geom), _obj(bn)
+        assert b.sync is None, "the interpreter models a single rank"
+        self._vtb_conv_dgrad(geom, dy, lddy, wd, dx, lddx, accumulate, st)
+        pixels = g.n * g.h * g.w
+        bounds = [(0, g.cin)] if b.split == 0 else [(0, b.split), (b.split, g.cin)]
+        for lay, (c0, c1) in zip(b.layer, bounds):
+            c = c1 - c0
+            dz, xhat = self._dz_xhat(dx + 2 * c0, lddx, lay.y, lay.ldy, pixels, c, lay.scale, lay.shift, lay.mean,
+                                     lay.invstd, lay.relu)
+            s0, s1 = dz.double().sum(0), (dz.double() * xhat.double()).sum(0)
+            if lay.dgamma:
+                _flat(lay.dgamma, c, torch.float32).copy_(s1.float())
+            if lay.dbeta:
+                _flat(lay.dbeta, c, torch.float32).copy_(s0.float())
+            _flat(lay.coef, 2 * c, torch.float32).view(c, 2).copy_(torch.stack([s0 / b.count, s1 / b.count], 1).float())
 
     def _dw(self, g, dy, lddy, x, ldx):
         ho, wo = self._hw(g)

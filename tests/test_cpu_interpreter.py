@@ -85,11 +85,15 @@ def test_eval_forward(name):
         assert torch.equal(m.state_dict()[k], v), k
 
 
+@pytest.mark.parametrize("dgrad_bn", ["0", "1"], ids=["bn-bwd-kernel", "bn-bwd-sums-in-dgrad"])
 @pytest.mark.parametrize("x_grad", [False, True], ids=["stem-gathered", "image-gradient"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_train_backward(name, x_grad):
+def test_train_backward(name, x_grad, dgrad_bn, monkeypatch):
+    monkeypatch.setenv("VTB_DGRAD_BN", dgrad_bn)   # opt-in plan: vtb_conv_dgrad_bn + vtb_bn_bwd_apply
     g = load_golden(name)
     m, graph, outs, grads, gx = _run(name, g, True, True, x_grad)
+    fused = sum(op.dgrad_bn is not None for op in graph.ops if op.kind == "conv")
+    assert (fused > 0) == (dgrad_bn == "1" and sum(op.kind == "conv" for op in graph.ops) > 1), fused
     ref16, ref32 = dict(g["train_bf16_dparams"]), dict(g["train_fp32_dparams"])
     if x_grad:
         grads["__dx__"], ref16["__dx__"], ref32["__dx__"] = gx, g["train_bf16_dx"], g["train_fp32_dx"]

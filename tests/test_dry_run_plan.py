@@ -21,7 +21,8 @@ from vision_toolbox_b200.backbones.darknet import CSPDarknetStage
 
 HOST_ONLY = {"vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows", "vtb_bn_bwd_fused_rows", "vtb_conv_out_hw",
              "vtb_conv_wgrad_workspace_bytes", "vtb_f32_conv_wgrad_workspace_bytes", "vtb_f32_bn_rows",
-             "vtb_pack_job_blocks", "vtb_launch_count", "vtb_version", "vtb_num_sms", "vtb_bn_sync_buffer_bytes"}
+             "vtb_pack_job_blocks", "vtb_launch_count", "vtb_version", "vtb_num_sms", "vtb_bn_sync_buffer_bytes",
+             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info"}
 
 
 class RecordingLib:
@@ -84,6 +85,14 @@ def _views(name, a, es):
         g, pin, pout = _geom(a[0])
         dx, ld, acc = (a[5], a[6], a[7]) if f32 else (a[4], a[5], a[6])
         return [(a[1], a[2], pout, g.cout, "r"), (dx, ld, pin, g.cin, "rw" if acc else "w")]
+    if base == "vtb_conv_dgrad_bn":
+        g, pin, pout = _geom(a[0])
+        bn = a[7]._obj if hasattr(a[7], "_obj") else a[7]
+        v = [(a[1], a[2], pout, g.cout, "r"), (a[4], a[5], pin, g.cin, "rw" if a[6] else "w")]
+        bounds = [(0, g.cin)] if bn.split == 0 else [(0, bn.split), (bn.split, g.cin)]
+        for lay, (c0, c1) in zip(bn.layer, bounds):     # the producers' raw conv outputs, on dx's pixel lattice
+            v.append((lay.y, lay.ldy, pin, c1 - c0, "r"))
+        return v
     if base in ("vtb_conv_wgrad", "vtb_conv_wgrad_pair"):
         g, pin, pout = _geom(a[0])
         return [(a[1], a[2], pout, g.cout, "r"), (a[3], a[4], pin, g.cin, "r")]
@@ -254,9 +263,17 @@ def test_eval_and_frozen_statistics_plans(f32):
     _dry_run(vov, (2, 3, 32, 32), f32, training=False, need_grad=True)
 
 
-def test_launch_counts_cspdarknet53():
+def test_launch_counts_cspdarknet53(monkeypatch):
     """67 units: 5 sibling pairs run as one convolution each -> 62 fprop, 61 + 4 x 5 dgrad launches happen inside the
     library (stride-2 phases are one C call), the stem needs no dgrad."""
+    g, calls, n_fwd = _dry_run(backbones.cspdarknet53(), (2, 3, 64, 64), False)
+    bwd = Counter(n for n, _ in calls[n_fwd:])
+    units = sum(op.kind == "conv" for op in g.ops)
+    pairs = sum(op.kind == "conv" and op.pair is not None for op in g.ops)
+    # default plan: one fused reduce + apply BatchNorm-backward kernel per unit, plain dgrads
+    assert bwd["vtb_bn_bwd_fused"] == units and bwd["vtb_conv_dgrad"] == units - pairs - 1 and bwd["vtb_conv_dgrad_bn"] == 0
+    # opt-in plan (VTB_DGRAD_BN=1): the BatchNorm-backward sums ride in the dgrad epilogues
+    monkeypatch.setenv("VTB_DGRAD_BN", "1")
     g, calls, n_fwd = _dry_run(backbones.cspdarknet53(), (2, 3, 64, 64), False)
     fwd = Counter(n for n, _ in calls[:n_fwd])
     bwd = Counter(n for n, _ in calls[n_fwd:])
@@ -265,11 +282,16 @@ def test_launch_counts_cspdarknet53():
     assert (units, pairs) == (67, 5)
     assert fwd == Counter({"vtb_pack_weights": 1, "vtb_im2col_input": 1, "vtb_conv_fprop_bn": units - pairs,
                            "vtb_bn_act": units})
-    assert bwd["vtb_bn_bwd_fused"] == units
+    # BatchNorm backward: every dgrad is the last contribution to its input's gradient and carries the (dz, dz*xhat) sums
+    # of the unit(s) that produced it (the CSP concat buffer: two units per out_conv dgrad) -> one apply pass per unit;
+    # only the last unit, whose gradient arrives from outside the plan, keeps the reduce + apply kernel
+    assert bwd["vtb_bn_bwd_fused"] == 1 and bwd["vtb_bn_bwd_apply"] == units - 1
     assert bwd["vtb_conv_wgrad"] + bwd["vtb_conv_wgrad_pair"] == units - pairs and bwd["vtb_conv_wgrad_pair"] == pairs
-    assert bwd["vtb_conv_dgrad"] == units - pairs - 1          # every convolution but the stem
+    assert bwd["vtb_conv_dgrad_bn"] == units - pairs - 1 and bwd["vtb_conv_dgrad"] == 0   # every convolution but the stem
+    two = sum(1 for n, a in calls[n_fwd:] if n == "vtb_conv_dgrad_bn" and a[7]._obj.split > 0)
+    assert two == pairs                                       # the five out_conv dgrads serve conv1 | last block
     # stem weight gradient; one injection per feature map that received a gradient (the trainer only uses the last one)
     assert bwd["vtb_dw_from_col"] == 1 and bwd["vtb_grad_add"] == len(g.outputs) == 5
     # the residual of every DarknetBlock is aliased into its output's gradient memory: no extra fan-out copies
-    assert set(bwd) == {"vtb_bn_bwd_fused", "vtb_conv_wgrad", "vtb_conv_wgrad_pair", "vtb_conv_dgrad", "vtb_dw_from_col",
-                        "vtb_grad_add"}
+    assert set(bwd) == {"vtb_bn_bwd_fused", "vtb_bn_bwd_apply", "vtb_conv_wgrad", "vtb_conv_wgrad_pair",
+                        "vtb_conv_dgrad_bn", "vtb_dw_from_col", "vtb_grad_add"}

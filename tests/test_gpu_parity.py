@@ -91,6 +91,33 @@ def test_train_backward(name):
     print(f"{name}: worst (our err)/(reference bf16 err) vs fp32 truth = {worst:.2f}")
 
 
+@pytest.mark.parametrize("name", [n for n in GOLDEN_CASES if not n.startswith("unit_")])
+def test_train_backward_with_bn_sums_in_dgrad(name, monkeypatch):
+    """Opt-in plan (VTB_DGRAD_BN=1): the dgrad that completes a unit's output gradient also reduces its BatchNorm-backward
+    sums (vtb_conv_dgrad_bn, incl. the four-phase stride-2 and the two-producer CSP concat cases); the unit's own
+    backward is then one apply pass.  Same criterion as test_train_backward, plus agreement with the default plan."""
+    g = load_golden(name)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VTB_DGRAD_BN", flag)
+        m = _native(name, g)
+        x = g["x"].cuda().requires_grad_(True)
+        outs = module_outputs(m, x)
+        sum((o.float() * c.cuda()).sum() for o, c in zip(outs, g["cotangents"])).backward()
+        torch.cuda.synchronize()
+        res[flag] = {k: p.grad.float().cpu() for k, p in m.named_parameters()}
+        res[flag]["__dx__"] = x.grad.float().cpu()
+        plans = list(m.__dict__["_vtb_plans"].values())
+        fused = sum(op.dgrad_bn is not None for op in plans[0].g.ops if op.kind == "conv")
+        assert (fused > 0) == (flag == "1")
+    ref16 = dict(g["train_bf16_dparams"]); ref16["__dx__"] = g["train_bf16_dx"]
+    ref32 = dict(g["train_fp32_dparams"]); ref32["__dx__"] = g["train_fp32_dx"]
+    for k in ref32:
+        e_ours, e_ref = rel_err(res["1"][k], ref32[k]), rel_err(ref16[k], ref32[k])
+        assert e_ours < 2.0 * e_ref + 1e-2, (k, e_ours, e_ref)
+        assert rel_err(res["1"][k], res["0"][k]) < 2e-2 + e_ref, (k, rel_err(res["1"][k], res["0"][k]))
+
+
 def test_native_library_is_what_ran():
     from vision_toolbox_b200 import _lib
 

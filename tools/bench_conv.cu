@@ -56,13 +56,28 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const double flops = 2.0 * outpix * c.cout * kk * c.cin;
   const double bytes = 2.0 * (inpix * c.cin + outpix * c.cout) + 2.0 * kk * c.cin * c.cout;
-  const char* names[3] = {"fprop", "dgrad", "wgrad"};
+  const char* names[5] = {"fprop", "dgrad", "wgrad", "dgradbn", "dgr+acc"};
+  // fake producer layer for the dgrad that carries BatchNorm-backward statistics (vtb_conv_dgrad_bn)
+  __nv_bfloat16* yprod; float *bnp, *partial_d; unsigned int* tickets;
+  CK(cudaMalloc(&yprod, inpix * c.cin * 2)); fill(yprod, inpix * c.cin, 5);
+  CK(cudaMalloc(&bnp, (size_t)c.cin * 8 * 4));
+  { std::vector<float> hb((size_t)c.cin * 8, 0.5f); CK(cudaMemcpy(bnp, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice)); }
+  const int drows = vtb_conv_dgrad_stats_rows(&c);
+  CK(cudaMalloc(&partial_d, (size_t)(drows > 0 ? drows : 1) * c.cin * 8));
+  CK(cudaMalloc(&tickets, 4096)); CK(cudaMemset(tickets, 0, 4096));
+  VtbDgradBn dbn; memset(&dbn, 0, sizeof(dbn));
+  dbn.layer[0].y = yprod; dbn.layer[0].ldy = c.cin; dbn.layer[0].scale = bnp; dbn.layer[0].shift = bnp + c.cin;
+  dbn.layer[0].mean = bnp + 2 * c.cin; dbn.layer[0].invstd = bnp + 3 * c.cin; dbn.layer[0].relu = 1;
+  dbn.layer[0].dgamma = bnp + 4 * c.cin; dbn.layer[0].dbeta = bnp + 5 * c.cin; dbn.layer[0].coef = bnp + 6 * c.cin;
+  dbn.count = (double)inpix; dbn.partial = partial_d; dbn.tickets = tickets;
   const bool flush_l2 = getenv("VTB_FLUSH") != nullptr;
-  for (int which = 0; which < 3; ++which) {
+  for (int which = 0; which < 5; ++which) {
     auto run = [&]() {
       if (which == 0) CV(vtb_conv_fprop(&c, x, c.cin, wf, y, c.cout, stats, nullptr, nullptr, 0, nullptr, 0, 0));
       if (which == 1) CV(vtb_conv_dgrad(&c, dy, c.cout, wd, dx, c.cin, 0, 0));
       if (which == 2) CV(vtb_conv_wgrad(&c, dy, c.cout, x, c.cin, ws, dw, c.cin, 0, 0));
+      if (which == 3) CV(vtb_conv_dgrad_bn(&c, dy, c.cout, wd, dx, c.cin, 0, &dbn, 0));
+      if (which == 4) CV(vtb_conv_dgrad(&c, dy, c.cout, wd, dx, c.cin, 1, 0));
     };
     vtb_debug_counters(nullptr);
     {  // warm up until the clocks have ramped (idle GPUs sit far below boost for the first tens of ms)
@@ -92,6 +107,8 @@ int main(int argc, char** argv) {
         if (which == 0) CV(vtb_conv_fprop(&c, x, c.cin, wf, y, c.cout, stats, nullptr, nullptr, 0, nullptr, 0, st));
         if (which == 1) CV(vtb_conv_dgrad(&c, dy, c.cout, wd, dx, c.cin, 0, st));
         if (which == 2) CV(vtb_conv_wgrad(&c, dy, c.cout, x, c.cin, ws, dw, c.cin, 0, st));
+        if (which == 3) CV(vtb_conv_dgrad_bn(&c, dy, c.cout, wd, dx, c.cin, 0, &dbn, st));
+        if (which == 4) CV(vtb_conv_dgrad(&c, dy, c.cout, wd, dx, c.cin, 1, st));
       };
       cudaGraph_t graph; cudaGraphExec_t exec;
       CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
@@ -122,7 +139,7 @@ int main(int argc, char** argv) {
       if (n) printf("       ctas %d | cycles/CTA %.0f | setup %.0f | first-full %.0f | producer0 on empty %.0f | MMA on full %.0f | epi on tmem-full %.0f, drain %.0f\n",
                     n, s[2] / n, s[6] / n, s[5] / n, s[0] / n, s[1] / n, s[3] / n, s[4] / n);
     }
-    if (which < 2 && !(which == 1 && c.stride == 2)) {
+    if (which != 2 && !(which != 0 && c.stride == 2)) {
       CK(cudaMemset(dbg, 0, 1024 * 128));
       vtb_debug_counters(dbg);
       run();

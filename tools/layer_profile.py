@@ -47,7 +47,7 @@ for fn, geom, a, b, args in prof.records:
     t = a.elapsed_time(b)
     key = fn
     fl = by = 0.0
-    if geom is not None and fn in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_wgrad", "vtb_conv_wgrad_pair"):
+    if geom is not None and fn in ("vtb_conv_fprop", "vtb_conv_fprop_bn", "vtb_conv_dgrad", "vtb_conv_dgrad_bn", "vtb_conv_wgrad", "vtb_conv_wgrad_pair"):
         g = geom._obj
         ho = (g.h + 2 * g.pad - g.k) // g.stride + 1
         key = f"{fn[9:]:8s} {g.cin:4d}->{g.cout:4d} k{g.k}s{g.stride} {g.h:3d}->{ho:3d}"

@@ -32,6 +32,21 @@ class VtbBnTrain(C.Structure):
                 ("running_var2", C.c_void_p), ("num_batches_tracked2", C.c_void_p)]
 
 
+class VtbBnBwdLayer(C.Structure):
+    """struct VtbBnBwdLayer of include/vtb.h (one producer layer of a dgrad that carries BatchNorm-backward statistics)."""
+
+    _fields_ = [("y", C.c_void_p), ("ldy", C.c_int), ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p),
+                ("invstd", C.c_void_p), ("relu", C.c_int), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("coef", C.c_void_p)]
+
+
+class VtbDgradBn(C.Structure):
+    """struct VtbDgradBn of include/vtb.h."""
+
+    _fields_ = [("split", C.c_int), ("layer", VtbBnBwdLayer * 2), ("count", C.c_double), ("partial", C.c_void_p),
+                ("tickets", C.c_void_p), ("sync", C.c_void_p)]
+
+
 class VtbPackJob(C.Structure):
     """struct VtbPackJob of include/vtb.h (one convolution's weight re-pack inside the batched launch)."""
 
@@ -69,6 +84,9 @@ SIGNATURES = {
     "vtb_conv_fprop": (_i, [_cp, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _p]),
     "vtb_conv_fprop_bn": (_i, [_cp, _p, _i, _p, _p, _i, _p, C.POINTER(VtbBnTrain), _p]),
     "vtb_conv_dgrad": (_i, [_cp, _p, _i, _p, _p, _i, _i, _p]),
+    "vtb_conv_dgrad_stats_rows": (_i, [_cp]),
+    "vtb_conv_dgrad_panel_w": (_i, [_cp]),
+    "vtb_conv_dgrad_bn": (_i, [_cp, _p, _i, _p, _p, _i, _i, C.POINTER(VtbDgradBn), _p]),
     "vtb_conv_wgrad": (_i, [_cp, _p, _i, _p, _i, _p, _p, _i, _i, _p]),
     "vtb_conv_wgrad_pair": (_i, [_cp, _p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _p]),
     "vtb_bn_stats_reduce": (_i, [_p, _i, _i, _p, _p]),

@@ -537,9 +537,60 @@ int vtb_conv_fprop_bn(const VtbConv* c, const void* x, int ldx, const void* wf, 
   return fprop_impl(c, x, ldx, wf, y, ldy, stats_partial, nullptr, nullptr, 0, nullptr, 0, bn, stream);
 }
 
-int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
-                   void* stream) {
+// tiling of the dgrad launch(es) of a geometry: stride 1 -> one launch; stride 2 -> one per output-parity phase
+static int dgrad_phase_tiling(const VtbConv* c, int ph, int pq, ConvTiling* tl, int* nr_out, int* ns_out) {
+  const int k = c->k, pad = c->pad;
+  if (c->stride == 1) {
+    *tl = plan_conv_tiling((long long)c->n * c->h * c->w, c->cin, k * k * c->cout / 16);
+    return 1;
+  }
+  const int Hph = (c->h - ph + 1) / 2, Wph = (c->w - pq + 1) / 2;
+  if (Hph <= 0 || Wph <= 0) return 0;
+  int nr = 0, ns = 0;
+  for (int r = 0; r < k; ++r) nr += (((ph + pad - r) % 2 + 2) % 2 == 0);
+  for (int s = 0; s < k; ++s) ns += (((pq + pad - s) % 2 + 2) % 2 == 0);
+  if (nr_out) *nr_out = nr;
+  if (ns_out) *ns_out = ns;
+  if (nr == 0 || ns == 0) return -1;
+  *tl = plan_conv_tiling((long long)c->n * Hph * Wph, c->cin, nr * ns * c->cout / 16);
+  return 1;
+}
+
+// copies the BatchNorm-backward statistics request into the kernel parameters; `panel_w`: a staged panel must not
+// straddle the boundary between the two producer layers
+static int apply_dgrad_bn(ConvIgemmParams& p, const VtbConv* c, const VtbDgradBn* bn, int panel_w) {
+  if (!bn->partial || bn->count <= 0 || bn->split < 0 || bn->split >= c->cin || (bn->split % panel_w) != 0)
+    return fail(VTB_EINVAL, "vtb_conv_dgrad_bn: bad statistics arguments (split must be a multiple of %d)", panel_w);
+  const int nl = bn->split > 0 ? 2 : 1;
+  for (int l = 0; l < nl; ++l) {
+    const VtbBnBwdLayer& L = bn->layer[l];
+    const int lc = (nl == 1) ? c->cin : (l == 0 ? bn->split : c->cin - bn->split);
+    if (!L.y || L.ldy < lc || L.ldy % 8 || (reinterpret_cast<uintptr_t>(L.y) & 15) || !L.scale || !L.shift || !L.mean ||
+        !L.invstd || !L.coef)
+      return fail(VTB_EINVAL, "vtb_conv_dgrad_bn: bad producer layer %d", l);
+    p.bwd_y[l] = (const __nv_bfloat16*)L.y;
+    p.bwd_ldy[l] = L.ldy;
+    p.bwd_scale[l] = L.scale;
+    p.bwd_shift[l] = L.shift;
+    p.bwd_mean[l] = L.mean;
+    p.bwd_invstd[l] = L.invstd;
+    p.bwd_relu[l] = L.relu;
+    p.bwd_dgamma[l] = L.dgamma;
+    p.bwd_dbeta[l] = L.dbeta;
+    p.bwd_coef[l] = L.coef;
+  }
+  p.bwd_split = bn->split;
+  p.stats_partial = bn->partial;
+  p.bn_count = bn->count;
+  if (bn->sync && !sync_args_ok(bn->sync, c->cin)) return fail(VTB_EINVAL, "vtb_conv_dgrad_bn: bad SyncBN peers");
+  p.sync = make_sync_peers(bn->sync);
+  return VTB_OK;
+}
+
+static int dgrad_impl(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
+                      const VtbDgradBn* bn, void* stream) {
   if (!conv_ok(c) || !dy || !wd || !dx) return fail(VTB_EINVAL, "vtb_conv_dgrad: bad arguments");
+  if (bn && !bn->tickets) return fail(VTB_EINVAL, "vtb_conv_dgrad_bn: tickets must not be NULL");
   if (lddy < c->cout || lddx < c->cin || lddy % 8 || lddx % 8) return fail(VTB_EINVAL, "vtb_conv_dgrad: bad pitch");
   if (!driver_api().ok) return fail(VTB_ENODEV, "cuTensorMapEncode* not available from this driver");
   int ho, wo;
@@ -586,10 +637,28 @@ int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, v
       return fail(VTB_ECUDA, "vtb_conv_dgrad: im2col tensor map for dy failed");
     if (!tmap_tiled_2d(&tmD, dx, c->cin, p.M, (uint64_t)lddx * 2, p.panel_w, 32, p.panel_w * 2))
       return fail(VTB_ECUDA, "vtb_conv_dgrad: tensor map for dx failed");
+    if (bn) {
+      if (int e = apply_dgrad_bn(p, c, bn, p.panel_w)) return e;
+      p.tickets = bn->tickets;
+    }
     count_launch(1);
     return check_cuda(launch_conv_igemm(tmA, tmB, tmD, p, tl.grid, (cudaStream_t)stream),
                       "conv_igemm_kernel(dgrad s1)");
   }
+
+  // statistics rows of the phase launches are stacked; the last launch reduces all of them
+  int last_ph = -1, total_rows = 0;
+  if (bn) {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pq = 0; pq < 2; ++pq) {
+        ConvTiling tl;
+        if (dgrad_phase_tiling(c, ph, pq, &tl, nullptr, nullptr) > 0) {
+          last_ph = ph * 2 + pq;
+          total_rows += tl.stat_rows;
+        }
+      }
+  }
+  int row0 = 0;
 
   // stride 2: one launch per output-parity phase (ph, pw); each is a dense stride-1 walk over dY.
   for (int ph = 0; ph < 2; ++ph) {
@@ -648,12 +717,54 @@ int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, v
       if (!tmap_im2col_nhwc(&tmA, dy, c->cout, wo, ho, c->n, lddy, lo_w, lo_h, up_w, up_h, q.kc, q.block_m, 1,
                             q.kc * 2))
         return fail(VTB_ECUDA, "vtb_conv_dgrad: im2col tensor map for dy (phase %d,%d) failed", ph, pq);
+      if (bn) {
+        if (int e = apply_dgrad_bn(q, c, bn, q.panel_w)) return e;
+        q.stats_row0 = row0;
+        row0 += tl.stat_rows;
+        if (ph * 2 + pq == last_ph) {
+          q.tickets = bn->tickets;
+          q.fin_rows = total_rows;
+        }
+      }
       count_launch(1);
       int e = launch_conv_igemm(tmA, tmB, tmD, q, tl.grid, (cudaStream_t)stream);
       if (e) return check_cuda(e, "conv_igemm_kernel(dgrad s2)");
     }
   }
   return VTB_OK;
+}
+
+int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
+                   void* stream) {
+  return dgrad_impl(c, dy, lddy, wd, dx, lddx, accumulate, nullptr, stream);
+}
+
+int vtb_conv_dgrad_bn(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
+                      const VtbDgradBn* bn, void* stream) {
+  if (!bn) return fail(VTB_EINVAL, "vtb_conv_dgrad_bn: bn must not be NULL");
+  return dgrad_impl(c, dy, lddy, wd, dx, lddx, accumulate, bn, stream);
+}
+
+int vtb_conv_dgrad_stats_rows(const VtbConv* c) {
+  if (!conv_ok(c)) return fail(VTB_EINVAL, "vtb_conv_dgrad_stats_rows: bad geometry");
+  int rows = 0;
+  for (int ph = 0; ph < (c->stride == 1 ? 1 : 2); ++ph)
+    for (int pq = 0; pq < (c->stride == 1 ? 1 : 2); ++pq) {
+      ConvTiling tl;
+      if (dgrad_phase_tiling(c, ph, pq, &tl, nullptr, nullptr) > 0) rows += tl.stat_rows;
+    }
+  return rows;
+}
+
+// panel width of the dgrad epilogue: VtbDgradBn.split must be a multiple of it
+int vtb_conv_dgrad_panel_w(const VtbConv* c) {
+  if (!conv_ok(c)) return fail(VTB_EINVAL, "vtb_conv_dgrad_panel_w: bad geometry");
+  ConvTiling tl;
+  int w = 0;
+  for (int ph = 0; ph < (c->stride == 1 ? 1 : 2); ++ph)
+    for (int pq = 0; pq < (c->stride == 1 ? 1 : 2); ++pq)
+      if (dgrad_phase_tiling(c, ph, pq, &tl, nullptr, nullptr) > 0) w = std::max(w, tl.panel_w);
+  return w;
 }
 
 static int wgrad_impl(const VtbConv* c, const void* dy, int lddy, const void* x, int ldx, void* workspace,

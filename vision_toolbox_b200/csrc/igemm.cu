@@ -39,62 +39,125 @@ __device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return of
 
 
 // Per-warp drain of a staged bf16 panel of 32 rows x (8*CH) columns (row pitch 16*CH bytes, XOR-swizzled 16-byte
-// chunks): lane = rg * CH + chunk reads chunk `chunk` of the rows of row group rg with 16-byte loads, writes them
-// to global memory (a warp instruction covers whole 16*CH-byte row segments -> coalesced; ADD = read-modify-write
-// for gradient fan-in, rounding like two bf16 tensors being added) and, if STATS, sums its 8 columns; a
-// recursive-halving butterfly across the row groups then leaves the 32-row (sum, sumsq) totals of
-//   CH == 8: columns chunk*8 + (rg&1)*4 + (rg>>1)*2, +1                        -> (o0,o1) and (o2,o3)
-//   CH == 4: column  chunk*8 + (rg&1)*4 + ((rg>>1)&1)*2 + (rg>>2)               -> (o0,o1)
-//   CH == 2: same column formula on rg bits 0..2; lanes with rg bit 3 clear hold the result -> (o0,o1)
-template <int CH, bool ADD, bool STATS>
-__device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloat16* gdst, int ld, int rows_valid,
-                                            float& o0, float& o1, float& o2, float& o3) {
+// chunks): lane = rg * CH + chunk reads chunk `chunk` of the CH rows of row group rg with 16-byte loads and writes them to
+// global memory at pixel index pix[r] (< 0: row outside the tensor) - a warp instruction covers whole 16*CH-byte row
+// segments -> coalesced; dense tiles pass consecutive pixel indices, stride-2 dgrad phases a strided lattice.
+//   ADD    : read-modify-write for gradient fan-in, rounding like two bf16 tensors being added
+//   MODE 1 : BatchNorm forward statistics of the stored values: S = sum v, Q = sum v^2
+//   MODE 2 : BatchNorm(+ReLU) backward statistics against the producer's raw output y (BwdCols): the stored value is the
+//            final gradient g; dz = g * (y*scale + shift > 0); S = sum dz, Q = sum dz * y (the finaliser subtracts
+//            mean * S in double: two per-channel constants in registers instead of three)
+// A recursive-halving butterfly across the row groups then leaves the 32-row (S, Q) totals of
+//   CH == 4: column chunk*8 + (rg&1)*4 + ((rg>>1)&1)*2 + (rg>>2)      CH == 2: same formula on rg bits 0..2; lanes with
+//   rg bit 3 clear hold the result                                                                   -> (o0, o1)
+struct BwdCols {            // per-panel view of the producer layer: pointers already offset to the panel's first column
+  const __nv_bfloat16* y;
+  int ldy;
+  const float* scale;
+  const float* shift;
+  int relu;
+};
+// `early`: rows the caller loaded BEFORE staging the panel (their latency overlaps the TMEM -> shared-memory staging):
+// the producer's y rows in MODE 2, else the old destination rows when ADD (see panel_early_load).
+template <int CH, bool ADD, int MODE>
+__device__ __forceinline__ void panel_early_load(int lane, const __nv_bfloat16* gcol, int ld, const int (&pix)[4],
+                                                 const BwdCols& bw, uint4 (&early)[4]) {
+  const int chunk = lane % CH;
+  if (MODE == 2) {
+#pragma unroll
+    for (int r = 0; r < CH; ++r)
+      early[r] = (pix[r] >= 0) ? __ldg(reinterpret_cast<const uint4*>(bw.y + (size_t)pix[r] * bw.ldy + chunk * 8))
+                               : make_uint4(0u, 0u, 0u, 0u);
+  } else if (ADD) {
+#pragma unroll
+    for (int r = 0; r < CH; ++r)
+      early[r] = (pix[r] >= 0) ? *reinterpret_cast<const uint4*>(gcol + (size_t)pix[r] * ld + chunk * 8)
+                               : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+template <int CH, bool ADD, int MODE>
+__device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloat16* gcol, int ld, const int (&pix)[4],
+                                            const BwdCols& bw, const uint4 (&early)[4], float& o0, float& o1) {
   constexpr int RG = 32 / CH;          // row groups
-  constexpr int ROWS = 32 / RG;        // rows per group
+  constexpr int ROWS = CH;             // rows per group
   constexpr uint32_t PITCH = 16 * CH;
-  constexpr uint32_t SMASK = (CH == 8) ? 7u : (CH == 4 ? 3u : 1u);
+  constexpr uint32_t SMASK = (CH == 4) ? 3u : 1u;
   const int chunk = lane % CH, rg = lane / CH;
   float S[8], Q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) S[j] = Q[j] = 0.f;
-  // read-modify-write epilogue: issue every global read of this lane before the first dependent add, so the ROWS
-  // round trips overlap instead of serialising (the drain is latency-bound per warp)
-  uint4 old[ADD ? ROWS : 1];
-  if (ADD) {
+  float sc[MODE == 2 ? 8 : 1], sh[MODE == 2 ? 8 : 1];
+  if (MODE == 2) {
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const int rr = rg * ROWS + r;
-      old[r] = (rr < rows_valid) ? *reinterpret_cast<const uint4*>(gdst + (size_t)rr * ld + chunk * 8) : make_uint4(0u, 0u, 0u, 0u);
+    for (int h = 0; h < 2; ++h) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(bw.scale + chunk * 8) + h);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bw.shift + chunk * 8) + h);
+      sc[4 * h] = a.x; sc[4 * h + 1] = a.y; sc[4 * h + 2] = a.z; sc[4 * h + 3] = a.w;
+      sh[4 * h] = b.x; sh[4 * h + 1] = b.y; sh[4 * h + 2] = b.z; sh[4 * h + 3] = b.w;
     }
   }
+  // MODE 2 with ADD still has to read the old destination rows here (the early registers hold y): two rows at a time,
+  // every read of a batch issued before its first use; the lines were prefetched into L2 at the start of the tile
+  constexpr bool LATE_OLD = ADD && MODE == 2;
+  constexpr int RB = LATE_OLD ? (ROWS > 2 ? 2 : ROWS) : ROWS;
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const int rr = rg * ROWS + r;
-    uint32_t w[4];
-    const uint32_t off = swz((uint32_t)rr * PITCH + chunk * 16, SMASK);
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(panel + off));
-    if (rr < rows_valid) {
-      uint4* gp = reinterpret_cast<uint4*>(gdst + (size_t)rr * ld + chunk * 8);
-      if (ADD) {
-        const uint4 ov = old[r];
-        const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w};
+  for (int r0 = 0; r0 < ROWS; r0 += RB) {
+    uint4 old[LATE_OLD ? RB : 1];
+    if (LATE_OLD) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(bf16lo(w[j]) + bf16lo(oo[j]), bf16hi(w[j]) + bf16hi(oo[j]));
-      }
-      *gp = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int r = 0; r < RB; ++r)
+        old[r] = (pix[r0 + r] >= 0) ? *reinterpret_cast<const uint4*>(gcol + (size_t)pix[r0 + r] * ld + chunk * 8)
+                                    : make_uint4(0u, 0u, 0u, 0u);
     }
-    if (STATS) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = bf16lo(w[j]), b = bf16hi(w[j]);
-        S[2 * j] += a;
-        Q[2 * j] = fmaf(a, a, Q[2 * j]);
-        S[2 * j + 1] += b;
-        Q[2 * j + 1] = fmaf(b, b, Q[2 * j + 1]);
+    for (int r = 0; r < RB; ++r) {
+      const int rr = rg * ROWS + r0 + r;
+      const int px = pix[r0 + r];
+      uint32_t w[4];
+      const uint32_t off = swz((uint32_t)rr * PITCH + chunk * 16, SMASK);
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(panel + off));
+      if (px >= 0) {
+        uint4* gp = reinterpret_cast<uint4*>(gcol + (size_t)px * ld + chunk * 8);
+        if (ADD) {
+          const uint4 ov = LATE_OLD ? old[r] : early[r0 + r];
+          const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(bf16lo(w[j]) + bf16lo(oo[j]), bf16hi(w[j]) + bf16hi(oo[j]));
+        }
+        *gp = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      if (MODE == 1) {   // rows outside the tensor hold zeros (TMA zero-fills the operand rows): they add nothing
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16lo(w[j]), b = bf16hi(w[j]);
+          S[2 * j] += a;
+          Q[2 * j] = fmaf(a, a, Q[2 * j]);
+          S[2 * j + 1] += b;
+          Q[2 * j + 1] = fmaf(b, b, Q[2 * j + 1]);
+        }
+      }
+      if (MODE == 2) {
+        if (px >= 0) {
+          const uint4 yy4 = early[r0 + r];
+          const uint32_t yy[4] = {yy4.x, yy4.y, yy4.z, yy4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int e = 2 * j + hh;
+              const float g = hh ? bf16hi(w[j]) : bf16lo(w[j]);
+              const float y = hh ? bf16hi(yy[j]) : bf16lo(yy[j]);
+              const float z = fmaf(y, sc[e], sh[e]);
+              const float dz = (!bw.relu || z > 0.f) ? g : 0.f;
+              S[e] += dz;
+              Q[e] = fmaf(dz, y, Q[e]);
+            }
+          }
+        }
       }
     }
   }
-  if (STATS) {
+  if (MODE != 0) {
     // butterfly over the row-group bits of the lane index
     int n = 8;
 #pragma unroll
@@ -122,15 +185,21 @@ __device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloa
   }
   o0 = S[0];
   o1 = Q[0];
-  o2 = (CH == 8) ? S[1] : 0.f;
-  o3 = (CH == 8) ? Q[1] : 0.f;
 }
-template <bool ADD, bool STATS>
-__device__ __forceinline__ void panel_drain_pw(int pw, uint32_t panel, int lane, __nv_bfloat16* gdst, int ld,
-                                               int rows_valid, float& o0, float& o1, float& o2, float& o3) {
-  if (pw == 32) panel_drain<4, ADD, STATS>(panel, lane, gdst, ld, rows_valid, o0, o1, o2, o3);
-  else panel_drain<2, ADD, STATS>(panel, lane, gdst, ld, rows_valid, o0, o1, o2, o3);
+template <bool ADD, int MODE>
+__device__ __forceinline__ void panel_drain_pw(int pw, uint32_t panel, int lane, __nv_bfloat16* gcol, int ld,
+                                               const int (&pix)[4], const BwdCols& bw, const uint4 (&early)[4], float& o0,
+                                               float& o1) {
+  if (pw == 32) panel_drain<4, ADD, MODE>(panel, lane, gcol, ld, pix, bw, early, o0, o1);
+  else panel_drain<2, ADD, MODE>(panel, lane, gcol, ld, pix, bw, early, o0, o1);
 }
+template <bool ADD, int MODE>
+__device__ __forceinline__ void panel_early_pw(int pw, int lane, const __nv_bfloat16* gcol, int ld, const int (&pix)[4],
+                                               const BwdCols& bw, uint4 (&early)[4]) {
+  if (pw == 32) panel_early_load<4, ADD, MODE>(lane, gcol, ld, pix, bw, early);
+  else panel_early_load<2, ADD, MODE>(lane, gcol, ld, pix, bw, early);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // mbarrier wait that optionally accounts the stalled cycles (development counters, ConvIgemmParams::dbg)
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool timed, long long& acc) {
@@ -165,9 +234,9 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool 
 // EPI selects the epilogue flavour at compile time (each instantiation only carries the registers it needs):
 //   kEpiStats   dense store + BatchNorm statistics (training fprop)
 //   kEpiAffine  dense store of [relu](acc*scale+shift)[+residual] (eval-mode fused fprop)
-//   kEpiPlain   dense store or read-modify-write accumulate (stride-1 dgrad, fprop without statistics)
-//   kEpiScatter strided per-row store / accumulate (stride-2 dgrad phases)
-enum EpiKind : int { kEpiStats = 0, kEpiAffine = 1, kEpiPlain = 2, kEpiScatter = 3 };
+//   kEpiPlain   store or read-modify-write accumulate, dense or strided pixel lattice (dgrad, fprop without statistics)
+//   kEpiBwd     kEpiPlain + BatchNorm(+ReLU) backward statistics of the producer layer(s) (ConvIgemmParams::bwd_*)
+enum EpiKind : int { kEpiStats = 0, kEpiAffine = 1, kEpiPlain = 2, kEpiBwd = 3 };
 
 template <bool TIMED, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -362,30 +431,70 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int pw = p.panel_w;
     const uint32_t pitch = pw * 2;
     const uint32_t smask = (pw == 64) ? 7u : (pw == 32 ? 3u : 1u);
-    constexpr bool tma_mode = (EPI != kEpiScatter);   // dense (staged, coalesced) store
-    constexpr bool do_stats = (EPI == kEpiStats);
+    constexpr bool do_stats = (EPI == kEpiStats || EPI == kEpiBwd);   // per-channel (S, Q) sums ride in the drain
+    const bool scatter = (p.store_mode == kStoreScatter || p.store_mode == kStoreScatterAdd);
+    const bool add = (p.store_mode == kStoreTmaAdd || p.store_mode == kStoreScatterAdd);
     const int npanels = p.block_n / pw;         // host guarantees npanels <= kMaxPanels
     const int n0 = n_blk * p.block_n;
     // this warp's staging buffer: 32 rows x 64 B (panels are at most 32 columns wide)
     const uint32_t my_panels = panel_base + (uint32_t)(warp - 4) * 2048u;
-    // running (sum, sumsq) totals of this lane's column(s) for the whole CTA lifetime, 16 registers:
-    // pw == 64: up to 4 panels x 4 values (two columns); pw < 64: up to 8 panels x 2 values (one column)
+    // running (S, Q) totals of this lane's column for the whole CTA lifetime: up to 4 local panels x 2 values
     // (scalars, not an array: a runtime-indexed array would be demoted to local memory = L2 round trips here)
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;   // <= 4 local panels x (sum, sumsq) of one column
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     // SyncBN: the sequence number of this launch must be read before any exchange of the launch can complete
     unsigned int my_seq = 0;
-    if (do_stats && p.sync.world > 1 && threadIdx.x == 128) my_seq = sync_read_seq(p.sync);
+    if (do_stats && p.sync.world > 1 && p.tickets != nullptr && threadIdx.x == 128) my_seq = sync_read_seq(p.sync);
     uint32_t lt = 0;
     long long w_tfull = 0, t_ld = 0, t_cvt = 0, t_drain = 0;
     // work split: with two halves each group drains its own half; with one half the groups take alternate panels
     const int my_half = (halves == 2) ? (grp >> 1) : 0;
     const int pi_first = (halves == 2) ? (grp & 1) : grp;
     const int pi_step = (halves == 2) ? 2 : 4;
+    // rows of the staged panel this lane writes out (panel_drain): row group rg, rows rg*CH .. rg*CH + CH-1
+    const int drain_ch = pw >> 3;               // 16-byte chunks per panel row: 4 (pw 32) or 2 (pw 16)
+    const int drain_row0 = quarter * 32 + (lane / drain_ch) * drain_ch;
     for (int m_blk = m_first; m_blk < num_m_blocks; m_blk += m_step, ++lt) {
       const int h = my_half;
       const uint32_t set = (nsets == 2u) ? (lt & 1u) : 0u;
       const uint32_t use = (nsets == 2u) ? (lt >> 1) : lt;
       const int m0 = m_blk * p.block_m + h * kBlockM;
+      // pixel index (in the output tensor's lattice) of the rows this lane stores; < 0: outside the tensor
+      int pix[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int mm = m0 + drain_row0 + r;
+        int px = -1;
+        if (r < drain_ch && mm < p.M) {
+          px = mm;
+          if (scatter) {
+            const int q = mm % p.Wq;
+            const int t = mm / p.Wq;
+            const int pp = t % p.Hp;
+            const int img = t / p.Hp;
+            px = (img * p.OH + pp * p.os + p.oph) * p.OW + q * p.os + p.opw;
+          }
+        }
+        pix[r] = px;
+      }
+      if (EPI == kEpiBwd || (EPI == kEpiPlain && add)) {
+        // the rows this lane will read in its drains (producer y / old destination): pull their lines into L2 while the
+        // tile's MMAs are still running, so the loads below are L2 hits
+        if ((lane % drain_ch) == 0) {
+          for (int pi = pi_first; pi < npanels; pi += pi_step) {
+            const int colp = n0 + pi * pw;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if (pix[r] >= 0) {
+                if (add) prefetch_l2(p.out + (size_t)pix[r] * p.ldo + colp);
+                if (EPI == kEpiBwd) {
+                  const int L = (p.bwd_split > 0 && colp >= p.bwd_split) ? 1 : 0;
+                  prefetch_l2(p.bwd_y[L] + (size_t)pix[r] * p.bwd_ldy[L] + (colp - (L ? p.bwd_split : 0)));
+                }
+              }
+            }
+          }
+        }
+      }
       mbar_wait_t(tfull_bar(set), use & 1u, timed, w_tfull);
       tc_fence_after();
       if (pi_first >= npanels) {  // nothing to drain for this group: release the set straight away
@@ -394,21 +503,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       const uint32_t acc0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * set_cols + (h * ksplit) * acc_stride;
 
-      // scatter-mode addressing for this thread's pixel
-      __nv_bfloat16* out_row = nullptr;
       const int m = m0 + row;
-      if (!tma_mode && m < p.M) {
-        const int q = m % p.Wq;
-        const int t = m / p.Wq;
-        const int pp = t % p.Hp;
-        const int img = t / p.Hp;
-        out_row = p.out + ((size_t)((size_t)img * p.OH + (size_t)pp * p.os + p.oph) * p.OW + (size_t)q * p.os + p.opw) *
-                              (size_t)p.ldo;
-      }
       for (int pi = pi_first; pi < npanels; pi += pi_step) {
         const uint32_t panel = my_panels;
         const uint32_t taddr = acc0 + pi * pw;
         long long tp_ld = 0, tp_cvt = 0;
+        const int colp = n0 + pi * pw;            // first column of this panel
+        __nv_bfloat16* gcol = p.out + colp;
+        BwdCols bw;
+        bw.y = nullptr; bw.ldy = 0; bw.scale = bw.shift = nullptr; bw.relu = 0;
+        uint4 early[4];
+        if (EPI == kEpiBwd) {
+          // the producer layer this panel's channels belong to (a panel never straddles bwd_split: host-checked)
+          const int L = (p.bwd_split > 0 && colp >= p.bwd_split) ? 1 : 0;
+          const int lc = colp - (L ? p.bwd_split : 0);
+          bw.y = p.bwd_y[L] + lc;
+          bw.ldy = p.bwd_ldy[L];
+          bw.scale = p.bwd_scale[L] + lc;
+          bw.shift = p.bwd_shift[L] + lc;
+          bw.relu = p.bwd_relu[L];
+          panel_early_pw<false, 2>(pw, lane, gcol, p.ldo, pix, bw, early);
+        } else if (EPI == kEpiPlain && add) {
+          panel_early_pw<true, 0>(pw, lane, gcol, p.ldo, pix, bw, early);
+        }
         // the panel is drained in pieces of 16 columns to keep the register footprint small: this kernel runs with
         // ~no L1 (all of it is shared memory), so a spilled register costs an L2 round trip
         const int npieces = pw / 16;
@@ -439,68 +556,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           const long long tq1 = timed ? clock64() : 0;
           {
-            {
-              const int ch = pc;   // 16-column chunk inside the panel
-              float f[16];
+            const int ch = pc;   // 16-column chunk inside the panel
+            float f[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-              const int col0 = n0 + pi * pw + ch * 16;
-              if (EPI == kEpiAffine && p.scale != nullptr) {
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            const int col0 = n0 + pi * pw + ch * 16;
+            if (EPI == kEpiAffine && p.scale != nullptr) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], __ldg(p.scale + col0 + i), __ldg(p.shift + col0 + i));
-              }
-              if (EPI == kEpiAffine && p.relu) {
+              for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], __ldg(p.scale + col0 + i), __ldg(p.shift + col0 + i));
+            }
+            if (EPI == kEpiAffine && p.relu) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-              }
-              if (EPI == kEpiAffine && p.residual != nullptr && m < p.M) {
-                const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.ldr + col0);
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (EPI == kEpiAffine && p.residual != nullptr && m < p.M) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.ldr + col0);
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  const uint4 rv = __ldg(r4 + hh);
-                  const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+              for (int hh = 0; hh < 2; ++hh) {
+                const uint4 rv = __ldg(r4 + hh);
+                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    // the reference adds two bf16 tensors: round first, then add
-                    f[hh * 8 + 2 * i] = __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i])) + bf16lo(rr[i]);
-                    f[hh * 8 + 2 * i + 1] =
-                        __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i + 1])) + bf16hi(rr[i]);
-                  }
+                for (int i = 0; i < 4; ++i) {
+                  // the reference adds two bf16 tensors: round first, then add
+                  f[hh * 8 + 2 * i] = __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i])) + bf16lo(rr[i]);
+                  f[hh * 8 + 2 * i + 1] =
+                      __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i + 1])) + bf16hi(rr[i]);
                 }
               }
-              if (tma_mode) {
-                uint32_t pk[8];
+            }
+            uint32_t pk[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  const uint32_t off = swz(lane * pitch + (ch * 2 + hh) * 16, smask);
-                  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(panel + off), "r"(pk[4 * hh]),
-                               "r"(pk[4 * hh + 1]), "r"(pk[4 * hh + 2]), "r"(pk[4 * hh + 3])
-                               : "memory");
-                }
-              } else if (out_row != nullptr) {
-                uint4* o4 = reinterpret_cast<uint4*>(out_row + col0);
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  if (p.store_mode == kStoreScatterAdd) {
-                    const uint4 ov = o4[hh];
-                    const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                      f[hh * 8 + 2 * i] = __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i])) + bf16lo(oo[i]);
-                      f[hh * 8 + 2 * i + 1] =
-                          __bfloat162float(__float2bfloat16_rn(f[hh * 8 + 2 * i + 1])) + bf16hi(oo[i]);
-                    }
-                  }
-                  uint4 sv;
-                  sv.x = pack_bf16x2(f[hh * 8 + 0], f[hh * 8 + 1]);
-                  sv.y = pack_bf16x2(f[hh * 8 + 2], f[hh * 8 + 3]);
-                  sv.z = pack_bf16x2(f[hh * 8 + 4], f[hh * 8 + 5]);
-                  sv.w = pack_bf16x2(f[hh * 8 + 6], f[hh * 8 + 7]);
-                  o4[hh] = sv;
-                }
-              }
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t off = swz(lane * pitch + (ch * 2 + hh) * 16, smask);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(panel + off), "r"(pk[4 * hh]),
+                           "r"(pk[4 * hh + 1]), "r"(pk[4 * hh + 2]), "r"(pk[4 * hh + 3])
+                           : "memory");
             }
           }
           if (timed) {
@@ -509,15 +601,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         const long long tp2 = timed ? clock64() : 0;
-        if (tma_mode) {
+        {
           __syncwarp();
-          float o0, o1, o2, o3;
-          const int rows_valid = p.M - (m0 + quarter * 32);   // rows of this warp inside the tensor (may be <= 0)
-          __nv_bfloat16* gdst = p.out + (size_t)(m0 + quarter * 32) * p.ldo + n0 + pi * pw;
-          if (do_stats) panel_drain_pw<false, true>(pw, panel, lane, gdst, p.ldo, rows_valid, o0, o1, o2, o3);
-          else if (EPI == kEpiPlain && p.store_mode == kStoreTmaAdd)
-            panel_drain_pw<true, false>(pw, panel, lane, gdst, p.ldo, rows_valid, o0, o1, o2, o3);
-          else panel_drain_pw<false, false>(pw, panel, lane, gdst, p.ldo, rows_valid, o0, o1, o2, o3);
+          float o0 = 0.f, o1 = 0.f;
+          if (EPI == kEpiBwd) {
+            if (add) panel_drain_pw<true, 2>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
+            else panel_drain_pw<false, 2>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
+          } else if (EPI == kEpiStats) {
+            panel_drain_pw<false, 1>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
+          } else if (EPI == kEpiPlain && add) {
+            panel_drain_pw<true, 0>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
+          } else {
+            panel_drain_pw<false, 0>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
+          }
           if (do_stats) {
             const int lpi = (pi - pi_first) / pi_step;   // local panel index of this group, < 4
             if (lpi == 0) { a0.x += o0; a0.y += o1; }
@@ -535,8 +631,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (do_stats) {
       // Combine the 4 (x2 halves) lane-quarter slices of the CTA in shared memory (fixed order), so that the CTA
       // contributes ONE statistics row; then, if the caller asked for it (p.tickets), the last CTA of this n-block
-      // to finish turns the rows into mean / invstd / scale / shift and the running-statistics update - BatchNorm's
-      // finalisation costs no extra launch.
+      // to finish turns the rows into mean / invstd / scale / shift and the running-statistics update (forward) or
+      // into the BatchNorm-backward coefficients and parameter gradients of the producer layer (kEpiBwd) -
+      // BatchNorm's finalisation costs no extra launch.
       const int et = threadIdx.x - 128;             // 0..511 over the 16 epilogue warps
       const int nslices = halves * 4;
       float2* slots = reinterpret_cast<float2*>(smem_raw + (panel_base - smem_u32(smem_raw)));   // [8][block_n]
@@ -558,7 +655,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (col >= 0) slots[q8 * p.block_n + pi * pw + col] = o;
       }
       named_bar_sync(1, kEpiWarps * 32);
-      float* rowp = p.stats_partial + (size_t)m_first * p.cout * 2;
+      float* rowp = p.stats_partial + (size_t)(p.stats_row0 + m_first) * p.cout * 2;
       if (et < p.block_n) {
         float sx = 0.f, sq = 0.f;
         for (int q = 0; q < nslices; ++q) {
@@ -584,18 +681,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // G row groups x block_n columns; each thread sums rows g, g+G, .. of its column in double
           const int G = (kEpiWarps * 32) / p.block_n;
           const int g = et / p.block_n, col = et - g * p.block_n;
+          const int nrows = p.fin_rows;
           double* dsl = reinterpret_cast<double*>(slots);   // [G][block_n][2]
           if (g < G) {
             double sx = 0.0, sq = 0.0;
             const float* src = p.stats_partial + (size_t)(n0 + col) * 2;
             const size_t rstride = (size_t)p.cout * 2;
             // 8 independent loads in flight per thread (a dependent add right behind each load would serialise them)
-            for (int r = g; r < m_step; r += 8 * G) {
+            for (int r = g; r < nrows; r += 8 * G) {
               float2 v[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
                 const int rr = r + u * G;
-                v[u] = (rr < m_step) ? __ldcg(reinterpret_cast<const float2*>(src + (size_t)rr * rstride)) : make_float2(0.f, 0.f);
+                v[u] = (rr < nrows) ? __ldcg(reinterpret_cast<const float2*>(src + (size_t)rr * rstride)) : make_float2(0.f, 0.f);
               }
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
@@ -614,6 +712,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               sx += dsl[(gg * p.block_n + et) * 2];
               sq += dsl[(gg * p.block_n + et) * 2 + 1];
             }
+          }
+          // kEpiBwd: the producer layer of this channel; its sums so far are S = sum dz, Q = sum dz*y
+          const int BL = (EPI == kEpiBwd && p.bwd_split > 0 && ch >= p.bwd_split) ? 1 : 0;
+          const int bc = ch - (BL ? p.bwd_split : 0);
+          if (EPI == kEpiBwd && et < p.block_n) {
+            sq = (sq - (double)p.bwd_mean[BL][bc] * sx) * (double)p.bwd_invstd[BL][bc];   // sum dz * xhat
+            // parameter gradients come from the LOCAL sums (the gradient all-reduce averages them across ranks)
+            if (p.bwd_dgamma[BL] != nullptr) p.bwd_dgamma[BL][bc] = (float)sq;
+            if (p.bwd_dbeta[BL] != nullptr) p.bwd_dbeta[BL][bc] = (float)sx;
           }
           if (p.sync.world > 1) {
             // SyncBN: exchange this n-block's sums with all ranks over NVLink peer memory (syncbn.cuh)
@@ -641,7 +748,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          if (et < p.block_n) {
+          if (EPI == kEpiBwd) {
+            if (et < p.block_n)
+              *reinterpret_cast<float2*>(p.bwd_coef[BL] + (size_t)bc * 2) =
+                  make_float2((float)(sx / p.bn_count), (float)(sq / p.bn_count));
+          } else if (et < p.block_n) {
             const double mean = sx / p.bn_count;
             double var = sq / p.bn_count - mean * mean;
             if (var < 0) var = 0;
@@ -983,23 +1094,23 @@ int launch_conv_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   ConvIgemmParams p = p_in;
   fill_derived(p, grid);
   const size_t smem = conv_igemm_smem_bytes(p.block_m, p.block_n, p.num_stages, p.panel_bufs);
-  const bool dense = (p.store_mode == kStoreTma || p.store_mode == kStoreTmaAdd);
-  const int epi = !dense ? kEpiScatter
-                         : (p.stats_partial != nullptr ? kEpiStats
-                                                       : ((p.scale != nullptr || p.relu || p.residual != nullptr) ? kEpiAffine : kEpiPlain));
+  if (p.fin_rows <= 0) p.fin_rows = p.m_step;
+  const int epi = p.bwd_y[0] != nullptr ? kEpiBwd
+                  : (p.stats_partial != nullptr ? kEpiStats
+                                                : ((p.scale != nullptr || p.relu || p.residual != nullptr) ? kEpiAffine : kEpiPlain));
   if (p.dbg != nullptr) {
     switch (epi) {
       case kEpiStats: return launch_conv_variant<true, kEpiStats>(tmA, tmB, tmD, p, grid, smem, stream);
       case kEpiAffine: return launch_conv_variant<true, kEpiAffine>(tmA, tmB, tmD, p, grid, smem, stream);
       case kEpiPlain: return launch_conv_variant<true, kEpiPlain>(tmA, tmB, tmD, p, grid, smem, stream);
-      default: return launch_conv_variant<true, kEpiScatter>(tmA, tmB, tmD, p, grid, smem, stream);
+      default: return launch_conv_variant<true, kEpiBwd>(tmA, tmB, tmD, p, grid, smem, stream);
     }
   }
   switch (epi) {
     case kEpiStats: return launch_conv_variant<false, kEpiStats>(tmA, tmB, tmD, p, grid, smem, stream);
     case kEpiAffine: return launch_conv_variant<false, kEpiAffine>(tmA, tmB, tmD, p, grid, smem, stream);
     case kEpiPlain: return launch_conv_variant<false, kEpiPlain>(tmA, tmB, tmD, p, grid, smem, stream);
-    default: return launch_conv_variant<false, kEpiScatter>(tmA, tmB, tmD, p, grid, smem, stream);
+    default: return launch_conv_variant<false, kEpiBwd>(tmA, tmB, tmD, p, grid, smem, stream);
   }
 }
 

@@ -95,7 +95,7 @@ struct ConvIgemmParams {
   // BatchNorm(+ReLU) BACKWARD statistics (dgrad launches, bwd_y[0] != nullptr): this launch completes the gradient `g` of
   // a tensor that was produced by one ConvNormAct (or two, side by side on the channel axis: channels >= bwd_split belong
   // to the second, indexed from 0).  The epilogue reads the producer's raw conv output y at the pixels it stores and
-  // accumulates, per channel, sum(dz) and sum(dz * (y - mean)) with dz = g * (y*scale + shift > 0) into stats_partial
+  // accumulates, per channel, sum(dz) and sum(dz * y) with dz = g * (y*scale + shift > 0) into stats_partial
   // rows [stats_row0, stats_row0 + m_step); with `tickets` the last CTA of each n-block reduces rows [0, fin_rows)
   // (a stride-2 dgrad is four launches: only the last one finalises), exchanges them under SyncBN and writes
   // coef[c][2] = (mean dz, mean dz*xhat), dgamma = sum dz*xhat, dbeta = sum dz (local sums): the standalone BatchNorm

@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import VtbBnTrain, VtbConv, check
+from ._lib import VtbBnTrain, VtbConv, VtbDgradBn, check
 
 BF16 = 2
 F32 = 4
@@ -140,6 +140,10 @@ class ConvOp:
     pair_geom: Any = None   # VtbConv with cout = both units (first op only)
     # gathered-operand stem: (taps, image channels) when this op is the image's first convolution run as a 1x1 GEMM
     col: Any = None
+    # BatchNorm-backward statistics carried by this op's dgrad (Graph._plan_dgrad_bn): ([producer ConvOp, ...], split) when
+    # the dgrad into x is the LAST contribution to the gradient of the tensor(s) those producers wrote
+    dgrad_bn: Any = None
+    bwd_stats_from: Any = None   # producer side: the consumer op whose dgrad epilogue reduces this layer's (dz, dz*xhat) sums
 
 
 @dataclass
@@ -415,6 +419,64 @@ class Graph:
             if (res is not None and not res.is_output and not res.is_input and max(res.consumers) == i
                     and res.buf.exclusive_owner is res):  # a concat slice also receives gradient through the full view
                 res.grad_alias = op.out
+        self._plan_dgrad_bn()
+
+    def _plan_dgrad_bn(self) -> None:
+        """Decide which dgrad launches also reduce the BatchNorm(+ReLU) backward sums of the layer(s) that produced their
+        output tensor (``vtb_conv_dgrad_bn``; autograd chain ConvolutionBackward0 -> ReluBackward0 ->
+        NativeBatchNormBackward0 of reference components.py:26-39).
+
+        The backward pass visits the ops in reverse order; op i's dgrad writes (or accumulates into) the gradient of its
+        input view X.  That write completes the gradient of a producer's output region R inside X iff i is the
+        smallest-index op that reads any view overlapping R (every other contribution - later ops' dgrads, residual
+        identities, the seeds of graph outputs - has been applied before op i is visited).  X must be tiled exactly by
+        the outputs of one or two ConvNormAct units (two: the CSP concat buffer, darknet.py:53)."""
+        # Opt-in (VTB_DGRAD_BN=1).  Measured on B200 (profiles/r02_dgrad_bn_*.txt): the per-element mask / sum work costs the
+        # 16 epilogue warps of the GEMM more than the standalone reduce pass saves (1x1 128->128 @22^2: dgrad 16.7 -> 38.6 us
+        # per launch for 10 us saved in the BatchNorm kernel), so the default plan keeps vtb_bn_bwd_fused.
+        if not (self.training and self.need_grad) or self.f32 or _os.environ.get("VTB_DGRAD_BN", "0") != "1":
+            return
+        L = _lib.lib()
+        readers: dict[int, list[tuple[int, int, int, str]]] = {}   # buffer idx -> (op idx, c0, c1, role)
+        producers: dict[int, list[Any]] = {}
+        for i, op in enumerate(self.ops):
+            for role in ("x", "residual"):
+                t = getattr(op, role, None)
+                if t is not None:
+                    readers.setdefault(id(t.buf), []).append((i, t.coff, t.coff + t.c, role))
+            if op.kind == "conv" and op.y is not None:
+                producers.setdefault(id(op.out.buf), []).append(op)
+        for i, op in enumerate(self.ops):
+            if op.kind != "conv" or op.pair_of is not None or op.col is not None:
+                continue
+            x = op.x
+            if x.is_input:
+                continue
+            geom = op.pair_geom if op.pair is not None else op.geom
+            c0, c1 = x.coff, x.coff + x.c
+            prods = sorted((q for q in producers.get(id(x.buf), ())
+                            if q.out.coff >= c0 and q.out.coff + q.out.c <= c1 and q.bwd_stats_from is None),
+                           key=lambda q: q.out.coff)
+            if not prods or len(prods) > 2 or prods[0].out.coff != c0 or prods[-1].out.coff + prods[-1].out.c != c1:
+                continue
+            if len(prods) == 2 and prods[0].out.coff + prods[0].out.c != prods[1].out.coff:
+                continue
+            ok = True
+            for q in prods:
+                r0, r1 = q.out.coff, q.out.coff + q.out.c
+                first = min((j, role) for j, a, b, role in readers.get(id(x.buf), ()) if a < r1 and b > r0)
+                ok = ok and first == (i, "x") and (q.out.n, q.out.h, q.out.w) == (x.n, x.h, x.w)
+            split = prods[0].out.c if len(prods) == 2 else 0
+            pw = L.vtb_conv_dgrad_panel_w(C.byref(geom))
+            if not ok or pw <= 0 or split % pw:
+                continue
+            rows = L.vtb_conv_dgrad_stats_rows(C.byref(geom))
+            if rows <= 0:
+                check(-1, "vtb_conv_dgrad_stats_rows")
+            op.dgrad_bn = (prods, split)
+            for q in prods:
+                q.bwd_stats_from = op
+            self._stat(op, "partial_d", rows * x.c * 2)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -423,7 +485,7 @@ class Graph:
 class Run:
     """Device state of one forward call that backward needs (activation + statistics arenas)."""
 
-    __slots__ = ("act", "stat", "x_shape", "x_dtype", "x_requires_grad", "count_scale")
+    __slots__ = ("act", "stat", "x_shape", "x_dtype", "x_requires_grad", "count_scale", "bwd_stats_done")
 
 
 class DistConfig:
@@ -769,6 +831,11 @@ class Runner:
         for op, off in ((op_b, op_a.geom.cout), (op_a, 0)):
             fo = lambda name, op=op: sbase + 4 * op.st[name]
             out, yy = op.out, op.y
+            if id(op) in run.bwd_stats_done:
+                check(L.vtb_bn_bwd_apply(gp(out), gld(out), abase + yy.byte_offset(), yy.ld, out.pixels, op.geom.cout,
+                                         fo("scale"), fo("shift"), fo("mean"), fo("invstd"), int(op.relu), fo("coef"),
+                                         dybase + off * BF16, tot, st), "vtb_bn_bwd_apply(pair)")
+                continue
             check(L.vtb_bn_bwd_fused(gp(out), gld(out), abase + yy.byte_offset(), yy.ld, out.pixels, op.geom.cout,
                                      fo("scale"), fo("shift"), fo("mean"), fo("invstd"), int(op.relu),
                                      float(out.pixels) * world, fo("partial_b"), pgrads[op.pidx + 1].data_ptr(),
@@ -782,8 +849,7 @@ class Runner:
                                                                   pgrads[op_b.pidx].data_ptr(), op_a.geom.cout,
                                                                   op_a.cin_real, 0, s_), "vtb_conv_wgrad_pair"), st)
         if not (x.is_input and not run.x_requires_grad):
-            check(L.vtb_conv_dgrad(C.byref(geom), dybase, tot, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
-                  "vtb_conv_dgrad(pair)")
+            self._dgrad(op_a, geom, dybase, tot, wd, abase, gp, gld, is_init, pgrads, run, st)
             mark(x)
         for op in (op_a, op_b):
             self._residual_grad(op, gp, gld, is_init, mark, st)
@@ -909,6 +975,7 @@ class Runner:
         st = self._stream()
         dev = run.act.device
         abase, sbase = run.act.data_ptr(), (run.stat.data_ptr() + 255) // 256 * 256
+        run.bwd_stats_done = set()   # units whose BatchNorm-backward sums a consumer's dgrad epilogue has produced
         gact = torch.empty(g.grad_bytes, dtype=torch.uint8, device=dev)  # mirrors the "act" prefix of the arena
         gbase = gact.data_ptr()
         dy_stride = _round_up(g.dy_bytes, 1024)
@@ -1080,6 +1147,14 @@ class Runner:
         f = lambda name: sbase + 4 * op.st[name]
         dout_p, dout_ld = gp(out), gld(out)
         peer_sync = self.dist.sync if (world > 1 and self.dist is not None) else None
+        if id(op) in run.bwd_stats_done:
+            # the dgrad that completed this unit's output gradient already reduced (and exchanged) the sums: coef, dgamma
+            # and dbeta are final - BatchNorm+ReLU backward is one apply pass
+            check(L.vtb_bn_bwd_apply(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
+                                     f("shift"), f("mean"), f("invstd"), int(op.relu), f("coef"), dybase, cout, st),
+                  "vtb_bn_bwd_apply")
+            self._conv_backward_gemms(op, abase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st)
+            return
         if g.training and (world == 1 or peer_sync is not None):
             # reduce -> finalize (-> SyncBN exchange over NVLink) -> apply in one cooperative launch
             check(L.vtb_bn_bwd_fused(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
@@ -1135,10 +1210,41 @@ class Runner:
                                                                  wsbase, pgrads[op.pidx].data_ptr(), op.cin_real, 0, s_),
                                                 "vtb_conv_wgrad"), st)
         if not (x.is_input and not run.x_requires_grad):
-            check(L.vtb_conv_dgrad(C.byref(geom), dybase, cout, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
-                  "vtb_conv_dgrad")
+            self._dgrad(op, geom, dybase, cout, wd, abase, gp, gld, is_init, pgrads, run, st)
             mark(x)
         self._residual_grad(op, gp, gld, is_init, mark, st)
+
+    def _dgrad(self, op: ConvOp, geom, dybase: int, lddy: int, wd, abase: int, gp, gld, is_init, pgrads, run, st) -> None:
+        """dgrad of `op` (or of a side-by-side pair, `geom` = the pair geometry) into its input; when the plan marked this
+        write as the last contribution to the producers' output gradient it also reduces their BatchNorm-backward sums."""
+        L = self.L
+        x = op.x
+        world = self.dist.world if (self.dist is not None and self.dist.sync_bn) else 1
+        peer_sync = self.dist.sync if (world > 1 and self.dist is not None) else None
+        if op.dgrad_bn is None or not (world == 1 or peer_sync is not None):
+            check(L.vtb_conv_dgrad(C.byref(geom), dybase, lddy, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
+                  "vtb_conv_dgrad")
+            return
+        prods, split = op.dgrad_bn
+        sbase = (run.stat.data_ptr() + 255) // 256 * 256
+        bn = VtbDgradBn()
+        bn.split = split
+        for l, q in enumerate(prods):
+            fq = lambda name, q=q: sbase + 4 * q.st[name]
+            lay = bn.layer[l]
+            lay.y, lay.ldy = abase + q.y.byte_offset(), q.y.ld
+            lay.scale, lay.shift, lay.mean, lay.invstd = fq("scale"), fq("shift"), fq("mean"), fq("invstd")
+            lay.relu = int(q.relu)
+            lay.dgamma, lay.dbeta = pgrads[q.pidx + 1].data_ptr(), pgrads[q.pidx + 2].data_ptr()
+            lay.coef = fq("coef")
+        bn.count = float(x.pixels) * world
+        bn.partial = sbase + 4 * op.st["partial_d"]
+        bn.tickets = self.tickets.data_ptr()
+        bn.sync = C.addressof(peer_sync) if peer_sync is not None else None
+        check(L.vtb_conv_dgrad_bn(C.byref(geom), dybase, lddy, wd.data_ptr(), gp(x), gld(x), int(is_init(x)),
+                                  C.byref(bn), st), "vtb_conv_dgrad_bn")
+        for q in prods:
+            run.bwd_stats_done.add(id(q))
 
 
 def _stat_view_f32(self, off_floats: int, n: int, sbase: int) -> torch.Tensor:
