@@ -307,3 +307,107 @@ def test_unit_without_activation_batch_one_and_odd_inputs(mode):   # 1e-1 on dW 
         for k, v in ref_mod.state_dict().items():
             if "running" in k:
                 assert rel_err(gpu.state_dict()[k].cpu(), v) < (2e-3 if mode == "bf16" else 1e-5), k
+
+
+def _cpu_twin_step(m_cpu, x, cot):
+    xc = x.clone().requires_grad_(True)
+    out = m_cpu(xc)
+    (out * cot).sum().backward()
+    return out.detach(), xc.grad, {k: p.grad for k, p in m_cpu.named_parameters()}
+
+
+def _tols(prec):
+    # fp32 parity kernels: tight; bf16: forward budget, gradients only sanity (tiny deep cases amplify ReLU-mask flips,
+    # SURVEY.md Appendix B - the plan logic is identical in both precisions)
+    return (1e-4, 2e-3, 1e-5) if prec == "fp32" else (BF16_TOL, 6e-1, 2e-2)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_mixed_batchnorm_modes_follow_each_layer(prec):
+    """model.train() followed by bn.eval() on some layers (frozen-BN fine-tuning).  The reference decides per
+    BatchNorm2d (components.py:36): frozen layers normalise with running statistics and keep them; the others use and
+    update batch statistics.  Compared with the module's own torch composition on the CPU (fp32)."""
+    import copy
+
+    from vision_toolbox_b200.backbones.darknet import CSPDarknetStage
+
+    torch.manual_seed(5)
+    m = CSPDarknetStage(2, 16, 32)
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.uniform_(0.5, 1.5); mod.bias.uniform_(-0.2, 0.2)
+                mod.running_mean.uniform_(-0.2, 0.2); mod.running_var.uniform_(0.5, 1.5)
+    m.train()
+    m.conv1.norm.eval()
+    m.blocks[0].conv2.eval()
+    ref = copy.deepcopy(m)
+    x = torch.rand(4, 16, 24, 24)
+    cot = torch.randn(4, 32, 12, 12)
+    o_ref, dx_ref, dp_ref = _cpu_twin_step(ref, x, cot)
+    import vision_toolbox_b200 as vtb
+
+    tol_f, tol_g, tol_s = _tols(prec)
+    mg = m.cuda()
+    xg = x.cuda().requires_grad_(True)
+    with vtb.precision(prec):
+        out = mg(xg)
+        (out.float() * cot.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(out.float(), o_ref) < tol_f
+    sd, sd_ref = mg.state_dict(), ref.state_dict()
+    for k in sd_ref:
+        if "running" in k or "num_batches" in k:
+            frozen = k.startswith("conv1.norm") or k.startswith("blocks.0.conv2.norm")
+            if frozen:
+                assert torch.equal(sd[k].cpu(), sd_ref[k]), k      # untouched, exactly
+            elif "num_batches" in k:
+                assert int(sd[k]) == int(sd_ref[k]) == 1, k
+            else:
+                assert rel_err(sd[k].float(), sd_ref[k]) < tol_s, k
+    assert rel_err(xg.grad, dx_ref) < tol_g
+    for k, p in mg.named_parameters():
+        assert torch.isfinite(p.grad).all() and rel_err(p.grad, dp_ref[k]) < tol_g, (k, rel_err(p.grad, dp_ref[k]))
+    # toggling the layer back builds a new plan: batch statistics again
+    before = sd["conv1.norm.running_mean"].clone()
+    mg.conv1.norm.train()
+    with torch.no_grad(), vtb.precision(prec):
+        mg(x.cuda())
+    assert not torch.equal(mg.state_dict()["conv1.norm.running_mean"], before)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("ese", [True, False])
+def test_standalone_osa_block_and_stage(ese, prec):
+    """OSABlock(x) and vovnet.stages[i](x) called on their own (reference vovnet.py:50-63, 93-98): the block
+    input is the plan's input, so it is copied into slice 0 of the concat buffer instead of being re-homed."""
+    import copy
+
+    from vision_toolbox_b200.backbones import VoVNet
+    from vision_toolbox_b200.backbones.vovnet import OSABlock
+
+    torch.manual_seed(6)
+    blk = OSABlock(32, 16, 3, 32, ese=ese).train()          # in == out: identity add on the copied input
+    net = VoVNet(32, [(1, 16, 2, 32), (2, 16, 3, 48)], ese=ese).train()
+    for m, x, cshape in ((blk, torch.rand(3, 32, 10, 10), (3, 32, 10, 10)),
+                         (net.stages[1], torch.rand(3, 32, 12, 12), (3, 48, 6, 6))):
+        import vision_toolbox_b200 as vtb
+
+        tol_f, tol_g, _ = _tols(prec)
+        ref = copy.deepcopy(m)
+        cot = torch.randn(*cshape)
+        o_ref, dx_ref, dp_ref = _cpu_twin_step(ref, x, cot)
+        mg = m.cuda()
+        xg = x.cuda().requires_grad_(True)
+        with vtb.precision(prec):
+            out = mg(xg)
+            assert tuple(out.shape) == cshape
+            (out.float() * cot.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        assert rel_err(out.float(), o_ref) < tol_f
+        assert rel_err(xg.grad, dx_ref) < tol_g
+        for k, p in mg.named_parameters():
+            assert rel_err(p.grad, dp_ref[k]) < tol_g, (k, rel_err(p.grad, dp_ref[k]))
+        with torch.no_grad(), vtb.precision(prec):
+            e = mg.eval()(x.cuda())
+            assert rel_err(e.float(), ref.eval()(x)) < tol_f

@@ -135,3 +135,51 @@ def test_channel_mismatch_raises_like_the_reference():
     g = engine.Graph(True, True)
     with pytest.raises(RuntimeError, match="expected input to have 32 channels, but got 16"):
         unit._emit(g, g.new_tensor(2, 8, 8, 16))
+
+
+def test_half_precision_models_are_rejected_not_corrupted():
+    """BatchNorm / eSE tensors reach the kernels as raw fp32 pointers - a cast model must raise at plan build."""
+    from vision_toolbox_b200 import engine
+    from vision_toolbox_b200.backbones import VoVNet
+    from vision_toolbox_b200.components import ConvNormAct
+
+    for cast in ("half", "bfloat16"):
+        m = getattr(ConvNormAct(16, 32), cast)()
+        g = engine.Graph(True, False)
+        with pytest.raises(TypeError, match="float32"):
+            m._emit(g, g.input_image(2, 16, 8, 8))
+    v = VoVNet(32, [(1, 16, 2, 32)], ese=True)
+    v.stages[0].module_0.ese.half()
+    g = engine.Graph(False, False)
+    with pytest.raises(TypeError, match="float32"):
+        v._emit(g, g.input_image(2, 3, 32, 32))
+
+
+def test_per_layer_batchnorm_mode_is_part_of_the_plan():
+    """model.train() followed by bn.eval() (frozen statistics) must use running statistics for THAT layer and
+    must not reuse the plan of the all-training model."""
+    from vision_toolbox_b200 import engine
+    from vision_toolbox_b200.backbones.darknet import CSPDarknetStage
+
+    m = CSPDarknetStage(1, 16, 32).train()
+    sig_train = engine._bn_signature(m)
+    m.conv1.norm.eval()
+    m.blocks[0].conv2.eval()
+    sig_mixed = engine._bn_signature(m)
+    assert sig_train != sig_mixed and sum(f for f, _ in sig_train) == len(sig_train)
+    assert sum(f for f, _ in sig_mixed) == len(sig_train) - 2
+    g = engine.Graph(True, True, pair_ok=True)
+    m._emit(g, g.input_image(2, 16, 16, 16))
+    flags = {id(op.mod): op.batch_stats for op in g.ops if op.kind == "conv"}
+    assert flags[id(m.conv1)] is False and flags[id(m.blocks[0].conv2)] is False and flags[id(m.conv2)] is True
+    # conv1 | conv2 disagree on the statistics they use: they must not be fused into one side-by-side convolution
+    assert all(op.pair is None for op in g.ops if op.kind == "conv")
+    bn_none = CSPDarknetStage(1, 16, 32).eval()
+    bn_none.conv.norm.running_mean = None
+    bn_none.conv.norm.running_var = None
+    assert engine._bn_signature(bn_none)[0][0] is True       # eval without running statistics -> batch statistics
+    mom = CSPDarknetStage(1, 16, 32).train()
+    mom.conv.norm.momentum = None
+    with pytest.raises(NotImplementedError, match="momentum"):
+        g = engine.Graph(True, False)
+        mom._emit(g, g.input_image(2, 16, 16, 16))

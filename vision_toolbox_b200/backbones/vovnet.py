@@ -71,9 +71,15 @@ class OSABlock(_NativeMixin, nn.Module):
         in_c = self.convs[0].conv.in_channels
         mid = self.convs[0].conv.out_channels
         n_layers = len(self.convs)
+        have = g.input_c if (x.is_input and x is g.input) else x.c
+        if have != in_c:
+            raise RuntimeError(f"Given groups=1, weight of size {list(self.convs[0].conv.weight.shape)}, expected input "
+                               f"to have {in_c} channels, but got {have} channels instead")
         cat = g.new_buffer(x.n, x.h, x.w, in_c + mid * n_layers)
         if not g.rehome(x, cat, 0):
-            raise NotImplementedError("OSABlock input must be produced inside the same plan (stem / max-pool / OSA)")
+            # the block is called on its own (reference vovnet.py:50: OSABlock.forward(x)): x is the plan's input and
+            # cannot move - copy it into slice 0 (its gradient flows back through the copy)
+            x = g.copy_into(x, cat, 0)
         cur = x
         for i, conv in enumerate(self.convs):
             cur = conv._emit(g, cur, out=g.slice(cat, in_c + i * mid, mid))
@@ -91,8 +97,11 @@ class VoVNetStageConfig(NamedTuple):
     out_channels: int
 
 
-class _Stage(nn.Sequential):
+class _Stage(_NativeMixin, nn.Sequential):
     """max_pool -> module_0 -> module_1 ... (child names fixed by reference vovnet.py:93-98)."""
+
+    def _forward_cpu(self, x: Tensor) -> Tensor:
+        return nn.Sequential.forward(self, x)
 
     def _emit(self, g, x):
         for name, child in self.named_children():

@@ -77,6 +77,31 @@ def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+def _check_norm_tensors(mod) -> None:
+    """The kernels read and write BatchNorm parameters / statistics as fp32 arrays through raw pointers: anything else
+    (model.half(), model.bfloat16(), a non-contiguous view) must fail loudly instead of corrupting memory."""
+    norm = mod.norm
+    for name in ("weight", "bias", "running_mean", "running_var"):
+        t = getattr(norm, name, None)
+        if t is None:
+            if name in ("weight", "bias"):
+                raise NotImplementedError("BatchNorm2d(affine=False) has no sm_100a kernel here")
+            continue
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError(f"BatchNorm2d.{name} must be a contiguous float32 tensor for the native path (got {t.dtype}); "
+                            "keep normalisation parameters and buffers in fp32 (model.half()/bfloat16() are not supported)")
+
+
+def _bn_signature(module: nn.Module) -> tuple:
+    """Per-BatchNorm (batch statistics?, parameter dtype) flags of a module tree: part of the plan key, so toggling
+    sub-module modes (bn.eval(), stem.eval()) or casting the model builds a new plan instead of reusing a stale one."""
+    sig = []
+    for m in module.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            sig.append((bool(m.training or m.running_mean is None), m.weight.dtype if m.weight is not None else None))
+    return tuple(sig)
+
+
 # ----------------------------------------------------------------------------------------------------
 # symbolic tensors
 # ----------------------------------------------------------------------------------------------------
@@ -140,6 +165,9 @@ class ConvOp:
     pair_geom: Any = None   # VtbConv with cout = both units (first op only)
     # gathered-operand stem: (taps, image channels) when this op is the image's first convolution run as a 1x1 GEMM
     col: Any = None
+    # BatchNorm2d decides per LAYER whether it normalises with batch statistics (torch: `self.training or running stats
+    # are None`) - the frozen-BN fine-tuning pattern is model.train() followed by bn.eval() on some layers
+    batch_stats: bool = True
     # BatchNorm-backward statistics carried by this op's dgrad (Graph._plan_dgrad_bn): ([producer ConvOp, ...], split) when
     # the dgrad into x is the LAST contribution to the gradient of the tensor(s) those producers wrote
     dgrad_bn: Any = None
@@ -152,6 +180,14 @@ class PoolOp:
     out: TView
     idx: Optional[TView] = None   # saved argmax positions (uint8 per element), only when gradients are needed
     kind: str = "pool"
+
+
+@dataclass
+class CopyOp:
+    """out = x: places a tensor the plan does not own (the plan input) into a channel slice of a concat buffer."""
+    x: TView
+    out: TView
+    kind: str = "copy"
 
 
 @dataclass
@@ -226,6 +262,17 @@ class Graph:
         t.buf, t.coff = buf, coff
         return True
 
+    def copy_into(self, x: TView, buf: Buffer, coff: int) -> TView:
+        """`x` as channel slice [coff, coff + c) of `buf` when it cannot be re-homed (it is the plan's input): one copy
+        launch forward, one gradient add backward (reference vovnet.py:51: ``outputs = [x]`` of a standalone OSABlock)."""
+        c = self.input_c if (x.is_input and x is self.input) else x.c
+        if c != x.c:
+            raise NotImplementedError(f"a block input with {c} channels cannot be placed in a concat buffer (multiple of 16)")
+        out = self.slice(buf, coff, c)
+        x.consumers.append(len(self.ops))
+        self.ops.append(CopyOp(x, out))
+        return out
+
     def _stat(self, op, name: str, floats: int) -> None:
         self.stat_floats = _round_up(self.stat_floats, 64)
         op.st[name] = self.stat_floats
@@ -281,6 +328,11 @@ class Graph:
             y = None if self.fused_eval else self.new_tensor(x.n, ho, wo, cout, "raw")
         op = ConvOp(mod, x, y, out, residual, mod.act_is_relu(), geom, cin_real)
         op.col = col
+        op.batch_stats = bool(norm.training or norm.running_mean is None)
+        if op.batch_stats and norm.momentum is None and norm.running_mean is not None:
+            # cumulative moving average (factor 1 / num_batches_tracked): the factor lives on the device; not built
+            raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative moving average) has no sm_100a kernel here")
+        _check_norm_tensors(mod)
         idx = len(self.ops)
         x.consumers.append(idx)
         if residual is not None:
@@ -329,8 +381,9 @@ class Graph:
         fan-in, one wgrad - `x` is read once instead of twice in each of the three.  The normalise / BatchNorm-backward
         passes stay per unit (their outputs live in different buffers).  Elsewhere: two ordinary units."""
         ca, cb, na, nb = mod_a.conv, mod_b.conv, mod_a.norm, mod_b.norm
+        bs_a, bs_b = (bool(n_.training or n_.running_mean is None) for n_ in (na, nb))
         compatible = (
-            self.pair_ok and mod_a.native_supported() and mod_b.native_supported()
+            self.pair_ok and bs_a and bs_b and mod_a.native_supported() and mod_b.native_supported()
             and ca.kernel_size == cb.kernel_size and ca.stride == cb.stride and ca.padding == cb.padding
             and ca.in_channels == cb.in_channels and na.eps == nb.eps and na.momentum == nb.momentum
             and na.track_running_stats == nb.track_running_stats and (na.running_mean is None) == (nb.running_mean is None)
@@ -375,6 +428,10 @@ class Graph:
     def ese(self, mod, x: TView, residual: Optional[TView] = None, out: Optional[TView] = None) -> TView:
         if out is None:
             out = self.new_tensor(x.n, x.h, x.w, x.c)
+        for t in (mod.linear.weight, mod.linear.bias):
+            if t is None or t.dtype != torch.float32 or not t.is_contiguous():
+                raise TypeError("ESEBlock.linear weight and bias must be contiguous float32 tensors for the native path "
+                                "(model.half()/bfloat16() are not supported)")
         op = EseOp(mod, x, out, residual)
         idx = len(self.ops)
         x.consumers.append(idx)
@@ -444,7 +501,7 @@ class Graph:
                 t = getattr(op, role, None)
                 if t is not None:
                     readers.setdefault(id(t.buf), []).append((i, t.coff, t.coff + t.c, role))
-            if op.kind == "conv" and op.y is not None:
+            if op.kind == "conv" and op.y is not None and op.batch_stats:
                 producers.setdefault(id(op.out.buf), []).append(op)
         for i, op in enumerate(self.ops):
             if op.kind != "conv" or op.pair_of is not None or op.col is not None:
@@ -711,6 +768,10 @@ class Runner:
                     self._conv_forward_pair(op, abase, sbase, run, st, world)
                 elif op.pair_of is None:    # the second unit of a pair ran together with the first
                     self._conv_forward(op, abase, sbase, run, st, world)
+            elif op.kind == "copy":
+                xx, oo = op.x, op.out
+                check(self.fn_grad_add(abase + oo.byte_offset(), oo.ld, abase + xx.byte_offset(), xx.ld, xx.pixels, xx.c, 0,
+                                       st), "vtb_grad_add(copy)")
             elif op.kind == "pool":
                 xx, oo = op.x, op.out
                 check(self.fn_pool_fwd(abase + xx.byte_offset(), xx.ld, xx.n, xx.h, xx.w, xx.c,
@@ -746,7 +807,7 @@ class Runner:
                                    res_ld, st), "vtb_conv_fprop(eval)")
             return
         y = op.y
-        use_batch_stats = g.training
+        use_batch_stats = op.batch_stats
         if use_batch_stats:
             mom = norm.momentum if norm.momentum is not None else 0.1
             track = norm.track_running_stats and norm.running_mean is not None
@@ -865,7 +926,7 @@ class Runner:
         w = self._master_weight(op)
         check(L.vtb_f32_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, w.data_ptr(), op.cin_real,
                                    abase + y.byte_offset(), y.ld, st), "vtb_f32_conv_fprop")
-        if g.training:
+        if op.batch_stats:
             mom = norm.momentum if norm.momentum is not None else 0.1
             track = norm.track_running_stats and norm.running_mean is not None
             rm = norm.running_mean.data_ptr() if track else 0
@@ -906,7 +967,7 @@ class Runner:
         dgamma, dbeta = pgrads[op.pidx + 1].data_ptr(), pgrads[op.pidx + 2].data_ptr()
         check(L.vtb_f32_bn_bwd_reduce(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, *bn,
                                       f("partial_b"), f("lsums_b"), st), "vtb_f32_bn_bwd_reduce")
-        if g.training and world > 1:
+        if op.batch_stats and world > 1:
             sums = run.stat_view_f64(op.st["sums_b"], cout * 2, sbase)
             sums.copy_(run.stat_view_f64(op.st["lsums_b"], cout * 2, sbase))
             self.dist.all_reduce_(sums)
@@ -915,7 +976,7 @@ class Runner:
         else:
             check(L.vtb_bn_bwd_finalize(0, 0, f("lsums_b"), 0, count, cout, dgamma, dbeta, 0, f("coef"), 0, st),
                   "vtb_bn_bwd_finalize")
-            if not g.training:
+            if not op.batch_stats:
                 # frozen statistics: mean/var are constants, so dy = gamma * invstd * dz
                 run.stat_view_f32(op.st["coef"], cout * 2, sbase).zero_()
         check(L.vtb_f32_bn_bwd_apply(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, *bn, f("coef"),
@@ -1099,6 +1160,12 @@ class Runner:
                 if ready_cb is not None:
                     with self._grad_stream_ctx():   # the all-reduce must also wait for the side-stream wgrad
                         ready_cb(g.params[op.pidx : op.pidx + 3])
+            elif op.kind == "copy":
+                xx, oo = op.x, op.out
+                if not (xx.is_input and not run.x_requires_grad):
+                    check(self.fn_grad_add(gp(xx), gld(xx), gp(oo), gld(oo), xx.pixels, xx.c, int(is_init(xx)), st),
+                          "vtb_grad_add(copy)")
+                    mark(xx)
             elif op.kind == "pool":
                 xx, oo = op.x, op.out
                 if not (xx.is_input and not run.x_requires_grad):
@@ -1155,7 +1222,7 @@ class Runner:
                   "vtb_bn_bwd_apply")
             self._conv_backward_gemms(op, abase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st)
             return
-        if g.training and (world == 1 or peer_sync is not None):
+        if op.batch_stats and (world == 1 or peer_sync is not None):
             # reduce -> finalize (-> SyncBN exchange over NVLink) -> apply in one cooperative launch
             check(L.vtb_bn_bwd_fused(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
                                      f("shift"), f("mean"), f("invstd"), int(op.relu), float(out.pixels) * world,
@@ -1169,7 +1236,7 @@ class Runner:
               "vtb_bn_bwd_reduce")
         dgamma, dbeta = pgrads[op.pidx + 1].data_ptr(), pgrads[op.pidx + 2].data_ptr()
         count = float(out.pixels)
-        if g.training and world > 1:
+        if op.batch_stats and world > 1:
             check(L.vtb_bn_bwd_finalize(f("partial_b"), op.rows_b, 0, 0, count, cout, 0, 0, 0, 0, f("lsums_b"), st),
                   "vtb_bn_bwd_finalize(local)")
             sums = run.stat_view_f64(op.st["sums_b"], cout * 2, sbase)
@@ -1180,7 +1247,7 @@ class Runner:
         else:
             check(L.vtb_bn_bwd_finalize(f("partial_b"), op.rows_b, 0, 0, count, cout, dgamma, dbeta, 0, f("coef"), 0,
                                         st), "vtb_bn_bwd_finalize")
-            if not g.training:
+            if not op.batch_stats:
                 # frozen statistics: mean/var are constants, so dy = scale * dz (no mean-subtraction terms)
                 run.stat_view_f32(op.st["coef"], cout * 2, sbase).zero_()
         check(L.vtb_bn_bwd_apply(dout_p, dout_ld, abase + y.byte_offset(), y.ld, out.pixels, cout, f("scale"),
@@ -1291,19 +1358,23 @@ def run_native(module: nn.Module, x: torch.Tensor) -> list[torch.Tensor]:
     )
     f32 = _resolve_f32()
     dcfg = module.__dict__.get("_vtb_dist")
+    # batch statistics are decided per BatchNorm layer (reference: nn.BatchNorm2d at components.py:36 looks at ITS OWN
+    # .training): the plan is "training" as soon as one layer uses them, and the per-layer flags are part of the key
+    bn_sig = _bn_signature(module)
+    training = any(flag for flag, _ in bn_sig) if bn_sig else module.training
     # sibling units run as one convolution when BatchNorm is finalised inside the conv kernel (VTB_PAIR=0: A/B switch)
-    pair_ok = (_os.environ.get("VTB_PAIR", "1") == "1" and module.training and not f32
+    pair_ok = (_os.environ.get("VTB_PAIR", "1") == "1" and training and not f32
                and (dcfg is None or not dcfg.sync_bn or dcfg.world == 1 or dcfg.sync is not None))
     # the image's first convolution as a 1x1 GEMM over a gathered operand, unless the image itself needs a gradient
     col_stem = (_os.environ.get("VTB_COL_STEM", "1") == "1" and not f32
                 and not (torch.is_grad_enabled() and x.requires_grad))
-    key = (tuple(x.shape), module.training, need_grad, x.device.index, f32, pair_ok,
-           dcfg is not None and dcfg.world > 1, col_stem)
+    key = (tuple(x.shape), bn_sig, need_grad, x.device.index, f32, pair_ok,
+           dcfg is not None and dcfg.world > 1, col_stem, _os.environ.get("VTB_DGRAD_BN", "0"))
     plans = module.__dict__.setdefault("_vtb_plans", {})
     runner = plans.get(key)
     if runner is None:
         with torch.cuda.device(x.device):
-            g = Graph(module.training, need_grad, f32, pair_ok, col_stem)
+            g = Graph(training, need_grad, f32, pair_ok, col_stem)
             t_in = g.input_image(*x.shape)
             outs = module._emit(g, t_in)
             if isinstance(outs, TView):
