@@ -73,8 +73,8 @@ int main() {
   printf("per-launch time (us) of a 50-kernel dependent chain in a CUDA graph; each CTA spins %d cycles\n", spin);
   printf("%-44s %8s %8s\n", "config", "no PDL", "PDL");
   struct Cfg { const char* name; int grid, threads; size_t smem; bool tmem; } cfgs[] = {
-      {"148 CTAs x 640 thr, 227 KB smem, TMEM 512", 148, 640, 232448, true},
-      {"148 CTAs x 640 thr, 227 KB smem, no TMEM", 148, 640, 232448, false},
+      {"148 CTAs x 640 thr, 227 KB smem, TMEM 512", 148, 640, 231424, true},
+      {"148 CTAs x 640 thr, 227 KB smem, no TMEM", 148, 640, 231424, false},
       {"148 CTAs x 640 thr, 100 KB smem, TMEM 512", 148, 640, 102400, true},
       {"148 CTAs x 640 thr, 100 KB smem, no TMEM", 148, 640, 102400, false},
       {"148 CTAs x 640 thr,   0 KB smem, no TMEM", 148, 640, 0, false},

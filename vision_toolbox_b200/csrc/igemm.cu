@@ -57,8 +57,8 @@ struct BwdCols {            // per-panel view of the producer layer: pointers al
   const float* shift;
   int relu;
 };
-// `early`: rows the caller loaded BEFORE staging the panel (their latency overlaps the TMEM -> shared-memory staging):
-// the producer's y rows in MODE 2, else the old destination rows when ADD (see panel_early_load).
+// `early` (MODE 2): the producer's y rows, loaded by the caller BEFORE staging the panel (panel_early_load) so that their
+// latency overlaps the TMEM -> shared-memory staging.
 template <int CH, bool ADD, int MODE>
 __device__ __forceinline__ void panel_early_load(int lane, const __nv_bfloat16* gcol, int ld, const int (&pix)[4],
                                                  const BwdCols& bw, uint4 (&early)[4]) {
@@ -67,11 +67,6 @@ __device__ __forceinline__ void panel_early_load(int lane, const __nv_bfloat16* 
 #pragma unroll
     for (int r = 0; r < CH; ++r)
       early[r] = (pix[r] >= 0) ? __ldg(reinterpret_cast<const uint4*>(bw.y + (size_t)pix[r] * bw.ldy + chunk * 8))
-                               : make_uint4(0u, 0u, 0u, 0u);
-  } else if (ADD) {
-#pragma unroll
-    for (int r = 0; r < CH; ++r)
-      early[r] = (pix[r] >= 0) ? *reinterpret_cast<const uint4*>(gcol + (size_t)pix[r] * ld + chunk * 8)
                                : make_uint4(0u, 0u, 0u, 0u);
   }
 }
@@ -96,14 +91,13 @@ __device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloa
       sh[4 * h] = b.x; sh[4 * h + 1] = b.y; sh[4 * h + 2] = b.z; sh[4 * h + 3] = b.w;
     }
   }
-  // MODE 2 with ADD still has to read the old destination rows here (the early registers hold y): two rows at a time,
-  // every read of a batch issued before its first use; the lines were prefetched into L2 at the start of the tile
-  constexpr bool LATE_OLD = ADD && MODE == 2;
-  constexpr int RB = LATE_OLD ? (ROWS > 2 ? 2 : ROWS) : ROWS;
+  // ADD: the old destination rows are read here, every read of a batch issued before its first use so that the round
+  // trips overlap (the drain is latency-bound per warp); MODE 2 + ADD: two rows at a time (register budget)
+  constexpr int RB = (ADD && MODE == 2) ? (ROWS > 2 ? 2 : ROWS) : ROWS;
 #pragma unroll
   for (int r0 = 0; r0 < ROWS; r0 += RB) {
-    uint4 old[LATE_OLD ? RB : 1];
-    if (LATE_OLD) {
+    uint4 old[ADD ? RB : 1];
+    if (ADD) {
 #pragma unroll
       for (int r = 0; r < RB; ++r)
         old[r] = (pix[r0 + r] >= 0) ? *reinterpret_cast<const uint4*>(gcol + (size_t)pix[r0 + r] * ld + chunk * 8)
@@ -119,7 +113,7 @@ __device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloa
       if (px >= 0) {
         uint4* gp = reinterpret_cast<uint4*>(gcol + (size_t)px * ld + chunk * 8);
         if (ADD) {
-          const uint4 ov = LATE_OLD ? old[r] : early[r0 + r];
+          const uint4 ov = old[r];
           const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(bf16lo(w[j]) + bf16lo(oo[j]), bf16hi(w[j]) + bf16hi(oo[j]));
@@ -260,6 +254,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   constexpr bool timed = TIMED;   // development counters (ConvIgemmParams::dbg); compiled out of the production kernel
   const long long t_start = timed ? clock64() : 0;
+  if (timed && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[blockIdx.x * 16 + 11] = gt;   // CTA start (ns)
+  }
 
 #define halves p.halves
 #define ksplit p.ksplit
@@ -476,7 +475,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         pix[r] = px;
       }
-      if (EPI == kEpiBwd || (EPI == kEpiPlain && add)) {
+      if (EPI == kEpiBwd) {
         // the rows this lane will read in its drains (producer y / old destination): pull their lines into L2 while the
         // tile's MMAs are still running, so the loads below are L2 hits
         if ((lane % drain_ch) == 0) {
@@ -523,8 +522,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           bw.shift = p.bwd_shift[L] + lc;
           bw.relu = p.bwd_relu[L];
           panel_early_pw<false, 2>(pw, lane, gcol, p.ldo, pix, bw, early);
-        } else if (EPI == kEpiPlain && add) {
-          panel_early_pw<true, 0>(pw, lane, gcol, p.ldo, pix, bw, early);
         }
         // the panel is drained in pieces of 16 columns to keep the register footprint small: this kernel runs with
         // ~no L1 (all of it is shared memory), so a spilled register costs an L2 round trip
@@ -792,6 +789,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (timed && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[blockIdx.x * 16 + 12] = gt;   // every role of the CTA is done (ns)
+    p.dbg[blockIdx.x * 16 + 13] = clock64() - t_start;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
