@@ -79,9 +79,35 @@ typedef struct VtbPackJob {
   int wf_ld;             /* row pitch of wf in elements: kk * cin, or more (rows of the gathered-operand stem are padded
                             to a multiple of 16 columns; the pad columns are never written - keep them zero) */
   long long first_block;
+  /* vtb_sgd_pack_weights only (ignored by vtb_pack_weights): gradient and momentum buffer in the master's OIHW layout */
+  const float* g;
+  float* m;
+  float weight_decay;
 } VtbPackJob;
 long long vtb_pack_job_blocks(int cout, int cin, int kk);
 int vtb_pack_weights(const VtbPackJob* jobs_device, int njobs, long long total_blocks, void* stream);
+
+/* ---- optimizer step: replaces torch.optim.SGD (reference classifier.py:141-169: momentum 0.9, weight decay on conv /
+ * linear weights only) ----
+ * vtb_sgd_pack_weights: the SGD update of every convolution weight (g += weight_decay * w; m = momentum * m + g;
+ *   w -= lr * m; zero-initialised m reproduces torch's first step) FUSED with the bf16 re-pack above: the operands of the
+ *   next forward are cut from the updated master in the same pass, so no separate vtb_pack_weights launch runs.
+ * vtb_sgd_step: the same update for plain tensors (BatchNorm weight / bias, the classifier head), one launch for a table
+ *   of jobs; first_block = running sum of vtb_sgd_job_blocks(n) over the preceding jobs.
+ * hyper_device: two floats in DEVICE memory {lr, momentum} (a learning-rate schedule updates them without re-capturing
+ *   a CUDA graph). */
+typedef struct VtbSgdJob {
+  float* w;
+  const float* g;
+  float* m;
+  long long n;
+  float weight_decay;
+  long long first_block;
+} VtbSgdJob;
+int vtb_sgd_pack_weights(const VtbPackJob* jobs_device, int njobs, long long total_blocks, const float* hyper_device,
+                         void* stream);
+long long vtb_sgd_job_blocks(long long n);
+int vtb_sgd_step(const VtbSgdJob* jobs_device, int njobs, long long total_blocks, const float* hyper_device, void* stream);
 
 /* ---- convolution: replaces aten::convolution (cuDNN) at components.py:26-35 ----
  * y[n,ho,wo,:] = conv(x)  (bf16, fp32 accumulate).

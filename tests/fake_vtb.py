@@ -22,7 +22,7 @@ BF16 = torch.bfloat16
 HOST_ONLY = {"vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows", "vtb_bn_bwd_fused_rows", "vtb_conv_out_hw",
              "vtb_conv_wgrad_workspace_bytes", "vtb_f32_conv_wgrad_workspace_bytes", "vtb_f32_bn_rows",
              "vtb_pack_job_blocks", "vtb_launch_count", "vtb_version", "vtb_num_sms", "vtb_bn_sync_buffer_bytes",
-             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info"}
+             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info", "vtb_sgd_job_blocks"}
 
 
 def _flat(ptr: int, n: int, dt: torch.dtype) -> torch.Tensor:
@@ -77,6 +77,25 @@ class InterpreterLib:
         dst = _view(out, kp, n * L, kp)
         dst.zero_()
         dst[:, : k * k * c] = cols.to(BF16)
+
+    def _vtb_sgd_pack_weights(self, jobs, njobs, blocks, hyper, st):
+        lr, mu = _flat(hyper, 2, torch.float32).tolist()
+        for j in (_lib.VtbPackJob * njobs).from_address(jobs):
+            n = j.cout * j.cin_real * j.kk
+            self._sgd(_flat(j.w, n, torch.float32), _flat(j.g, n, torch.float32), _flat(j.m, n, torch.float32),
+                      j.weight_decay, lr, mu)
+        self._vtb_pack_weights(jobs, njobs, blocks, st)
+
+    def _vtb_sgd_step(self, jobs, njobs, blocks, hyper, st):
+        lr, mu = _flat(hyper, 2, torch.float32).tolist()
+        for j in (_lib.VtbSgdJob * njobs).from_address(jobs):
+            self._sgd(_flat(j.w, j.n, torch.float32), _flat(j.g, j.n, torch.float32), _flat(j.m, j.n, torch.float32),
+                      j.weight_decay, lr, mu)
+
+    @staticmethod
+    def _sgd(w, g, m, wd, lr, mu):
+        m.mul_(mu).add_(g + wd * w)
+        w.sub_(lr * m)
 
     def _vtb_pack_weights(self, jobs, njobs, blocks, st):
         table = (_lib.VtbPackJob * njobs).from_address(jobs)

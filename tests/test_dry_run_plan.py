@@ -22,7 +22,7 @@ from vision_toolbox_b200.backbones.darknet import CSPDarknetStage
 HOST_ONLY = {"vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows", "vtb_bn_bwd_fused_rows", "vtb_conv_out_hw",
              "vtb_conv_wgrad_workspace_bytes", "vtb_f32_conv_wgrad_workspace_bytes", "vtb_f32_bn_rows",
              "vtb_pack_job_blocks", "vtb_launch_count", "vtb_version", "vtb_num_sms", "vtb_bn_sync_buffer_bytes",
-             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info"}
+             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info", "vtb_sgd_job_blocks"}
 
 
 class RecordingLib:

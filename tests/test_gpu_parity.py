@@ -411,3 +411,50 @@ def test_standalone_osa_block_and_stage(ese, prec):
         with torch.no_grad(), vtb.precision(prec):
             e = mg.eval()(x.cuda())
             assert rel_err(e.float(), ref.eval()(x)) < tol_f
+
+
+def test_native_sgd_matches_torch_sgd_over_five_steps():
+    """SURVEY.md 8f.1 / VERDICT r01 item 7: the fused multi-tensor SGD-momentum (per-group weight decay, reference
+    classifier.py:141-169) that also re-packs the bf16 conv operands, against torch.optim.SGD on the same gradients -
+    and the operands it leaves behind are exactly what a fresh re-pack of the new weights gives."""
+    import copy
+
+    from vision_toolbox_b200 import parallel
+    from vision_toolbox_b200.backbones import Darknet
+    from vision_toolbox_b200.backbones.darknet import CSPDarknetStage
+
+    torch.manual_seed(11)
+    m = Darknet(16, [(1, 32), (2, 64)], CSPDarknetStage).cuda().train()
+    head = torch.nn.Linear(64, 10).cuda()
+    m_ref, head_ref = copy.deepcopy(m), copy.deepcopy(head)
+    tr = parallel.Trainer(m, head, lr=0.1, momentum=0.9, weight_decay=1e-2)
+    assert tr.native_sgd and isinstance(tr.opt, parallel.NativeSGD)
+    decay, no_decay = parallel.split_decay_groups([m_ref, head_ref])
+    opt = torch.optim.SGD([{"params": decay, "weight_decay": 1e-2}, {"params": no_decay, "weight_decay": 0.0}],
+                          lr=0.1, momentum=0.9)
+    ref_params = list(m_ref.parameters()) + list(head_ref.parameters())
+    x = torch.rand(4, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 10, (4,), device="cuda")
+    for step in range(5):
+        tr.flat.zero_()
+        tr.forward_loss(x, y).backward()
+        # the reference optimizer sees the SAME gradients (this test is about the update rule, not the backward)
+        for p, q in zip(tr.params, ref_params):
+            q.grad = p.grad.detach().clone()
+        tr.opt.step()
+        opt.step()
+        for (k, p), q in zip(list(m.named_parameters()) + list(head.named_parameters()), ref_params):
+            assert rel_err(p, q) < 2e-6, (step, k, rel_err(p, q))
+    # the operands left behind by the fused step == a fresh re-pack of the final weights: same forward, bit for bit
+    with torch.no_grad():
+        a = m(x).clone()
+        for r in m.__dict__["_vtb_plans"].values():
+            r._packs_token = None      # force the re-pack launch
+        b = m(x)
+    assert torch.equal(a, b)
+    # a torch-side write to a weight (state_dict load, manual edit) invalidates the shortcut through Parameter._version
+    tr.flat.zero_(); tr.forward_loss(x, y).backward(); tr.opt.step()
+    with torch.no_grad():
+        m.stem.conv.weight.mul_(0.5)
+        c = m(x)
+    assert not torch.equal(b, c)

@@ -52,7 +52,14 @@ class VtbPackJob(C.Structure):
 
     _fields_ = [("w", C.c_void_p), ("wf", C.c_void_p), ("wd", C.c_void_p), ("cout", C.c_int), ("cin_real", C.c_int),
                 ("cin", C.c_int), ("kk", C.c_int), ("wd_ld", C.c_int), ("wd_co_off", C.c_int), ("wf_ld", C.c_int),
-                ("first_block", C.c_longlong)]
+                ("first_block", C.c_longlong), ("g", C.c_void_p), ("m", C.c_void_p), ("weight_decay", C.c_float)]
+
+
+class VtbSgdJob(C.Structure):
+    """struct VtbSgdJob of include/vtb.h (one plain tensor of the fused SGD-momentum step)."""
+
+    _fields_ = [("w", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("n", C.c_longlong),
+                ("weight_decay", C.c_float), ("first_block", C.c_longlong)]
 
 
 class VtbSyncBn(C.Structure):
@@ -81,6 +88,9 @@ SIGNATURES = {
     "vtb_pack_weight": (_i, [_cp, _p, _i, _p, _p, _p]),
     "vtb_pack_job_blocks": (_ll, [_i, _i, _i]),
     "vtb_pack_weights": (_i, [_p, _i, _ll, _p]),
+    "vtb_sgd_pack_weights": (_i, [_p, _i, _ll, _p, _p]),
+    "vtb_sgd_job_blocks": (_ll, [_ll]),
+    "vtb_sgd_step": (_i, [_p, _i, _ll, _p, _p]),
     "vtb_conv_fprop": (_i, [_cp, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _p]),
     "vtb_conv_fprop_bn": (_i, [_cp, _p, _i, _p, _p, _i, _p, C.POINTER(VtbBnTrain), _p]),
     "vtb_conv_dgrad": (_i, [_cp, _p, _i, _p, _p, _i, _i, _p]),

@@ -162,8 +162,10 @@ __host__ __device__ inline int pack_ci_tile(int kk) { return kk == 1 ? 256 : (kk
 constexpr int kPackSmemElems = 36 * kPackCoT * 9;   // >= kk * 32 * (CI_T + 1): kk 1 (CI_T 256), kk <= 9 (CI_T 32), kk <= 36 (CI_T 8)
 
 // one 32 x CI_T tile of one job; KK > 0: compile-time tap count (divisions become shifts / multiplies), 0: runtime
-template <int KK>
-__device__ __forceinline__ void pack_tile(const VtbPackJob& J, int b, __nv_bfloat16* tile) {
+// SGD: J.g != NULL -> the master weight is first UPDATED in place (torch.optim.SGD: g += wd * w; m = mu * m + g;
+// w -= lr * m; reference classifier.py:141-169) and the bf16 operands are cut from the new value in the same pass.
+template <int KK, bool SGD>
+__device__ __forceinline__ void pack_tile(const VtbPackJob& J, int b, __nv_bfloat16* tile, float lr, float mu) {
   const int kk = KK > 0 ? KK : J.kk;
   const int cit = pack_ci_tile(kk), pitch = cit + 1;
   const int n_ci_tiles = (J.cin + cit - 1) / cit;
@@ -174,7 +176,21 @@ __device__ __forceinline__ void pack_tile(const VtbPackJob& J, int b, __nv_bfloa
     const int co_l = e / per_co, r = e - co_l * per_co;
     const int ci_l = r / kk, t = r - ci_l * kk;
     const int co = co0 + co_l, ci = ci0 + ci_l;
-    const float v = (co < J.cout && ci < J.cin_real) ? __ldg(w + ((long long)co * J.cin_real + ci) * kk + t) : 0.f;
+    float v = 0.f;
+    if (co < J.cout && ci < J.cin_real) {
+      const long long idx = ((long long)co * J.cin_real + ci) * kk + t;
+      if (SGD && J.g != nullptr) {
+        float* wm = const_cast<float*>(w);
+        const float w0 = wm[idx];
+        const float g = fmaf(J.weight_decay, w0, J.g[idx]);
+        const float m = fmaf(mu, J.m[idx], g);
+        J.m[idx] = m;
+        v = fmaf(-lr, m, w0);
+        wm[idx] = v;
+      } else {
+        v = __ldg(w + idx);
+      }
+    }
     tile[(t * kPackCoT + co_l) * pitch + ci_l] = __float2bfloat16_rn(v);
   }
   __syncthreads();
@@ -199,12 +215,14 @@ __device__ __forceinline__ void pack_tile(const VtbPackJob& J, int b, __nv_bfloa
 }
 
 constexpr int kPackMaxJobs = 256;
+template <bool SGD>
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const VtbPackJob* __restrict__ jobs, int njobs,
-                                                                  long long total_tiles) {
+                                                                  long long total_tiles, const float* __restrict__ hyper) {
   __shared__ __nv_bfloat16 tile[kPackSmemElems];   // [tap][co_l][CI_T + 1]
   __shared__ long long first[kPackMaxJobs];        // first tile of every job (the search below stays in shared memory)
   pdl_wait();
   pdl_trigger();
+  const float lr = SGD ? hyper[0] : 0.f, mu = SGD ? hyper[1] : 0.f;
   for (int j = threadIdx.x; j < njobs; j += blockDim.x) first[j] = jobs[j].first_block;
   __syncthreads();
   for (long long tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
@@ -215,9 +233,42 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const VtbPack
     }
     const VtbPackJob J = jobs[lo];
     const int b = (int)(tix - first[lo]);
-    if (J.kk == 1) pack_tile<1>(J, b, tile);
-    else if (J.kk == 9) pack_tile<9>(J, b, tile);
-    else pack_tile<0>(J, b, tile);
+    if (J.kk == 1) pack_tile<1, SGD>(J, b, tile, lr, mu);
+    else if (J.kk == 9) pack_tile<9, SGD>(J, b, tile, lr, mu);
+    else pack_tile<0, SGD>(J, b, tile, lr, mu);
+  }
+}
+
+// SGD with momentum over a table of plain tensors (BatchNorm weights / biases, the classifier head): block b serves 1024
+// consecutive elements of the job with the largest first_block <= b.
+constexpr int kSgdBlockElems = 1024;
+__global__ void __launch_bounds__(256) sgd_step_kernel(const VtbSgdJob* __restrict__ jobs, int njobs, long long total_blocks,
+                                                      const float* __restrict__ hyper) {
+  __shared__ long long first[kPackMaxJobs];
+  pdl_wait();
+  pdl_trigger();
+  const float lr = hyper[0], mu = hyper[1];
+  for (int j = threadIdx.x; j < njobs; j += blockDim.x) first[j] = jobs[j].first_block;
+  __syncthreads();
+  for (long long bix = blockIdx.x; bix < total_blocks; bix += gridDim.x) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (first[mid] <= bix) lo = mid; else hi = mid - 1;
+    }
+    const VtbSgdJob J = jobs[lo];
+    const long long e0 = (bix - first[lo]) * kSgdBlockElems;
+#pragma unroll
+    for (int u = 0; u < kSgdBlockElems / 256; ++u) {
+      const long long i = e0 + u * 256 + threadIdx.x;
+      if (i < J.n) {
+        const float w0 = J.w[i];
+        const float g = fmaf(J.weight_decay, w0, J.g[i]);
+        const float m = fmaf(mu, J.m[i], g);
+        J.m[i] = m;
+        J.w[i] = fmaf(-lr, m, w0);
+      }
+    }
   }
 }
 
@@ -432,9 +483,32 @@ int vtb_pack_weights(const VtbPackJob* jobs_device, int njobs, long long total_b
     return fail(VTB_EINVAL, "vtb_pack_weights: bad arguments (at most 256 jobs per launch)");
   count_launch(1);
   const long long grid = std::min<long long>(total_blocks, (long long)std::max(1, num_sms()) * 8);
-  return check_cuda((int)launch_pdl(pack_weights_batched_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream,
-                                    jobs_device, njobs, total_blocks),
+  return check_cuda((int)launch_pdl(pack_weights_batched_kernel<false>, dim3((unsigned)grid), dim3(256), 0,
+                                    (cudaStream_t)stream, jobs_device, njobs, total_blocks, (const float*)nullptr),
                     "pack_weights_batched_kernel");
+}
+
+int vtb_sgd_pack_weights(const VtbPackJob* jobs_device, int njobs, long long total_blocks, const float* hyper_device,
+                         void* stream) {
+  if (!jobs_device || njobs <= 0 || njobs > kPackMaxJobs || total_blocks <= 0 || !hyper_device)
+    return fail(VTB_EINVAL, "vtb_sgd_pack_weights: bad arguments (at most 256 jobs per launch)");
+  count_launch(1);
+  const long long grid = std::min<long long>(total_blocks, (long long)std::max(1, num_sms()) * 8);
+  return check_cuda((int)launch_pdl(pack_weights_batched_kernel<true>, dim3((unsigned)grid), dim3(256), 0,
+                                    (cudaStream_t)stream, jobs_device, njobs, total_blocks, hyper_device),
+                    "pack_weights_batched_kernel(sgd)");
+}
+
+long long vtb_sgd_job_blocks(long long n) { return n <= 0 ? 0 : (n + kSgdBlockElems - 1) / kSgdBlockElems; }
+
+int vtb_sgd_step(const VtbSgdJob* jobs_device, int njobs, long long total_blocks, const float* hyper_device, void* stream) {
+  if (!jobs_device || njobs <= 0 || njobs > kPackMaxJobs || total_blocks <= 0 || !hyper_device)
+    return fail(VTB_EINVAL, "vtb_sgd_step: bad arguments (at most 256 jobs per launch)");
+  count_launch(1);
+  const long long grid = std::min<long long>(total_blocks, (long long)std::max(1, num_sms()) * 8);
+  return check_cuda((int)launch_pdl(sgd_step_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, jobs_device,
+                                    njobs, total_blocks, hyper_device),
+                    "sgd_step_kernel");
 }
 
 static int fprop_impl(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,

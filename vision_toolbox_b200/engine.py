@@ -636,6 +636,7 @@ class Runner:
         self._dy_slots = 3 if self._side is not None else 1
         self._dy_free: list = []
         self._pack_key, self._pack_jobs, self._pack_launches, self._pack_srcs = None, None, [], None
+        self._packs_token = None   # set by parallel.NativeSGD after it re-packed the operands itself
         self.tdtype = torch.float32 if self.f32 else torch.bfloat16
         self.fn_grad_add = L.vtb_f32_grad_add if self.f32 else L.vtb_grad_add
         self.fn_to_nhwc = L.vtb_f32_nchw_to_nhwc if self.f32 else L.vtb_nchw_to_nhwc
@@ -659,6 +660,12 @@ class Runner:
         convs = self._conv_ops
         if not convs:
             return
+        if self._packs_token is not None and self._packs_token == self.pack_token():
+            # the native optimizer (parallel.NativeSGD -> vtb_sgd_pack_weights) cut the operands from the weights it has
+            # just written, and nothing touched the masters since (torch bumps Parameter._version on every in-place
+            # write; the token is only ever set by that optimizer): the packs are current
+            return
+        self._packs_token = None
         srcs = []
         for op in convs:
             w = op.mod.conv.weight.detach()
@@ -667,6 +674,24 @@ class Runner:
             srcs.append(w)
         key = tuple(w.data_ptr() for w in srcs)
         if key != self._pack_key:
+            table, launches = self.pack_job_table(srcs)
+            self._pack_jobs = table
+            self._pack_launches, self._pack_key = launches, key
+        self._pack_srcs = srcs   # converted copies (non-fp32 masters) must outlive the launch
+        base, rec = self._pack_jobs.data_ptr(), C.sizeof(_lib.VtbPackJob)
+        for j0, n, blocks in self._pack_launches:
+            check(L.vtb_pack_weights(base + j0 * rec, n, blocks, st), "vtb_pack_weights")
+
+    def pack_token(self) -> tuple:
+        """(storage, version) of every convolution master weight of the plan."""
+        return tuple((op.mod.conv.weight.data_ptr(), op.mod.conv.weight._version) for op in self._conv_ops)
+
+    def pack_job_table(self, srcs, sgd=None):
+        """Device-resident VtbPackJob table of every convolution of the plan (+ the launches that walk it).  `sgd`:
+        callable(parameter) -> (gradient pointer, momentum pointer, weight decay) for vtb_sgd_pack_weights."""
+        L = self.L
+        convs = self._conv_ops
+        if True:
             jobs = (_lib.VtbPackJob * len(convs))()
             blk, launches = 0, []
             for j, (op, w) in enumerate(zip(convs, srcs)):
@@ -708,17 +733,14 @@ class Runner:
                     nb = int(L.vtb_pack_job_blocks(g.cout, g.cin, g.k * g.k))
                 if nb <= 0:
                     check(-1, "vtb_pack_job_blocks")
+                if sgd is not None:
+                    jobs[j].g, jobs[j].m, jobs[j].weight_decay = sgd(op.mod.conv.weight)
                 blk += nb
                 if (j + 1) % 256 == 0 or j == len(convs) - 1:   # a launch serves at most 256 jobs
                     launches.append((j // 256 * 256, j % 256 + 1, blk))
                     blk = 0
             table = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
-            self._pack_jobs = table.to(self.device)
-            self._pack_launches, self._pack_key = launches, key
-        self._pack_srcs = srcs   # converted copies (non-fp32 masters) must outlive the launch
-        base, rec = self._pack_jobs.data_ptr(), C.sizeof(_lib.VtbPackJob)
-        for j0, n, blocks in self._pack_launches:
-            check(L.vtb_pack_weights(base + j0 * rec, n, blocks, st), "vtb_pack_weights")
+            return table.to(self.device), launches
 
     @staticmethod
     def _packed(op: ConvOp):

@@ -93,6 +93,81 @@ def split_decay_groups(modules: list[nn.Module]):
     return decay, no_decay
 
 
+class NativeSGD:
+    """SGD with momentum (torch.optim.SGD semantics, dampening 0, no Nesterov; reference classifier.py:141-169) through the
+    C ABI: ONE launch updates every convolution weight of the backbone and cuts the bf16 operands of the next forward from
+    the new values (``vtb_sgd_pack_weights`` - no separate re-pack pass), ONE launch updates everything else
+    (``vtb_sgd_step``: BatchNorm weights / biases, eSE and head parameters).  Gradients are read from the parameters'
+    ``.grad`` (Trainer: views of its flat all-reduce buffer); lr / momentum live in device memory, so a schedule can change
+    them under a captured CUDA graph (``set_lr``)."""
+
+    def __init__(self, backbone: nn.Module, params: list, decay: list, lr: float, momentum: float, weight_decay: float):
+        self.backbone, self.params = backbone, params
+        self.decay_ids = {id(p) for p in decay}
+        self.weight_decay = weight_decay
+        dev = params[0].device
+        self.hyper = torch.tensor([lr, momentum], dtype=torch.float32, device=dev)
+        self.mom = {id(p): torch.zeros_like(p, memory_format=torch.contiguous_format) for p in params}
+        self._runner = None
+        self._tables = None
+
+    def set_lr(self, lr: float) -> None:
+        self.hyper[0] = lr
+
+    def _build(self, runner) -> None:
+        import ctypes as C
+
+        from . import _lib
+        from ._lib import check
+
+        L = _lib.lib()
+        for p in self.params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.grad is None or p.grad.dtype != torch.float32 \
+                    or not p.grad.is_contiguous():
+                raise TypeError("NativeSGD needs contiguous float32 parameters and gradients")
+        wd = lambda p: self.weight_decay if id(p) in self.decay_ids else 0.0
+        packed = {id(op.mod.conv.weight) for op in runner._conv_ops}
+        srcs = [op.mod.conv.weight.detach() for op in runner._conv_ops]
+        table, launches = runner.pack_job_table(
+            srcs, sgd=lambda p: (p.grad.data_ptr(), self.mom[id(p)].data_ptr(), wd(p)))
+        rest = [p for p in self.params if id(p) not in packed]
+        plain, blk, plain_launches = (_lib.VtbSgdJob * max(1, len(rest)))(), 0, []
+        for j, p in enumerate(rest):
+            plain[j] = _lib.VtbSgdJob(p.data_ptr(), p.grad.data_ptr(), self.mom[id(p)].data_ptr(), p.numel(), wd(p), blk)
+            blk += int(L.vtb_sgd_job_blocks(p.numel()))
+            if (j + 1) % 256 == 0 or j == len(rest) - 1:
+                plain_launches.append((j // 256 * 256, j % 256 + 1, blk))
+                blk = 0
+        ptab = torch.frombuffer(bytearray(bytes(plain)), dtype=torch.uint8).to(self.hyper.device)
+        self._runner = runner
+        self._tables = (table, launches, ptab, plain_launches if rest else [], C.sizeof(_lib.VtbPackJob), C.sizeof(_lib.VtbSgdJob))
+        self._key = tuple(p.data_ptr() for p in self.params) + tuple(p.grad.data_ptr() for p in self.params)
+
+    def step(self) -> None:
+        from . import _lib
+        from ._lib import check
+
+        L = _lib.lib()
+        plans = self.backbone.__dict__.get("_vtb_plans", {})
+        runner = next((r for r in plans.values() if r.g.need_grad and not r.g.f32), None)
+        if runner is None:
+            raise RuntimeError("NativeSGD.step() needs a native training plan (run forward + backward first)")
+        key = tuple(p.data_ptr() for p in self.params) + tuple(p.grad.data_ptr() for p in self.params)
+        if self._tables is None or self._runner is not runner or self._key != key:
+            self._build(runner)
+        table, launches, ptab, plain_launches, rec, prec = self._tables
+        dev = self.hyper.device
+        st = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
+        for j0, n, blocks in launches:
+            check(L.vtb_sgd_pack_weights(table.data_ptr() + j0 * rec, n, blocks, self.hyper.data_ptr(), st),
+                  "vtb_sgd_pack_weights")
+        for j0, n, blocks in plain_launches:
+            check(L.vtb_sgd_step(ptab.data_ptr() + j0 * prec, n, blocks, self.hyper.data_ptr(), st), "vtb_sgd_step")
+        # the operands of `runner` are current; other plans of the module (other shapes / modes) re-pack as usual
+        for r in plans.values():
+            r._packs_token = r.pack_token() if r is runner else None
+
+
 def bucket_ranges(sizes: list[int], bucket_elems: int) -> list[tuple[int, int]]:
     """Greedy contiguous buckets over a flat buffer: [(start, end)] in elements, each >= bucket_elems except the last."""
     out, start, acc = [], 0, 0
@@ -172,9 +247,16 @@ class Trainer:
         self._works = []
         self.comm_stream = torch.cuda.Stream(dev) if (dev.type == "cuda" and self.world > 1) else None
         decay, no_decay = split_decay_groups([backbone, head])
-        self.opt = torch.optim.SGD(
-            [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}],
-            lr=lr, momentum=momentum, fused=dev.type == "cuda")
+        # optimizer: the native fused SGD + operand re-pack on CUDA (VTB_NATIVE_SGD=0: torch's fused SGD + a re-pack launch
+        # at the start of every forward), torch SGD for CPU modules
+        self.native_sgd = (dev.type == "cuda" and os.environ.get("VTB_NATIVE_SGD", "1") == "1"
+                           and all(p.dtype == torch.float32 for p in self.params))
+        if self.native_sgd:
+            self.opt = NativeSGD(backbone, self.params, decay, lr, momentum, weight_decay)
+        else:
+            self.opt = torch.optim.SGD(
+                [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}],
+                lr=lr, momentum=momentum, fused=dev.type == "cuda")
 
     # -- gradient exchange
     def _launch_bucket(self, b: int) -> None:
