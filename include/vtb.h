@@ -290,6 +290,13 @@ int vtb_im2col_input(const float* x, int n, int c, int h, int w, int k, int stri
                      void* stream);
 int vtb_dw_from_col(const float* dw_col, int cout, int c, int kk, float* dw_oihw, int accumulate, void* stream);
 
+/* ---- input side of the training step: RandomMixup / RandomCutmix (reference extras.py:14-109, classifier.py:86-87) ----
+ * out[i] = mix(x[i], x[i-1]) on NCHW fp32 batches (the reference pairs image i with the batch rolled by one).
+ * params_device: six floats in DEVICE memory {mode, lambda, x1, y1, x2, y2} - mode 0: copy, 1: mixup
+ * (x*lambda + x_prev*(1-lambda), rounded like the reference's two in-place multiplies and one add), 2: cutmix (the box
+ * rows [y1,y2) x columns [x1,x2) comes from x_prev).  The decision and its parameters never visit the host. */
+int vtb_mix_images(const float* x, float* out, int n, int c, int h, int w, const float* params_device, void* stream);
+
 /* NCHW fp32 (the layout model(x) receives, tests/test_backbones.py:21) -> NHWC bf16, channels zero-padded
  * to cpad (the 3-channel image is stored with 16 channels for the tensor-core stem). */
 int vtb_nchw_to_nhwc(const float* x, int n, int c, int h, int w, void* out, int cpad, void* stream);

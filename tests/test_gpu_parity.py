@@ -458,3 +458,21 @@ def test_native_sgd_matches_torch_sgd_over_five_steps():
         m.stem.conv.weight.mul_(0.5)
         c = m(x)
     assert not torch.equal(b, c)
+
+
+def test_training_step_with_device_side_mixup_cutmix_is_capturable():
+    """the reference's RandomCutMixMixUp (classifier.py:66-67, 86-87) inside the captured training step -
+    sampled and applied on the device, so a CUDA-graph replay draws NEW mixes each step without touching the host."""
+    from vision_toolbox_b200 import extras, parallel
+    from vision_toolbox_b200.backbones import Darknet
+
+    torch.manual_seed(3)
+    m = Darknet(16, [(1, 32), (1, 64)]).cuda().train()
+    head = torch.nn.Linear(64, 10).cuda()
+    tr = parallel.Trainer(m, head, lr=0.05, mixup_cutmix=extras.RandomCutMixMixUp(10, 1.0, 0.2))
+    x = torch.rand(8, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 10, (8,), device="cuda")
+    tr.enable_cuda_graph(x, y, warmup=2)
+    losses = [float(tr.step(x, y)) for _ in range(6)]
+    assert all(l == l and l > 0 for l in losses)
+    assert len(set(round(l, 6) for l in losses)) > 3      # different mixes (and weights) every replay

@@ -152,7 +152,9 @@ int main(int argc, char** argv) {
       {
         unsigned long long lo = ~0ull, hi = 0; double cyc = 0;
         for (int b = 0; b < 1024; ++b) if (h[b * 16 + 7]) { lo = h[b * 16 + 11] < lo ? h[b * 16 + 11] : lo; hi = h[b * 16 + 12] > hi ? h[b * 16 + 12] : hi; cyc += (double)h[b * 16 + 13]; }
-        if (n) printf("       kernel span (first CTA start -> last CTA done): %.2f us | full CTA lifetime %.0f cycles avg\n", (hi - lo) * 1e-3, cyc / n);
+        double mma = 0, epi = 0;
+        for (int b = 0; b < 1024; ++b) if (h[b * 16 + 7]) { mma += (double)h[b * 16 + 15]; epi += (double)h[b * 16 + 14]; }
+        if (n) printf("       kernel span (first CTA start -> last CTA done): %.2f us | full CTA lifetime %.0f cycles avg | MMA issuer done at %.0f, slowest epilogue warp done at %.0f\n", (hi - lo) * 1e-3, cyc / n, mma / n, epi / n);
       }
       if (n) printf("       ctas %d | cycles/CTA %.0f | waits: A0 %.0f A1 %.0f B %.0f (on empty) | MMA on full %.0f, on tmem-empty %.0f | epi0 %.0f epi1 %.0f (on tmem-full) | epi warp4: tmem-ld %.0f cvt+sts %.0f drain %.0f\n",
                     n, s[7] / n, s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n, s[5] / n, s[6] / n, s[8] / n, s[9] / n, s[10] / n);

@@ -740,6 +740,33 @@ im2col_input_kernel(const float* __restrict__ x, int n, int c, int h, int w, int
   }
 }
 
+// RandomMixup / RandomCutmix of the reference trainer (extras.py:14-109) on the device, decision and parameters read from
+// DEVICE memory (no host synchronisation): prm = {mode, lambda, x1, y1, x2, y2}; image i is paired with image i-1 (the
+// reference rolls the batch by one).  mode 1: out = x*lambda + x_prev*(1-lambda) with the reference's rounding sequence
+// (two products, one sum - no fused multiply-add); mode 2: the box [y1,y2) x [x1,x2) is taken from x_prev; else: copy.
+__global__ void __launch_bounds__(256)
+mix_images_kernel(const float* __restrict__ x, float* __restrict__ out, int n, long long chw, int h, int w,
+                  const float* __restrict__ prm) {
+  pdl_wait();
+  pdl_trigger();
+  const int mode = (int)prm[0];
+  const float lam = prm[1], oml = 1.0f - lam;
+  const int x1 = (int)prm[2], y1 = (int)prm[3], x2 = (int)prm[4], y2 = (int)prm[5];
+  const long long total = (long long)n * chw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / chw, r = i - img * chw;
+    const long long j = (img == 0 ? (long long)(n - 1) : img - 1) * chw + r;
+    float v = x[i];
+    if (mode == 1) {
+      v = __fadd_rn(__fmul_rn(v, lam), __fmul_rn(x[j], oml));
+    } else if (mode == 2) {
+      const int col = (int)(r % w), row = (int)((r / w) % h);
+      if (col >= x1 && col < x2 && row >= y1 && row < y2) v = x[j];
+    }
+    out[i] = v;
+  }
+}
+
 // weight gradient of the gathered-operand convolution, [cout][k*k*c] in (tap, ci) column order -> OIHW
 __global__ void dw_from_col_kernel(const float* __restrict__ dw_col, int cout, int c, int kk, float* __restrict__ dw,
                                    int accumulate) {
@@ -984,6 +1011,16 @@ int vtb_im2col_input(const float* x, int n, int c, int h, int w, int k, int stri
                (__nv_bfloat16*)out, kp);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "im2col_input_kernel");
+}
+
+int vtb_mix_images(const float* x, float* out, int n, int c, int h, int w, const float* params_device, void* stream) {
+  if (!x || !out || x == out || n <= 0 || c <= 0 || h <= 0 || w <= 0 || !params_device)
+    return fail(VTB_EINVAL, "vtb_mix_images: bad arguments (out of place only)");
+  const long long chw = (long long)c * h * w;
+  launch_pdl(mix_images_kernel, dim3(ew_grid((long long)n * chw, 256)), dim3(256), 0, (cudaStream_t)stream, x, out, n, chw, h, w,
+             params_device);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "mix_images_kernel");
 }
 
 int vtb_dw_from_col(const float* dw_col, int cout, int c, int kk, float* dw_oihw, int accumulate, void* stream) {

@@ -416,6 +416,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (timed) {
         p.dbg[blockIdx.x * 16 + 3] = w_full;
         p.dbg[blockIdx.x * 16 + 4] = w_tempty;
+        p.dbg[blockIdx.x * 16 + 15] = clock64() - t_start;   // MMA issuer done (all MMAs issued)
       }
     }
   } else {
@@ -778,6 +779,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    if (timed && lane == 0) atomicMax(p.dbg + blockIdx.x * 16 + 14, (unsigned long long)(clock64() - t_start));   // slowest epilogue warp
     if (timed && quarter == 0 && lane == 0 && grp < 2) p.dbg[blockIdx.x * 16 + 5 + grp] = w_tfull;
     if (timed && warp == 4 && lane == 0) {
       p.dbg[blockIdx.x * 16 + 8] = t_ld;

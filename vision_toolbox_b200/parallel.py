@@ -192,9 +192,12 @@ class Trainer:
 
     def __init__(self, backbone: nn.Module, head: nn.Module, lr: float = 0.05, momentum: float = 0.9,
                  weight_decay: float = 2e-5, label_smoothing: float = 0.1, sync_bn: bool = True,
-                 process_group=None, bucket_mb: float = 25.0):
+                 process_group=None, bucket_mb: float = 25.0, mixup_cutmix: Optional[nn.Module] = None):
         self.backbone, self.head = backbone, head
         self.label_smoothing = label_smoothing
+        # classifier.py:66-67, 86-87: RandomCutMixMixUp on the batch before the forward (vision_toolbox_b200.extras: sampled
+        # and applied on the device, capturable); targets become probability vectors
+        self.mixup_cutmix = mixup_cutmix
         self.group = process_group
         self.world = 1
         self.params = [p for p in list(backbone.parameters()) + list(head.parameters()) if p.requires_grad]
@@ -297,8 +300,10 @@ class Trainer:
         self._launched = [False] * len(self.buckets)
 
     def forward_loss(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self.mixup_cutmix is not None:
+            x, y = self.mixup_cutmix(x, y)   # y: (N, classes) probabilities from here on
         f = self.backbone(x)  # (N, C, H, W) bf16 on CUDA
-        if self.native_head and f.is_cuda and f.dtype == torch.bfloat16 and f.shape[1] % 8 == 0:
+        if self.native_head and y.ndim == 1 and f.is_cuda and f.dtype == torch.bfloat16 and f.shape[1] % 8 == 0:
             # pooling + linear + label-smoothed CE in the native library (head gradients land in the flat buffer)
             return _HeadCEFn.apply(f, self.head.weight, self.head.bias, y, self.label_smoothing, True)
         pooled = f.float().mean(dim=(2, 3))  # AdaptiveAvgPool2d + Flatten (classifier.py:61-62)
