@@ -15,7 +15,7 @@ ref = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(ref)
 
 torch.manual_seed(0)
-x = torch.rand(4, 3, 20, 24)
+x = torch.rand(4, 3, 10, 12)
 y = torch.randint(0, 10, (4,))
 cases = []
 for name, args in (("RandomMixup", (10, 0.7, 0.4)), ("RandomCutmix", (10, 0.7, 1.0)), ("RandomCutMixMixUp", (10, 1.0, 0.2))):
