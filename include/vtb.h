@@ -290,6 +290,17 @@ int vtb_im2col_input(const float* x, int n, int c, int h, int w, int k, int stri
                      void* stream);
 int vtb_dw_from_col(const float* dw_col, int cout, int c, int kk, float* dw_oihw, int accumulate, void* stream);
 
+/* ---- feature-pyramid fuse: replaces nn.Upsample(scale_factor=2 | 0.5, mode="nearest") + the "sum" aggregate of the
+ * reference necks (necks.py:16-20, 66, 69-79) ----
+ * out[n,y,x,:] = (a ? a[n,y,x,:] : 0) + b[n, src(y), src(x), :];  up != 0: b is (hb, wb) = (h/2, w/2), src(i) = i >> 1
+ * (top-down FPN); up == 0: h = hb/2, w = wb/2, src(i) = 2i (bottom-up path of PAN).  a == NULL: the plain resize (the
+ * "concat" aggregate writes it into a channel slice).  vtb_resize2_add_bwd: gb (+)= the transposed resize of gout
+ * (the gradient of `a` is gout itself). */
+int vtb_resize2_add(const void* a, int lda, const void* b, int ldb, int n, int h, int w, int c, int hb, int wb, int up,
+                    void* out, int ldo, void* stream);
+int vtb_resize2_add_bwd(const void* gout, int ldg, int n, int h, int w, int c, void* gb, int ldgb, int hb, int wb, int up,
+                        int accumulate, void* stream);
+
 /* ---- input side of the training step: RandomMixup / RandomCutmix (reference extras.py:14-109, classifier.py:86-87) ----
  * out[i] = mix(x[i], x[i-1]) on NCHW fp32 batches (the reference pairs image i with the batch rolled by one).
  * params_device: six floats in DEVICE memory {mode, lambda, x1, y1, x2, y2} - mode 0: copy, 1: mixup

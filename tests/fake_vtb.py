@@ -290,6 +290,40 @@ class InterpreterLib:
         out = _flat(scale, c, torch.float32) * (dz - k[:, 0] - xhat * k[:, 1])
         _view(dy, lddy, pixels, c).copy_(out.to(BF16))
 
+    def _vtb_resize2_add(self, a, lda, b, ldb, n, h, w, c, hb, wb, up, out, ldo, st):
+        bb = _view(b, ldb, n * hb * wb, c).float().view(n, hb, wb, c)
+        r = bb.repeat_interleave(2, 1).repeat_interleave(2, 2) if up else bb[:, ::2, ::2][:, :h, :w]
+        r = r.reshape(n * h * w, c)
+        if a:
+            r = r + _view(a, lda, n * h * w, c).float()
+        _view(out, ldo, n * h * w, c).copy_(r.to(BF16))
+
+    def _vtb_resize2_add_bwd(self, gout, ldg, n, h, w, c, gb, ldgb, hb, wb, up, accumulate, st):
+        g = _view(gout, ldg, n * h * w, c).float().view(n, h, w, c)
+        if up:
+            new = g.view(n, hb, 2, wb, 2, c).sum(dim=(2, 4))
+        else:
+            new = torch.zeros(n, hb, wb, c)
+            new[:, : 2 * h : 2, : 2 * w : 2] = g
+        new = new.reshape(n * hb * wb, c)
+        dst = _view(gb, ldgb, n * hb * wb, c)
+        dst.copy_(((_r(new) + dst.float()) if accumulate else new).to(BF16))
+
+    def _vtb_mix_images(self, x, out, n, c, h, w, prm, st):
+        p = _flat(prm, 6, torch.float32)
+        xi = _flat(x, n * c * h * w, torch.float32).view(n, c, h, w)
+        prev = xi.roll(1, 0)
+        mode, lam = int(p[0]), p[1]
+        if mode == 1:
+            o = xi * lam + prev * (1.0 - lam)
+        elif mode == 2:
+            o = xi.clone()
+            x1, y1, x2, y2 = (int(v) for v in p[2:6])
+            o[:, :, y1:y2, x1:x2] = prev[:, :, y1:y2, x1:x2]
+        else:
+            o = xi.clone()
+        _flat(out, n * c * h * w, torch.float32).copy_(o.reshape(-1))
+
     def _vtb_grad_add(self, dst, ldd, src, lds, pixels, c, accumulate, st):
         d, s = _view(dst, ldd, pixels, c), _view(src, lds, pixels, c)
         d.copy_((d.float() + s.float()).to(BF16) if accumulate else s)

@@ -169,3 +169,34 @@ def test_all_reduce_syncbn_path_with_a_twin_rank(name, f32):
     for k, ref in g["buffers_after_step" if f32 else "buffers_after_bf16_step"].items():
         if "running_mean" in k:
             assert rel_err(sd[k], ref) < (1e-5 if f32 else 2e-3), k
+
+
+def test_bias_conv_unit_plan():
+    """The planner's bias unit (a bare nn.Conv2d with bias: the lateral convolutions of the reference necks, necks.py:60-65)
+    on the CPU interpreter: forward, input / weight / bias gradients against torch."""
+    from vision_toolbox_b200.necks import _BiasConvUnit
+
+    torch.manual_seed(0)
+    for k, s in ((1, 1), (3, 2)):
+        conv = torch.nn.Conv2d(32, 48, k, s, padding=k // 2)
+        unit = _BiasConvUnit(conv)
+        x = torch.rand(2, 32, 9, 10)
+        cot = torch.randn(2, 48, (9 + 2 * (k // 2) - k) // s + 1, (10 + 2 * (k // 2) - k) // s + 1)
+        graph = engine.Graph(True, True)
+        out = unit._emit(graph, graph.input_image(*x.shape))
+        graph.mark_output(out)
+        graph.finalize()
+        lib = InterpreterLib()
+        with mock.patch.object(engine._lib, "lib", return_value=lib):
+            runner = engine.Runner(graph, torch.device("cpu"))
+        runner._stream = lambda: 0
+        xx = x.clone().requires_grad_(True)
+        outs, run = runner.forward(xx)
+        gx, pg = runner.backward(run, [cot.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)])
+        xr = x.clone().requires_grad_(True)
+        ref = conv(xr)
+        (ref * cot).sum().backward()
+        assert rel_err(outs[0].float(), ref) < 1e-2
+        assert rel_err(gx, xr.grad) < 2e-2
+        assert rel_err(pg[0], conv.weight.grad) < 2e-2 and rel_err(pg[1], conv.bias.grad) < 2e-2
+        assert [n for n in lib.calls if "bn_act" in n or "fprop_bn" in n] == []      # one conv launch, no normalise pass

@@ -117,6 +117,8 @@ SIGNATURES = {
     "vtb_im2col_input": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "vtb_dw_from_col": (_i, [_p, _i, _i, _i, _p, _i, _p]),
     "vtb_mix_images": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "vtb_resize2_add": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "vtb_resize2_add_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
     "vtb_maxpool3s2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
     "vtb_maxpool3s2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p]),
     "vtb_ese_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p]),

@@ -740,6 +740,79 @@ im2col_input_kernel(const float* __restrict__ x, int n, int c, int h, int w, int
   }
 }
 
+// Feature-pyramid fuse (reference necks.py:69-79): out = [a +] resize(b) with nn.Upsample(scale_factor=2 | 0.5, "nearest"):
+//   up   (top-down):  b is (hb, wb) = (h/2, w/2), out[y][x] reads b[y >> 1][x >> 1]
+//   down (bottom-up): b is (hb, wb) with h = hb/2, w = wb/2 (floor), out[y][x] reads b[2y][2x]
+// a == nullptr: plain resize (the "concat" fuse writes it into a channel slice).  bf16 in / out, the add in fp32.
+template <bool UP, bool HAS_A>
+__global__ void __launch_bounds__(256)
+resize2_add_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b, int ldb, int n, int h,
+                   int w, int c8, int hb, int wb, __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = (long long)n * h * w * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c8);
+    long long pix = i / c8;
+    const int x = (int)(pix % w), y = (int)((pix / w) % h);
+    const long long img = pix / ((long long)w * h);
+    const int sy = UP ? (y >> 1) : (y << 1), sx = UP ? (x >> 1) : (x << 1);
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((img * hb + sy) * wb + sx) * ldb + v * 8)), f);
+    if (HAS_A) {
+      float g[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a + pix * lda + v * 8)), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += g[j];
+    }
+    *reinterpret_cast<uint4*>(out + pix * ldo + v * 8) = pack8(f);
+  }
+}
+
+// gradient of the resized operand: gb (+)= resize^T(gout).  up: every b pixel gathers its 2x2 block of gout (fp32 sum,
+// one rounding, as upsample_nearest2d_backward does); down: b pixels (2y, 2x) take gout[y][x], all others get zero.
+template <bool UP, bool ADD>
+__global__ void __launch_bounds__(256)
+resize2_add_bwd_kernel(const __nv_bfloat16* __restrict__ gout, int ldg, int n, int h, int w, int c8,
+                       __nv_bfloat16* __restrict__ gb, int ldgb, int hb, int wb) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = (long long)n * hb * wb * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c8);
+    long long pix = i / c8;
+    const int x = (int)(pix % wb), y = (int)((pix / wb) % hb);
+    const long long img = pix / ((long long)wb * hb);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (UP) {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int oy = 2 * y + dy, ox = 2 * x + dx;
+          if (oy < h && ox < w) {
+            float g[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(gout + ((img * h + oy) * w + ox) * ldg + v * 8)), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += g[j];
+          }
+        }
+    } else if ((y & 1) == 0 && (x & 1) == 0 && (y >> 1) < h && (x >> 1) < w) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gout + ((img * h + (y >> 1)) * w + (x >> 1)) * ldg + v * 8)), f);
+    }
+    __nv_bfloat16* dst = gb + pix * ldgb + v * 8;
+    if (ADD) {
+      float o[8];
+      unpack8(*reinterpret_cast<const uint4*>(dst), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = rbf(f[j]) + o[j];
+    }
+    *reinterpret_cast<uint4*>(dst) = pack8(f);
+  }
+}
+
 // RandomMixup / RandomCutmix of the reference trainer (extras.py:14-109) on the device, decision and parameters read from
 // DEVICE memory (no host synchronisation): prm = {mode, lambda, x1, y1, x2, y2}; image i is paired with image i-1 (the
 // reference rolls the batch by one).  mode 1: out = x*lambda + x_prev*(1-lambda) with the reference's rounding sequence
@@ -1011,6 +1084,45 @@ int vtb_im2col_input(const float* x, int n, int c, int h, int w, int k, int stri
                (__nv_bfloat16*)out, kp);
   count_launch(1);
   return check_cuda((int)cudaGetLastError(), "im2col_input_kernel");
+}
+
+static bool resize_ok(int h, int w, int hb, int wb, int up) {
+  return up ? (h == 2 * hb && w == 2 * wb) : (h == hb / 2 && w == wb / 2 && h > 0 && w > 0);
+}
+
+int vtb_resize2_add(const void* a, int lda, const void* b, int ldb, int n, int h, int w, int c, int hb, int wb, int up,
+                    void* out, int ldo, void* stream) {
+  if (n <= 0 || c <= 0 || c % 8 || !resize_ok(h, w, hb, wb, up) || !VIEW_OK(b, ldb, c) || !VIEW_OK(out, ldo, c) ||
+      (a && !VIEW_OK(a, lda, c)))
+    return fail(VTB_EINVAL, "vtb_resize2_add: bad arguments (nearest x2 needs h == 2*hb, x0.5 needs h == hb/2)");
+  const int c8 = c / 8;
+  const dim3 grid(ew_grid((long long)n * h * w * c8, 256));
+  const __nv_bfloat16 *aa = (const __nv_bfloat16*)a, *bb = (const __nv_bfloat16*)b;
+  __nv_bfloat16* oo = (__nv_bfloat16*)out;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (up && a) launch_pdl(resize2_add_kernel<true, true>, grid, dim3(256), 0, st, aa, lda, bb, ldb, n, h, w, c8, hb, wb, oo, ldo);
+  else if (up) launch_pdl(resize2_add_kernel<true, false>, grid, dim3(256), 0, st, aa, lda, bb, ldb, n, h, w, c8, hb, wb, oo, ldo);
+  else if (a) launch_pdl(resize2_add_kernel<false, true>, grid, dim3(256), 0, st, aa, lda, bb, ldb, n, h, w, c8, hb, wb, oo, ldo);
+  else launch_pdl(resize2_add_kernel<false, false>, grid, dim3(256), 0, st, aa, lda, bb, ldb, n, h, w, c8, hb, wb, oo, ldo);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "resize2_add_kernel");
+}
+
+int vtb_resize2_add_bwd(const void* gout, int ldg, int n, int h, int w, int c, void* gb, int ldgb, int hb, int wb, int up,
+                        int accumulate, void* stream) {
+  if (n <= 0 || c <= 0 || c % 8 || !resize_ok(h, w, hb, wb, up) || !VIEW_OK(gout, ldg, c) || !VIEW_OK(gb, ldgb, c))
+    return fail(VTB_EINVAL, "vtb_resize2_add_bwd: bad arguments");
+  const int c8 = c / 8;
+  const dim3 grid(ew_grid((long long)n * hb * wb * c8, 256));
+  const __nv_bfloat16* gg = (const __nv_bfloat16*)gout;
+  __nv_bfloat16* bb = (__nv_bfloat16*)gb;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (up && accumulate) launch_pdl(resize2_add_bwd_kernel<true, true>, grid, dim3(256), 0, st, gg, ldg, n, h, w, c8, bb, ldgb, hb, wb);
+  else if (up) launch_pdl(resize2_add_bwd_kernel<true, false>, grid, dim3(256), 0, st, gg, ldg, n, h, w, c8, bb, ldgb, hb, wb);
+  else if (accumulate) launch_pdl(resize2_add_bwd_kernel<false, true>, grid, dim3(256), 0, st, gg, ldg, n, h, w, c8, bb, ldgb, hb, wb);
+  else launch_pdl(resize2_add_bwd_kernel<false, false>, grid, dim3(256), 0, st, gg, ldg, n, h, w, c8, bb, ldgb, hb, wb);
+  count_launch(1);
+  return check_cuda((int)cudaGetLastError(), "resize2_add_bwd_kernel");
 }
 
 int vtb_mix_images(const float* x, float* out, int n, int c, int h, int w, const float* params_device, void* stream) {

@@ -168,6 +168,10 @@ class ConvOp:
     # BatchNorm2d decides per LAYER whether it normalises with batch statistics (torch: `self.training or running stats
     # are None`) - the frozen-BN fine-tuning pattern is model.train() followed by bn.eval() on some layers
     batch_stats: bool = True
+    # plain nn.Conv2d WITH bias and no normalisation (the lateral 1x1 convolutions of the reference necks, necks.py:60-65):
+    # the bias rides in the fused affine epilogue (scale = 1, shift = bias); parameters are (weight, bias)
+    bias: bool = False
+    nparams: int = 3
     # BatchNorm-backward statistics carried by this op's dgrad (Graph._plan_dgrad_bn): ([producer ConvOp, ...], split) when
     # the dgrad into x is the LAST contribution to the gradient of the tensor(s) those producers wrote
     dgrad_bn: Any = None
@@ -369,6 +373,48 @@ class Graph:
             self.ws_bytes = max(self.ws_bytes, int(wsq(C.byref(geom))))
             self.dy_bytes = max(self.dy_bytes, out.pixels * cout * self.esize)
         op.rows_f, op.rows_b = rows_f, rows_b
+        self.ops.append(op)
+        return out
+
+    def conv_bias(self, unit, x: TView, out: Optional[TView] = None) -> TView:
+        """A bare ``nn.Conv2d(..., bias=True)`` (reference necks.py:60-65 lateral convolutions): `unit.conv` is the module.
+        One launch forward (bias in the affine epilogue); backward = dgrad + wgrad straight from the output gradient and a
+        per-channel sum for the bias gradient."""
+        conv = unit.conv
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        cin_real, cout = conv.in_channels, conv.out_channels
+        ok = (conv.bias is not None and conv.groups == 1 and conv.dilation == (1, 1) and conv.kernel_size[0] == conv.kernel_size[1]
+              and conv.stride[0] == conv.stride[1] and s in (1, 2) and conv.padding[0] == conv.padding[1]
+              and conv.padding_mode == "zeros" and k * k <= 36 and not self.f32)
+        if not ok:
+            raise NotImplementedError("this nn.Conv2d configuration has no sm_100a kernel here (bf16 plans, groups=1, "
+                                      "dilation=1, square kernel, stride 1|2, with bias)")
+        have = self.input_c if (x.is_input and x is self.input) else x.c
+        if have != cin_real:
+            raise RuntimeError(f"Given groups=1, weight of size {list(conv.weight.shape)}, expected input to have "
+                               f"{cin_real} channels, but got {have} channels instead")
+        if cout % 16 or x.c % 16:
+            raise NotImplementedError(f"channel counts must be multiples of 16 (got {cin_real}->{cout})")
+        for t in (conv.weight, conv.bias):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise TypeError("nn.Conv2d weight and bias must be contiguous float32 tensors for the native path")
+        geom = VtbConv(x.n, x.h, x.w, x.c, cout, k, s, p)
+        ho, wo = (x.h + 2 * p - k) // s + 1, (x.w + 2 * p - k) // s + 1
+        if out is None:
+            out = self.new_tensor(x.n, ho, wo, cout)
+        op = ConvOp(unit, x, None, out, None, False, geom, cin_real)
+        op.bias, op.nparams, op.batch_stats = True, 2, False
+        x.consumers.append(len(self.ops))
+        op.pidx = len(self.params)
+        self.params += [conv.weight, conv.bias]
+        L = _lib.lib()
+        self._stat(op, "scale", cout)           # ones
+        if self.need_grad:
+            rows_b = L.vtb_bn_bwd_rows(out.pixels, cout)
+            self._stat(op, "partial_b", (rows_b + 1) * cout * 2)
+            self._stat(op, "coef", cout * 2)
+            op.rows_b = rows_b
+            self.ws_bytes = max(self.ws_bytes, int(L.vtb_conv_wgrad_workspace_bytes(C.byref(geom))))
         self.ops.append(op)
         return out
 
@@ -767,16 +813,23 @@ class Runner:
 
         # input layout conversion (NCHW float -> NHWC bf16, channels padded to a multiple of 16)
         xin = x.detach()
-        if xin.dtype != torch.float32 or not xin.is_contiguous():
-            xin = xin.float().contiguous()
         n, c, h, w = xin.shape
         t_in = g.input
+        if (not self.f32 and g.input_col is None and xin.dtype == torch.bfloat16 and c == t_in.c and xin.stride(1) == 1
+                and xin.stride(3) % 8 == 0 and xin.stride(2) == w * xin.stride(3) and xin.stride(0) == h * w * xin.stride(3)
+                and xin.data_ptr() % 16 == 0):
+            # already an NHWC bf16 view (a feature map of another native plan): one strided copy into the arena
+            check(self.fn_grad_add(abase + t_in.byte_offset(), t_in.c, xin.data_ptr(), xin.stride(3), n * h * w, c, 0, st),
+                  "vtb_grad_add(input)")
+            xin = None
+        elif xin.dtype != torch.float32 or not xin.is_contiguous():
+            xin = xin.float().contiguous()
         if g.input_col is not None:
             xc = g.input_col
             kk_, ss_, pp_, _ = xc.col_of
             check(L.vtb_im2col_input(xin.data_ptr(), n, c, h, w, kk_, ss_, pp_, abase + xc.byte_offset(), xc.c, st),
                   "vtb_im2col_input")
-        if not g.input_unused:
+        if not g.input_unused and xin is not None:
             check(self.fn_to_nhwc(xin.data_ptr(), n, c, h, w, abase + t_in.byte_offset(), t_in.c, st), "vtb_nchw_to_nhwc")
 
         if not self.f32:
@@ -813,13 +866,20 @@ class Runner:
 
     def _conv_forward(self, op: ConvOp, abase: int, sbase: int, run: Run, st: int, world: int) -> None:
         g, L = self.g, self.L
-        geom, norm = op.geom, op.mod.norm
+        geom, norm = op.geom, (None if op.bias else op.mod.norm)
         wf, _ = self._packed(op)
         x, out, res = op.x, op.out, op.residual
         f = lambda name: sbase + 4 * op.st[name]
         cout = geom.cout
         res_p = 0 if res is None else abase + res.byte_offset()
         res_ld = 0 if res is None else res.ld
+        if op.bias:
+            ones = run.stat_view_f32(op.st["scale"], cout, sbase)
+            ones.fill_(1.0)
+            check(L.vtb_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(), abase + out.byte_offset(),
+                                   out.ld, 0, ones.data_ptr(), op.mod.conv.bias.data_ptr(), 0, 0, 0, st),
+                  "vtb_conv_fprop(bias)")
+            return
         if g.fused_eval:
             check(L.vtb_bn_eval_affine(cout, norm.weight.data_ptr(), norm.bias.data_ptr(), norm.running_mean.data_ptr(),
                                        norm.running_var.data_ptr(), norm.eps, f("scale"), f("shift"), st),
@@ -1170,7 +1230,7 @@ class Runner:
             if not is_init(op.out):
                 # no gradient reaches this op: its parameters get zero gradient
                 if op.kind in ("conv", "ese"):
-                    n_p = 3 if op.kind == "conv" else 2
+                    n_p = op.nparams if op.kind == "conv" else 2
                     for j in range(n_p):
                         pgrads[op.pidx + j].zero_()
                     if ready_cb is not None:
@@ -1181,7 +1241,7 @@ class Runner:
                 bwd(op, abase, sbase, gp, gld, is_init, mark, next_dy(), wsbase, pgrads, run, st, world)
                 if ready_cb is not None:
                     with self._grad_stream_ctx():   # the all-reduce must also wait for the side-stream wgrad
-                        ready_cb(g.params[op.pidx : op.pidx + 3])
+                        ready_cb(g.params[op.pidx : op.pidx + op.nparams])
             elif op.kind == "copy":
                 xx, oo = op.x, op.out
                 if not (xx.is_input and not run.x_requires_grad):
@@ -1236,6 +1296,15 @@ class Runner:
         f = lambda name: sbase + 4 * op.st[name]
         dout_p, dout_ld = gp(out), gld(out)
         peer_sync = self.dist.sync if (world > 1 and self.dist is not None) else None
+        if op.bias:
+            # no normalisation, no activation: dy IS the output gradient; the bias gradient is its per-channel sum (the
+            # reduce kernel of the BatchNorm backward with the mask off - its second sum is not used)
+            check(L.vtb_bn_bwd_reduce(dout_p, dout_ld, dout_p, dout_ld, out.pixels, cout, f("scale"), f("scale"), f("scale"),
+                                      f("scale"), 0, f("partial_b"), st), "vtb_bn_bwd_reduce(bias)")
+            check(L.vtb_bn_bwd_finalize(f("partial_b"), op.rows_b, 0, 0, 1.0, cout, 0, pgrads[op.pidx + 1].data_ptr(), 0,
+                                        f("coef"), 0, st), "vtb_bn_bwd_finalize(bias)")
+            self._conv_backward_gemms(op, abase, gp, gld, is_init, mark, dout_p, wsbase, pgrads, run, st, lddy=dout_ld)
+            return
         if id(op) in run.bwd_stats_done:
             # the dgrad that completed this unit's output gradient already reduced (and exchanged) the sums: coef, dgamma
             # and dbeta are final - BatchNorm+ReLU backward is one apply pass
@@ -1277,9 +1346,10 @@ class Runner:
               "vtb_bn_bwd_apply")
         self._conv_backward_gemms(op, abase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st)
 
-    def _conv_backward_gemms(self, op: ConvOp, abase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st):
+    def _conv_backward_gemms(self, op: ConvOp, abase, gp, gld, is_init, mark, dybase, wsbase, pgrads, run, st, lddy=None):
         L = self.L
         geom, cout = op.geom, op.geom.cout
+        lddy = cout if lddy is None else lddy
         x, out, res = op.x, op.out, op.residual
         dout_p, dout_ld = gp(out), gld(out)
         _, wd = self._packed(op)
@@ -1295,11 +1365,11 @@ class Runner:
 
             self._launch_wgrad(launch, st)
         else:
-            self._launch_wgrad(lambda s_: check(L.vtb_conv_wgrad(C.byref(geom), dybase, cout, abase + x.byte_offset(), x.ld,
+            self._launch_wgrad(lambda s_: check(L.vtb_conv_wgrad(C.byref(geom), dybase, lddy, abase + x.byte_offset(), x.ld,
                                                                  wsbase, pgrads[op.pidx].data_ptr(), op.cin_real, 0, s_),
                                                 "vtb_conv_wgrad"), st)
         if not (x.is_input and not run.x_requires_grad):
-            self._dgrad(op, geom, dybase, cout, wd, abase, gp, gld, is_init, pgrads, run, st)
+            self._dgrad(op, geom, dybase, lddy, wd, abase, gp, gld, is_init, pgrads, run, st)
             mark(x)
         self._residual_grad(op, gp, gld, is_init, mark, st)
 
