@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(const VtbSgdJob* __restri
 // coalesced reads (many independent loads in flight: the split count, not the tile, carries the parallelism for small
 // layers), the groups are combined through shared memory in a fixed order (deterministic), and the slice is written out
 // in OIHW order, which is contiguous for the block ((ci, t) fastest).
-template <int EW>
+template <int EW, bool DEEP>
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, int cin_real, int kk,
                     float* __restrict__ dw, int accumulate, float* __restrict__ dw2, int split) {
@@ -301,7 +301,23 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin,
     for (int t = 0; t < kk; ++t) mine[t * pitch] = 0.f;
     const int total = kk * splits;
     int q = sg;
-    for (; q + 3 * SG < total; q += 4 * SG) {   // 4 independent loads in flight
+    // DEEP (many splits: the small layers): 16, then 4 independent loads in flight per thread - the sums are latency-bound
+    // (partials sit in L2) and there are few blocks, so memory-level parallelism is what shortens the kernel; layers with
+    // few splits have thousands of blocks and prefer the lighter variant (registers -> occupancy)
+    for (; DEEP && q + 15 * SG < total; q += 16 * SG) {
+      float v[16];
+      int tt[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int qq = q + u * SG;
+        const int t = qq / splits, sp = qq - t * splits;
+        tt[u] = t;
+        v[u] = __ldg(src + (size_t)sp * split_stride + (size_t)t * cin);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) mine[tt[u] * pitch] += v[u];
+    }
+    for (; q + 3 * SG < total; q += 4 * SG) {
       float v[4];
       int tt[4];
 #pragma unroll
@@ -899,12 +915,14 @@ static int wgrad_impl(const VtbConv* c, const void* dy, int lddy, const void* x,
   const float* wsf = (const float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t re;
-  if (ew == 16)
-    re = launch_pdl(wgrad_reduce_kernel<16>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate, dw2, split);
-  else if (ew == 32)
-    re = launch_pdl(wgrad_reduce_kernel<32>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate, dw2, split);
-  else
-    re = launch_pdl(wgrad_reduce_kernel<64>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, dw_oihw, accumulate, dw2, split);
+  const bool deep = (long long)p.ntaps * w.splits >= 16 * (256 / ew);
+#define VTB_REDUCE(EWV, DEEPV)                                                                                              \
+  launch_pdl(wgrad_reduce_kernel<EWV, DEEPV>, rgrid, dim3(256), rsmem, st, wsf, w.splits, c->cout, c->cin, cin_real, p.ntaps, \
+             dw_oihw, accumulate, dw2, split)
+  if (ew == 16) re = deep ? VTB_REDUCE(16, true) : VTB_REDUCE(16, false);
+  else if (ew == 32) re = deep ? VTB_REDUCE(32, true) : VTB_REDUCE(32, false);
+  else re = deep ? VTB_REDUCE(64, true) : VTB_REDUCE(64, false);
+#undef VTB_REDUCE
   return check_cuda((int)re, "wgrad_reduce_kernel");
 }
 
