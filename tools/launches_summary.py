@@ -37,6 +37,10 @@ def main(path: str, tag: str) -> None:
     if not starts:
         starts = [i for i, k in enumerate(ids) if "nchw_to_nhwc" in launches[k]["kernel"]]
     step = ids[starts[-1]:] if starts else ids
+    # native optimizer (round 2): a step ENDS with the fused SGD + re-pack launch followed by vtb_sgd_step
+    ends = [i for i, k in enumerate(ids) if "sgd_step_kernel" in launches[k]["kernel"]]
+    if len(ends) >= 2:
+        step = ids[ends[-2] + 1: ends[-1] + 1]
     agg, tot = collections.OrderedDict(), 0.0
     conv_bytes, conv_n = 0.0, 0
     have_dram = False

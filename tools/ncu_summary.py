@@ -9,6 +9,17 @@ KEYS = [
     "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    # tcgen05 work (round 2: the counters that DO register UTCHMMA; the hmma / pipe_tensor ones below are legacy-HMMA)
+    "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.sum",
+    "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.per_cycle_elapsed",
+    "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.peak_sustained",
+    "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__mem_tensor_reads.sum", "sm__mem_tensor_writes.sum", "sm__inst_executed_pipe_tmem.sum",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_a.sum",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_b_scope_1cta.sum",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg",
     "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",

@@ -70,17 +70,52 @@ __device__ __forceinline__ void panel_early_load(int lane, const __nv_bfloat16* 
                                : make_uint4(0u, 0u, 0u, 0u);
   }
 }
-template <int CH, bool ADD, int MODE>
+// lane-level butterfly over the row-group bits of the lane index (see panel_drain): 8 (S, Q) pairs per lane -> the totals
+// of one column per lane
+template <int CH>
+__device__ __forceinline__ void stats_butterfly(int lane, float (&S)[8], float (&Q)[8]) {
+  constexpr int RG = 32 / CH;
+  int n = 8;
+#pragma unroll
+  for (int step = 0; (1 << step) < RG; ++step) {
+    const int partner_bit = CH << step;
+    const bool upper = (lane & partner_bit) != 0;
+    if (n > 1) {
+      const int hn = n / 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < hn) {
+          // send the half I do not keep, receive the partner's copy of the half I keep
+          const float sendS = upper ? S[j] : S[j + hn], sendQ = upper ? Q[j] : Q[j + hn];
+          const float keepS = upper ? S[j + hn] : S[j], keepQ = upper ? Q[j + hn] : Q[j];
+          S[j] = keepS + __shfl_xor_sync(0xffffffffu, sendS, partner_bit);
+          Q[j] = keepQ + __shfl_xor_sync(0xffffffffu, sendQ, partner_bit);
+        }
+      }
+      n = hn;
+    } else {
+      S[0] += __shfl_xor_sync(0xffffffffu, S[0], partner_bit);
+      Q[0] += __shfl_xor_sync(0xffffffffu, Q[0], partner_bit);
+    }
+  }
+}
+
+// DEFER: the caller keeps this lane's 8 (S, Q) pairs in registers across ALL tiles of the CTA (accS / accQ) and runs the
+// butterfly once at the end - possible when every drain of the warp covers the same columns (one local panel).
+template <int CH, bool ADD, int MODE, bool DEFER = false>
 __device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloat16* gcol, int ld, const int (&pix)[4],
-                                            const BwdCols& bw, const uint4 (&early)[4], float& o0, float& o1) {
-  constexpr int RG = 32 / CH;          // row groups
+                                            const BwdCols& bw, const uint4 (&early)[4], float& o0, float& o1,
+                                            float (&accS)[8], float (&accQ)[8]) {
   constexpr int ROWS = CH;             // rows per group
   constexpr uint32_t PITCH = 16 * CH;
   constexpr uint32_t SMASK = (CH == 4) ? 3u : 1u;
   const int chunk = lane % CH, rg = lane / CH;
   float S[8], Q[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) S[j] = Q[j] = 0.f;
+  for (int j = 0; j < 8; ++j) {
+    S[j] = DEFER ? accS[j] : 0.f;
+    Q[j] = DEFER ? accQ[j] : 0.f;
+  }
   float sc[MODE == 2 ? 8 : 1], sh[MODE == 2 ? 8 : 1];
   if (MODE == 2) {
 #pragma unroll
@@ -151,41 +186,24 @@ __device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloa
       }
     }
   }
-  if (MODE != 0) {
-    // butterfly over the row-group bits of the lane index
-    int n = 8;
+  if (DEFER) {
 #pragma unroll
-    for (int step = 0; (1 << step) < RG; ++step) {
-      const int partner_bit = CH << step;
-      const bool upper = (lane & partner_bit) != 0;
-      if (n > 1) {
-        const int hn = n / 2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < hn) {
-            // send the half I do not keep, receive the partner's copy of the half I keep
-            const float sendS = upper ? S[j] : S[j + hn], sendQ = upper ? Q[j] : Q[j + hn];
-            const float keepS = upper ? S[j + hn] : S[j], keepQ = upper ? Q[j + hn] : Q[j];
-            S[j] = keepS + __shfl_xor_sync(0xffffffffu, sendS, partner_bit);
-            Q[j] = keepQ + __shfl_xor_sync(0xffffffffu, sendQ, partner_bit);
-          }
-        }
-        n = hn;
-      } else {
-        S[0] += __shfl_xor_sync(0xffffffffu, S[0], partner_bit);
-        Q[0] += __shfl_xor_sync(0xffffffffu, Q[0], partner_bit);
-      }
+    for (int j = 0; j < 8; ++j) {
+      accS[j] = S[j];
+      accQ[j] = Q[j];
     }
+    return;
   }
+  if (MODE != 0) stats_butterfly<CH>(lane, S, Q);
   o0 = S[0];
   o1 = Q[0];
 }
-template <bool ADD, int MODE>
+template <bool ADD, int MODE, bool DEFER = false>
 __device__ __forceinline__ void panel_drain_pw(int pw, uint32_t panel, int lane, __nv_bfloat16* gcol, int ld,
                                                const int (&pix)[4], const BwdCols& bw, const uint4 (&early)[4], float& o0,
-                                               float& o1) {
-  if (pw == 32) panel_drain<4, ADD, MODE>(panel, lane, gcol, ld, pix, bw, early, o0, o1);
-  else panel_drain<2, ADD, MODE>(panel, lane, gcol, ld, pix, bw, early, o0, o1);
+                                               float& o1, float (&accS)[8], float (&accQ)[8]) {
+  if (pw == 32) panel_drain<4, ADD, MODE, DEFER>(panel, lane, gcol, ld, pix, bw, early, o0, o1, accS, accQ);
+  else panel_drain<2, ADD, MODE, DEFER>(panel, lane, gcol, ld, pix, bw, early, o0, o1, accS, accQ);
 }
 template <bool ADD, int MODE>
 __device__ __forceinline__ void panel_early_pw(int pw, int lane, const __nv_bfloat16* gcol, int ld, const int (&pix)[4],
@@ -230,7 +248,9 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool 
 //   kEpiAffine  dense store of [relu](acc*scale+shift)[+residual] (eval-mode fused fprop)
 //   kEpiPlain   store or read-modify-write accumulate, dense or strided pixel lattice (dgrad, fprop without statistics)
 //   kEpiBwd     kEpiPlain + BatchNorm(+ReLU) backward statistics of the producer layer(s) (ConvIgemmParams::bwd_*)
-enum EpiKind : int { kEpiStats = 0, kEpiAffine = 1, kEpiPlain = 2, kEpiBwd = 3 };
+//   kEpiStats1  kEpiStats for tiles whose every epilogue warp owns ONE panel (block_n <= 64 with 256-row tiles, <= 128
+//               with 128-row tiles): the per-lane sums stay in registers across tiles, one butterfly at the end
+enum EpiKind : int { kEpiStats = 0, kEpiAffine = 1, kEpiPlain = 2, kEpiBwd = 3, kEpiStats1 = 4 };
 
 template <bool TIMED, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -431,7 +451,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int pw = p.panel_w;
     const uint32_t pitch = pw * 2;
     const uint32_t smask = (pw == 64) ? 7u : (pw == 32 ? 3u : 1u);
-    constexpr bool do_stats = (EPI == kEpiStats || EPI == kEpiBwd);   // per-channel (S, Q) sums ride in the drain
+    constexpr bool do_stats = (EPI == kEpiStats || EPI == kEpiBwd || EPI == kEpiStats1);   // per-channel (S, Q) sums ride in the drain
+    float accS[8], accQ[8];   // kEpiStats1: this lane's sums over every tile of the CTA
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accS[j] = accQ[j] = 0.f;
     const bool scatter = (p.store_mode == kStoreScatter || p.store_mode == kStoreScatterAdd);
     const bool add = (p.store_mode == kStoreTmaAdd || p.store_mode == kStoreScatterAdd);
     const int npanels = p.block_n / pw;         // host guarantees npanels <= kMaxPanels
@@ -603,16 +626,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           float o0 = 0.f, o1 = 0.f;
           if (EPI == kEpiBwd) {
-            if (add) panel_drain_pw<true, 2>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
-            else panel_drain_pw<false, 2>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
+            if (add) panel_drain_pw<true, 2>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
+            else panel_drain_pw<false, 2>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
           } else if (EPI == kEpiStats) {
-            panel_drain_pw<false, 1>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
+            panel_drain_pw<false, 1>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
+          } else if (EPI == kEpiStats1) {
+            panel_drain_pw<false, 1, true>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
           } else if (EPI == kEpiPlain && add) {
-            panel_drain_pw<true, 0>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
+            panel_drain_pw<true, 0>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
           } else {
-            panel_drain_pw<false, 0>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1);
+            panel_drain_pw<false, 0>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
           }
-          if (do_stats) {
+          if (do_stats && EPI != kEpiStats1) {
             const int lpi = (pi - pi_first) / pi_step;   // local panel index of this group, < 4
             if (lpi == 0) { a0.x += o0; a0.y += o1; }
             else if (lpi == 1) { a0.z += o0; a0.w += o1; }
@@ -632,6 +657,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // to finish turns the rows into mean / invstd / scale / shift and the running-statistics update (forward) or
       // into the BatchNorm-backward coefficients and parameter gradients of the producer layer (kEpiBwd) -
       // BatchNorm's finalisation costs no extra launch.
+      if (EPI == kEpiStats1) {   // the one deferred butterfly: per-lane sums of all tiles -> this lane's column totals
+        if (pw == 32) stats_butterfly<4>(lane, accS, accQ);
+        else stats_butterfly<2>(lane, accS, accQ);
+        a0.x = accS[0];
+        a0.y = accQ[0];
+      }
       const int et = threadIdx.x - 128;             // 0..511 over the 16 epilogue warps
       const int nslices = halves * 4;
       float2* slots = reinterpret_cast<float2*>(smem_raw + (panel_base - smem_u32(smem_raw)));   // [8][block_n]
@@ -1100,12 +1131,16 @@ int launch_conv_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   fill_derived(p, grid);
   const size_t smem = conv_igemm_smem_bytes(p.block_m, p.block_n, p.num_stages, p.panel_bufs);
   if (p.fin_rows <= 0) p.fin_rows = p.m_step;
+  // one local panel per epilogue warp; 1x1 layers only (measured: the 3x3 32->32 layer loses 6 % to the extra registers)
+  const bool one_panel = p.a_tiled && (p.block_n / p.panel_w) <= (p.halves == 2 ? 2 : 4);
+  static const bool defer_ok = !(getenv("VTB_STATS_DEFER") && atoi(getenv("VTB_STATS_DEFER")) == 0);
   const int epi = p.bwd_y[0] != nullptr ? kEpiBwd
-                  : (p.stats_partial != nullptr ? kEpiStats
+                  : (p.stats_partial != nullptr ? ((one_panel && defer_ok) ? kEpiStats1 : kEpiStats)
                                                 : ((p.scale != nullptr || p.relu || p.residual != nullptr) ? kEpiAffine : kEpiPlain));
   if (p.dbg != nullptr) {
     switch (epi) {
       case kEpiStats: return launch_conv_variant<true, kEpiStats>(tmA, tmB, tmD, p, grid, smem, stream);
+      case kEpiStats1: return launch_conv_variant<true, kEpiStats1>(tmA, tmB, tmD, p, grid, smem, stream);
       case kEpiAffine: return launch_conv_variant<true, kEpiAffine>(tmA, tmB, tmD, p, grid, smem, stream);
       case kEpiPlain: return launch_conv_variant<true, kEpiPlain>(tmA, tmB, tmD, p, grid, smem, stream);
       default: return launch_conv_variant<true, kEpiBwd>(tmA, tmB, tmD, p, grid, smem, stream);
@@ -1113,6 +1148,7 @@ int launch_conv_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   }
   switch (epi) {
     case kEpiStats: return launch_conv_variant<false, kEpiStats>(tmA, tmB, tmD, p, grid, smem, stream);
+    case kEpiStats1: return launch_conv_variant<false, kEpiStats1>(tmA, tmB, tmD, p, grid, smem, stream);
     case kEpiAffine: return launch_conv_variant<false, kEpiAffine>(tmA, tmB, tmD, p, grid, smem, stream);
     case kEpiPlain: return launch_conv_variant<false, kEpiPlain>(tmA, tmB, tmD, p, grid, smem, stream);
     default: return launch_conv_variant<false, kEpiBwd>(tmA, tmB, tmD, p, grid, smem, stream);
