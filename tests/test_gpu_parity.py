@@ -476,3 +476,53 @@ def test_training_step_with_device_side_mixup_cutmix_is_capturable():
     losses = [float(tr.step(x, y)) for _ in range(6)]
     assert all(l == l and l > 0 for l in losses)
     assert len(set(round(l, 6) for l in losses)) > 3      # different mixes (and weights) every replay
+
+
+def test_bf16_tiny_stem_against_the_bf16_oracle():
+    """Root cause of the case parked in round 1 (a bf16 3x3 stride-2 stem unit on a 1x3x17x13 image,
+    63 output pixels, dW 1e-1 away from FP32 truth).  The yardstick was wrong, not the kernel: against the bf16-mode
+    ORACLE on the same tensors (same rounding points; reference components.py:26-39 under autocast) the gradients agree to
+    ~2e-3 with ZERO ReLU-mask flips (measured over 6 seeds) - the 1e-1 is what bf16 rounding of a conv output costs a
+    63-sample BatchNorm against fp32, in the reference as well.  The forced-mask comparison (SURVEY.md Appendix B,
+    conclusion 1) is kept for the case that a flip does occur."""
+    from oracle import vt_oracle as O
+    from vision_toolbox_b200.components import ConvNormAct
+
+    worst_forced, total_flips = 0.0, 0
+    for seed in range(6):
+        torch.manual_seed(seed)
+        m = ConvNormAct(3, 32, 3, 2).train()
+        with torch.no_grad():
+            m.norm.weight.uniform_(0.5, 1.5)
+            m.norm.bias.uniform_(-0.2, 0.2)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        x = torch.rand(1, 3, 17, 13)
+        cot = torch.randn(1, 32, 9, 7)
+        mg = m.cuda()
+        out = mg(x.cuda())
+        (out.float() * cot.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        ours = {k: p.grad.cpu() for k, p in mg.named_parameters()}
+        mask_ours = (out.float() > 0).cpu()
+
+        def oracle(mask):
+            params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+            full = dict(sd); full.update(params); full["__stride__"] = {"": 2}
+            z = O.conv_norm_act(full, "", x, True, "bf16", act=False)
+            o = torch.relu(z) if mask is None else z * mask
+            g = torch.autograd.grad((o * cot).sum(), list(params.values()))
+            return o.detach(), dict(zip(params.keys(), g))
+
+        o_ref, g_ref = oracle(None)
+        flips = int(((o_ref > 0) != mask_ours).sum())
+        total_flips += flips
+        _, g_forced = oracle(mask_ours.float())
+        e_free = max(rel_err(ours[k], g_ref[k]) for k in ours)
+        e_forced = max(rel_err(ours[k], g_forced[k]) for k in ours)
+        worst_forced = max(worst_forced, e_forced)
+        print(f"seed {seed}: {flips} mask flips of {mask_ours.numel()}, grads vs bf16 oracle {e_free:.2e}, with our mask forced {e_forced:.2e}")
+        assert rel_err(out.float(), o_ref) < BF16_TOL
+        assert e_forced < BF16_TOL, (seed, e_forced)
+        if flips == 0:
+            assert e_free < BF16_TOL, (seed, e_free)
+    print(f"worst forced-mask gradient error {worst_forced:.2e}; {total_flips} flips over 6 seeds")
