@@ -14,7 +14,13 @@
  *    channel slice of a wider concat buffer (ld >= C, ld % 8 == 0, base 16-byte aligned).
  *  - parameters / statistics / parameter gradients are fp32 in the reference's own layouts (OIHW, [C]).
  *  - every function returns 0 on success, a negative VTB_E* code otherwise; vtb_last_error() gives text.
- *  - all functions are asynchronous on `stream` and re-entrant per stream.
+ *  - all functions are asynchronous on `stream` and re-entrant per stream, with ONE restriction: vtb_bn_bwd_fused without
+ *    SyncBN peers is an ordinary (not cooperative) launch whose <= num_SMs blocks meet at a hand-rolled grid barrier.
+ *    Everything else this library launches finishes without waiting for it, so within one model's streams the blocks
+ *    always become co-resident; two such kernels in flight on two user streams of one device, or foreign work that holds
+ *    SMs indefinitely, can starve the barrier.  VTB_BWD_COOP=1 selects the cooperative launch (co-residency guaranteed by
+ *    the driver) for such setups; the SyncBN variant always uses it.
+ *  - SyncBN assumes the same per-rank batch size on every rank (count * world); BatchNorm2d(momentum=None) is rejected.
  */
 #ifndef VTB_H_
 #define VTB_H_
