@@ -102,14 +102,19 @@ __device__ __forceinline__ void stats_butterfly(int lane, float (&S)[8], float (
 
 // DEFER: the caller keeps this lane's 8 (S, Q) pairs in registers across ALL tiles of the CTA (accS / accQ) and runs the
 // butterfly once at the end - possible when every drain of the warp covers the same columns (one local panel).
+// Addressing is prepared by the caller ONCE per CTA / per tile (the drain is issue-bound: every integer instruction saved
+// here is saved 8 x per 256 x 128 tile and warp): dsm0 / dsm1 = shared-memory addresses of this lane's chunk in its first
+// / third staged row (the swizzle XOR is folded in; rows 1 and 3 sit one row pitch behind), rowoff[r] = element offset of
+// row r in the destination (pixel index * pitch; 0xFFFFFFFF: row outside the tensor).
 template <int CH, bool ADD, int MODE, bool DEFER = false>
-__device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloat16* gcol, int ld, const int (&pix)[4],
-                                            const BwdCols& bw, const uint4 (&early)[4], float& o0, float& o1,
-                                            float (&accS)[8], float (&accQ)[8]) {
+__device__ __forceinline__ void panel_drain(uint32_t dsm0, uint32_t dsm1, int lane, __nv_bfloat16* gcol,
+                                            const uint32_t (&rowoff)[4], const int (&pix)[4], const BwdCols& bw,
+                                            const uint4 (&early)[4], float& o0, float& o1, float (&accS)[8],
+                                            float (&accQ)[8]) {
   constexpr int ROWS = CH;             // rows per group
   constexpr uint32_t PITCH = 16 * CH;
-  constexpr uint32_t SMASK = (CH == 4) ? 3u : 1u;
-  const int chunk = lane % CH, rg = lane / CH;
+  const int chunk = lane % CH;
+  __nv_bfloat16* gbase = gcol + chunk * 8;
   float S[8], Q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -135,18 +140,18 @@ __device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloa
     if (ADD) {
 #pragma unroll
       for (int r = 0; r < RB; ++r)
-        old[r] = (pix[r0 + r] >= 0) ? *reinterpret_cast<const uint4*>(gcol + (size_t)pix[r0 + r] * ld + chunk * 8)
-                                    : make_uint4(0u, 0u, 0u, 0u);
+        old[r] = (rowoff[r0 + r] != 0xFFFFFFFFu) ? *reinterpret_cast<const uint4*>(gbase + rowoff[r0 + r])
+                                                  : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      const int rr = rg * ROWS + r0 + r;
-      const int px = pix[r0 + r];
+      const uint32_t ro = rowoff[r0 + r];
+      const int px = (ro != 0xFFFFFFFFu) ? 0 : -1;
       uint32_t w[4];
-      const uint32_t off = swz((uint32_t)rr * PITCH + chunk * 16, SMASK);
-      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(panel + off));
+      const uint32_t sa = (((r0 + r) & 2) ? dsm1 : dsm0) + ((r0 + r) & 1) * PITCH;
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(sa));
       if (px >= 0) {
-        uint4* gp = reinterpret_cast<uint4*>(gcol + (size_t)px * ld + chunk * 8);
+        uint4* gp = reinterpret_cast<uint4*>(gbase + ro);
         if (ADD) {
           const uint4 ov = old[r];
           const uint32_t oo[4] = {ov.x, ov.y, ov.z, ov.w};
@@ -198,19 +203,6 @@ __device__ __forceinline__ void panel_drain(uint32_t panel, int lane, __nv_bfloa
   o0 = S[0];
   o1 = Q[0];
 }
-template <bool ADD, int MODE, bool DEFER = false>
-__device__ __forceinline__ void panel_drain_pw(int pw, uint32_t panel, int lane, __nv_bfloat16* gcol, int ld,
-                                               const int (&pix)[4], const BwdCols& bw, const uint4 (&early)[4], float& o0,
-                                               float& o1, float (&accS)[8], float (&accQ)[8]) {
-  if (pw == 32) panel_drain<4, ADD, MODE, DEFER>(panel, lane, gcol, ld, pix, bw, early, o0, o1, accS, accQ);
-  else panel_drain<2, ADD, MODE, DEFER>(panel, lane, gcol, ld, pix, bw, early, o0, o1, accS, accQ);
-}
-template <bool ADD, int MODE>
-__device__ __forceinline__ void panel_early_pw(int pw, int lane, const __nv_bfloat16* gcol, int ld, const int (&pix)[4],
-                                               const BwdCols& bw, uint4 (&early)[4]) {
-  if (pw == 32) panel_early_load<4, ADD, MODE>(lane, gcol, ld, pix, bw, early);
-  else panel_early_load<2, ADD, MODE>(lane, gcol, ld, pix, bw, early);
-}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // mbarrier wait that optionally accounts the stalled cycles (development counters, ConvIgemmParams::dbg)
@@ -252,7 +244,7 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool 
 //               with 128-row tiles): the per-lane sums stay in registers across tiles, one butterfly at the end
 enum EpiKind : int { kEpiStats = 0, kEpiAffine = 1, kEpiPlain = 2, kEpiBwd = 3, kEpiStats1 = 4 };
 
-template <bool TIMED, int EPI>
+template <bool TIMED, int EPI, int PW>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ ConvIgemmParams p) {
@@ -448,9 +440,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int grp = (warp - 4) >> 2;            // epilogue group 0..3
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;        // row inside the 128-row half == TMEM lane
-    const int pw = p.panel_w;
-    const uint32_t pitch = pw * 2;
-    const uint32_t smask = (pw == 64) ? 7u : (pw == 32 ? 3u : 1u);
+    constexpr int pw = PW;                      // staged panel width: 32 or 16 columns (compile time: the drain is issue-bound)
+    constexpr uint32_t pitch = PW * 2;
+    constexpr uint32_t smask = (PW == 32) ? 3u : 1u;
+    constexpr int CH = PW / 8;                  // 16-byte chunks per staged row = rows each lane drains per panel
     constexpr bool do_stats = (EPI == kEpiStats || EPI == kEpiBwd || EPI == kEpiStats1);   // per-channel (S, Q) sums ride in the drain
     float accS[8], accQ[8];   // kEpiStats1: this lane's sums over every tile of the CTA
 #pragma unroll
@@ -474,8 +467,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int pi_first = (halves == 2) ? (grp & 1) : grp;
     const int pi_step = (halves == 2) ? 2 : 4;
     // rows of the staged panel this lane writes out (panel_drain): row group rg, rows rg*CH .. rg*CH + CH-1
-    const int drain_ch = pw >> 3;               // 16-byte chunks per panel row: 4 (pw 32) or 2 (pw 16)
+    constexpr int drain_ch = CH;
     const int drain_row0 = quarter * 32 + (lane / drain_ch) * drain_ch;
+    // loop-invariant shared-memory addresses of this lane (swizzle XOR folded in):
+    //   staging writes: row `lane`, 16-byte chunk c -> st_base | ((c << 4) ^ st_x)
+    //   drain reads   : rows rg*CH + {0,1} from dsm0 (+ pitch), rows rg*CH + {2,3} from dsm1 (+ pitch)
+    const uint32_t st_base = my_panels + (uint32_t)lane * pitch;
+    const uint32_t st_x = ((((uint32_t)lane * pitch) >> 7) & smask) << 4;
+    uint32_t dsm0, dsm1;
+    {
+      const uint32_t rg = (uint32_t)lane / CH, chunk = (uint32_t)lane % CH;
+      const uint32_t row0 = rg * CH;
+      dsm0 = my_panels + row0 * pitch + ((chunk ^ (((row0 * pitch) >> 7) & smask)) << 4);
+      dsm1 = my_panels + (row0 + 2) * pitch + ((chunk ^ ((((row0 + 2) * pitch) >> 7) & smask)) << 4);
+    }
+    // TMEM: this warp's lane quarter and accumulator half
+    const uint32_t tm_h = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(my_half * ksplit) * acc_stride;
     for (int m_blk = m_first; m_blk < num_m_blocks; m_blk += m_step, ++lt) {
       const int h = my_half;
       const uint32_t set = (nsets == 2u) ? (lt & 1u) : 0u;
@@ -483,6 +490,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0 = m_blk * p.block_m + h * kBlockM;
       // pixel index (in the output tensor's lattice) of the rows this lane stores; < 0: outside the tensor
       int pix[4];
+      uint32_t rowoff[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int mm = m0 + drain_row0 + r;
@@ -498,6 +506,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         pix[r] = px;
+        rowoff[r] = (px >= 0) ? (uint32_t)px * (uint32_t)p.ldo : 0xFFFFFFFFu;   // host: pixels * pitch < 2^32
       }
       if (EPI == kEpiBwd) {
         // the rows this lane will read in its drains (producer y / old destination): pull their lines into L2 while the
@@ -524,11 +533,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_before();
         if (lane == 0) mbar_arrive(tempty_bar(set));
       }
-      const uint32_t acc0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + set * set_cols + (h * ksplit) * acc_stride;
+      const uint32_t acc0 = tm_h + set * set_cols;
 
       const int m = m0 + row;
       for (int pi = pi_first; pi < npanels; pi += pi_step) {
-        const uint32_t panel = my_panels;
         const uint32_t taddr = acc0 + pi * pw;
         long long tp_ld = 0, tp_cvt = 0;
         const int colp = n0 + pi * pw;            // first column of this panel
@@ -545,14 +553,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           bw.scale = p.bwd_scale[L] + lc;
           bw.shift = p.bwd_shift[L] + lc;
           bw.relu = p.bwd_relu[L];
-          panel_early_pw<false, 2>(pw, lane, gcol, p.ldo, pix, bw, early);
+          panel_early_load<CH, false, 2>(lane, gcol, p.ldo, pix, bw, early);
         }
         // the panel is drained in pieces of 16 columns to keep the register footprint small: this kernel runs with
         // ~no L1 (all of it is shared memory), so a spilled register costs an L2 round trip
-        const int npieces = pw / 16;
+        constexpr int npieces = PW / 16;
+#pragma unroll
         for (int pc = 0; pc < npieces; ++pc) {
           const long long tq0 = timed ? clock64() : 0;
           uint32_t v[16];
+          float f[16];
           const uint32_t ta = taddr + pc * 16;
           tmem_ld16(ta, v);
           if (ksplit >= 2) {   // sum the K-interleaved partial accumulators; loads are issued before the single wait
@@ -560,15 +570,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld16(ta + acc_stride, v2);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + __uint_as_float(v2[i]);
             for (int ksel = 2; ksel < ksplit; ++ksel) {
               tmem_ld16(ta + ksel * acc_stride, v2);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+              for (int i = 0; i < 16; ++i) f[i] += __uint_as_float(v2[i]);
             }
           } else {
             tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
           }
           if (pi + pi_step >= npanels && pc == npieces - 1) {
             tc_fence_before();
@@ -578,9 +590,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const long long tq1 = timed ? clock64() : 0;
           {
             const int ch = pc;   // 16-column chunk inside the panel
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
             const int col0 = n0 + pi * pw + ch * 16;
             if (EPI == kEpiAffine && p.scale != nullptr) {
 #pragma unroll
@@ -610,8 +619,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              const uint32_t off = swz(lane * pitch + (ch * 2 + hh) * 16, smask);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(panel + off), "r"(pk[4 * hh]),
+              const uint32_t sa = st_base | ((uint32_t)((ch * 2 + hh) << 4) ^ st_x);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa), "r"(pk[4 * hh]),
                            "r"(pk[4 * hh + 1]), "r"(pk[4 * hh + 2]), "r"(pk[4 * hh + 3])
                            : "memory");
             }
@@ -626,16 +635,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           float o0 = 0.f, o1 = 0.f;
           if (EPI == kEpiBwd) {
-            if (add) panel_drain_pw<true, 2>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
-            else panel_drain_pw<false, 2>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
+            if (add) panel_drain<CH, true, 2>(dsm0, dsm1, lane, gcol, rowoff, pix, bw, early, o0, o1, accS, accQ);
+            else panel_drain<CH, false, 2>(dsm0, dsm1, lane, gcol, rowoff, pix, bw, early, o0, o1, accS, accQ);
           } else if (EPI == kEpiStats) {
-            panel_drain_pw<false, 1>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
+            panel_drain<CH, false, 1>(dsm0, dsm1, lane, gcol, rowoff, pix, bw, early, o0, o1, accS, accQ);
           } else if (EPI == kEpiStats1) {
-            panel_drain_pw<false, 1, true>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
+            panel_drain<CH, false, 1, true>(dsm0, dsm1, lane, gcol, rowoff, pix, bw, early, o0, o1, accS, accQ);
           } else if (EPI == kEpiPlain && add) {
-            panel_drain_pw<true, 0>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
+            panel_drain<CH, true, 0>(dsm0, dsm1, lane, gcol, rowoff, pix, bw, early, o0, o1, accS, accQ);
           } else {
-            panel_drain_pw<false, 0>(pw, panel, lane, gcol, p.ldo, pix, bw, early, o0, o1, accS, accQ);
+            panel_drain<CH, false, 0>(dsm0, dsm1, lane, gcol, rowoff, pix, bw, early, o0, o1, accS, accQ);
           }
           if (do_stats && EPI != kEpiStats1) {
             const int lpi = (pi - pi_first) / pi_step;   // local panel index of this group, < 4
@@ -658,8 +667,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // into the BatchNorm-backward coefficients and parameter gradients of the producer layer (kEpiBwd) -
       // BatchNorm's finalisation costs no extra launch.
       if (EPI == kEpiStats1) {   // the one deferred butterfly: per-lane sums of all tiles -> this lane's column totals
-        if (pw == 32) stats_butterfly<4>(lane, accS, accQ);
-        else stats_butterfly<2>(lane, accS, accQ);
+        stats_butterfly<CH>(lane, accS, accQ);
         a0.x = accS[0];
         a0.y = accQ[0];
       }
@@ -1112,17 +1120,23 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-template <bool TIMED, int EPI>
-static int launch_conv_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+template <bool TIMED, int EPI, int PW>
+static int launch_conv_variant_pw(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                                const ConvIgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<TIMED, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<TIMED, EPI, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBudget);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  return (int)launch_pdl(conv_igemm_kernel<TIMED, EPI>, dim3(grid), dim3(kConvThreads), smem, stream, tmA, tmB, tmD, p);
+  return (int)launch_pdl(conv_igemm_kernel<TIMED, EPI, PW>, dim3(grid), dim3(kConvThreads), smem, stream, tmA, tmB, tmD, p);
+}
+template <bool TIMED, int EPI>
+static int launch_conv_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                               const ConvIgemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  if (p.panel_w == 32) return launch_conv_variant_pw<TIMED, EPI, 32>(tmA, tmB, tmD, p, grid, smem, stream);
+  return launch_conv_variant_pw<TIMED, EPI, 16>(tmA, tmB, tmD, p, grid, smem, stream);
 }
 
 int launch_conv_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
