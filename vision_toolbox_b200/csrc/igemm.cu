@@ -115,11 +115,12 @@ __device__ __forceinline__ void panel_drain(uint32_t dsm0, uint32_t dsm1, int la
   constexpr uint32_t PITCH = 16 * CH;
   const int chunk = lane % CH;
   __nv_bfloat16* gbase = gcol + chunk * 8;
-  float S[8], Q[8];
+  // sums of the lane's 8 channels as packed fp32 pairs: element 2j in the low word, 2j+1 in the high word
+  uint64_t S2[4], Q2[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    S[j] = DEFER ? accS[j] : 0.f;
-    Q[j] = DEFER ? accQ[j] : 0.f;
+  for (int j = 0; j < 4; ++j) {
+    S2[j] = DEFER ? f2_pack(accS[2 * j], accS[2 * j + 1]) : 0ull;
+    Q2[j] = DEFER ? f2_pack(accQ[2 * j], accQ[2 * j + 1]) : 0ull;
   }
   float sc[MODE == 2 ? 8 : 1], sh[MODE == 2 ? 8 : 1];
   if (MODE == 2) {
@@ -163,11 +164,9 @@ __device__ __forceinline__ void panel_drain(uint32_t dsm0, uint32_t dsm1, int la
       if (MODE == 1) {   // rows outside the tensor hold zeros (TMA zero-fills the operand rows): they add nothing
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float a = bf16lo(w[j]), b = bf16hi(w[j]);
-          S[2 * j] += a;
-          Q[2 * j] = fmaf(a, a, Q[2 * j]);
-          S[2 * j + 1] += b;
-          Q[2 * j + 1] = fmaf(b, b, Q[2 * j + 1]);
+          const uint64_t v2 = f2_pack(bf16lo(w[j]), bf16hi(w[j]));
+          S2[j] = f2_add(S2[j], v2);
+          Q2[j] = f2_fma(v2, v2, Q2[j]);
         }
       }
       if (MODE == 2) {
@@ -176,20 +175,29 @@ __device__ __forceinline__ void panel_drain(uint32_t dsm0, uint32_t dsm1, int la
           const uint32_t yy[4] = {yy4.x, yy4.y, yy4.z, yy4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            float dzv[2], yv2[2];
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const int e = 2 * j + hh;
               const float g = hh ? bf16hi(w[j]) : bf16lo(w[j]);
               const float y = hh ? bf16hi(yy[j]) : bf16lo(yy[j]);
               const float z = fmaf(y, sc[e], sh[e]);
-              const float dz = (!bw.relu || z > 0.f) ? g : 0.f;
-              S[e] += dz;
-              Q[e] = fmaf(dz, y, Q[e]);
+              dzv[hh] = (!bw.relu || z > 0.f) ? g : 0.f;
+              yv2[hh] = y;
             }
+            const uint64_t d2 = f2_pack(dzv[0], dzv[1]);
+            S2[j] = f2_add(S2[j], d2);
+            Q2[j] = f2_fma(d2, f2_pack(yv2[0], yv2[1]), Q2[j]);
           }
         }
       }
     }
+  }
+  float S[8], Q[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f2_unpack(S2[j], S[2 * j], S[2 * j + 1]);
+    f2_unpack(Q2[j], Q[2 * j], Q[2 * j + 1]);
   }
   if (DEFER) {
 #pragma unroll
