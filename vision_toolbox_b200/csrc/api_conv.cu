@@ -89,7 +89,9 @@ static ConvTiling plan_conv_tiling(long long M, int ncols, int total_k16) {
   // staged output panels: at most 32 columns (the 16 epilogue warps each stage 32 rows x 64 B), and at least two
   // panels per accumulator so that all four epilogue groups have work
   t.panel_w = std::min(32, chunk_of(t.block_n));
-  if (t.block_n / t.panel_w < 2 && t.panel_w > 16) t.panel_w /= 2;
+  // (narrow tiles, block_n <= 64, run the tile-parallel epilogue: whole 32-column panels, 64-byte row segments)
+  static const bool tp_ok = !(getenv("VTB_TILE_PAR") && atoi(getenv("VTB_TILE_PAR")) == 0);
+  if (!(tp_ok && t.block_n <= 64) && t.block_n / t.panel_w < 2 && t.panel_w > 16) t.panel_w /= 2;
   t.n_blocks = ncols / t.block_n;
   // 256-row tiles halve the weight traffic per FLOP and double the bytes per TMA request; use them whenever
   // there are enough of them to occupy most of the machine

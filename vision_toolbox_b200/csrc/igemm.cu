@@ -306,7 +306,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps);   // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), p.tile_par ? kEpiWarps / 2 : kEpiWarps);   // one arrival per epilogue warp that drains the set
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -471,9 +471,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t lt = 0;
     long long w_tfull = 0, t_ld = 0, t_cvt = 0, t_drain = 0;
     // work split: with two halves each group drains its own half; with one half the groups take alternate panels
-    const int my_half = (halves == 2) ? (grp >> 1) : 0;
-    const int pi_first = (halves == 2) ? (grp & 1) : grp;
-    const int pi_step = (halves == 2) ? 2 : 4;
+    // tile-parallel mode: the group pair gp = grp >> 1 owns every second tile (and TMEM set gp); inside the pair the two
+    // groups split the halves of a 256-row tile, or alternate panels of a 128-row one
+    const bool tp = p.tile_par != 0;
+    const int gp = tp ? (grp >> 1) : 0;
+    const int my_half = (halves == 2) ? (tp ? (grp & 1) : (grp >> 1)) : 0;
+    const int pi_first = (halves == 2) ? (tp ? 0 : (grp & 1)) : (tp ? (grp & 1) : grp);
+    const int pi_step = (halves == 2) ? (tp ? 1 : 2) : (tp ? 2 : 4);
     // rows of the staged panel this lane writes out (panel_drain): row group rg, rows rg*CH .. rg*CH + CH-1
     constexpr int drain_ch = CH;
     const int drain_row0 = quarter * 32 + (lane / drain_ch) * drain_ch;
@@ -491,7 +495,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     // TMEM: this warp's lane quarter and accumulator half
     const uint32_t tm_h = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(my_half * ksplit) * acc_stride;
-    for (int m_blk = m_first; m_blk < num_m_blocks; m_blk += m_step, ++lt) {
+    const int lt_step = tp ? 2 : 1;
+    lt = (uint32_t)gp;
+    for (int m_blk = m_first + gp * m_step; m_blk < num_m_blocks; m_blk += m_step * lt_step, lt += lt_step) {
       const int h = my_half;
       const uint32_t set = (nsets == 2u) ? (lt & 1u) : 0u;
       const uint32_t use = (nsets == 2u) ? (lt >> 1) : lt;
@@ -680,10 +686,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         a0.y = accQ[0];
       }
       const int et = threadIdx.x - 128;             // 0..511 over the 16 epilogue warps
-      const int nslices = halves * 4;
+      const int nslices = halves * 4 * (tp ? 2 : 1);
       float2* slots = reinterpret_cast<float2*>(smem_raw + (panel_base - smem_u32(smem_raw)));   // [8][block_n]
       named_bar_sync(1, kEpiWarps * 32);            // every warp is done with its staging buffer
-      const int q8 = my_half * 4 + quarter;
+      const int q8 = (gp * halves + my_half) * 4 + quarter;
       for (int pi = pi_first; pi < npanels; pi += pi_step) {
         const int lpi = (pi - pi_first) / pi_step;
         const float4 o4 = (lpi < 2) ? a0 : a1;
@@ -880,6 +886,11 @@ void fill_derived(ConvIgemmParams& p, int grid) {
   p.acc_stride = (uint32_t)((p.block_n + 31) & ~31);
   p.set_cols = (uint32_t)(p.halves * p.ksplit) * p.acc_stride;
   p.nsets = (2u * p.set_cols <= 512u) ? 2u : 1u;
+  {
+    static const bool tp_ok = !(getenv("VTB_TILE_PAR") && atoi(getenv("VTB_TILE_PAR")) == 0);
+    // narrow tiles only: each epilogue warp then owns <= 2 panels per tile (its running statistics live in 8 registers)
+    p.tile_par = (tp_ok && p.nsets == 2u && p.block_n <= 64 && p.block_n / p.panel_w <= (p.halves == 2 ? 2 : 4)) ? 1 : 0;
+  }
   p.a_stage = L.a_stage;
   p.b_stage = L.b_stage;
   p.b_off = L.b_off;
@@ -1154,7 +1165,9 @@ int launch_conv_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   const size_t smem = conv_igemm_smem_bytes(p.block_m, p.block_n, p.num_stages, p.panel_bufs);
   if (p.fin_rows <= 0) p.fin_rows = p.m_step;
   // one local panel per epilogue warp; 1x1 layers only (measured: the 3x3 32->32 layer loses 6 % to the extra registers)
-  const bool one_panel = p.a_tiled && (p.block_n / p.panel_w) <= (p.halves == 2 ? 2 : 4);
+  const int local_panels = p.tile_par ? ((p.block_n / p.panel_w + (p.halves == 2 ? 0 : 1)) / (p.halves == 2 ? 1 : 2))
+                                      : ((p.block_n / p.panel_w + (p.halves == 2 ? 1 : 3)) / (p.halves == 2 ? 2 : 4));
+  const bool one_panel = p.a_tiled && local_panels <= 1;
   static const bool defer_ok = !(getenv("VTB_STATS_DEFER") && atoi(getenv("VTB_STATS_DEFER")) == 0);
   const int epi = p.bwd_y[0] != nullptr ? kEpiBwd
                   : (p.stats_partial != nullptr ? ((one_panel && defer_ok) ? kEpiStats1 : kEpiStats)

@@ -44,6 +44,10 @@ struct ConvIgemmParams {
   // values derived on the host (fill_derived) so that no kernel role has to keep division results in registers
   int halves, n_blocks, num_m_blocks, m_step, chunks_per_tap, total_chunks, subs_per_stage, num_k_stages;
   uint32_t acc_stride, set_cols, nsets;                          // TMEM layout
+  // tile-parallel epilogue (narrow tiles, two TMEM sets): epilogue groups {0,1} drain the even tiles of the CTA (set 0),
+  // groups {2,3} the odd ones (set 1) - two tiles' TMEM -> staging -> global chains overlap instead of one tile being
+  // cut into panels too small to hide the chain's latency
+  int tile_par;
   uint32_t a_stage, b_stage, b_off, panel_off, bar_off;          // shared-memory layout (bytes from the aligned base)
   uint32_t a_sub_bytes, a_half_bytes, b_sub_bytes;
   int Wq, Hp;       // output-pixel lattice (q fastest, then p, then image)
