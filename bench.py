@@ -393,7 +393,14 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # the SyncBN kernels leave VTB_SM_RESERVE (16) SMs free for the gradient all-reduce: keep NCCL inside them
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(os.environ.get("VTB_SM_RESERVE", "16"))
+        except Exception:  # noqa: BLE001 - older / different torch builds: NCCL's default
+            opts = None
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     W = max(args.warmup, 3)
     K = args.steps
 
@@ -510,9 +517,8 @@ def main() -> None:
     sides = [getattr(r, "_side", None) for r in runners]
     for r in runners:
         r._side = None          # instrumented step: one stream, so that every event pair brackets exactly one kernel family
-    if rank == 0:
-        for r in runners:
-            r.L = prof
+    for r in runners:
+        r.L = prof       # EVERY rank runs the instrumented step (same host pacing on all ranks); rank 0 reports it
     barrier()
     torch.cuda._sleep(30_000_000)  # let the host run ahead so event intervals contain no launch gaps
     trainer._step_eager(dev_x[0], dev_y[0])   # eager on purpose: per-call events cannot be recorded inside a graph replay

@@ -998,7 +998,21 @@ int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long lo
       !scale || !shift || !mean || !invstd || !partial || !sync || count <= 0)
     return fail(VTB_EINVAL, "vtb_bn_bwd_fused: bad arguments");
   int c8 = c / 8;
-  const EwGeom g = bwd_fused_geom(pixels, c8);
+  EwGeom g = bwd_fused_geom(pixels, c8);
+  if (peers != nullptr) {
+    // SyncBN: every block of this launch stays resident while the chunk's block 0 waits for the peers' sums.  A launch
+    // that holds EVERY SM can close a cross-rank wait cycle with a collective on another stream (rank A: this kernel
+    // resident, spinning for rank B; rank B: its NCCL kernel resident, waiting for A's NCCL kernel, which finds no SM
+    // on A; B's copy of this kernel cannot become co-resident next to B's NCCL blocks) - observed at 8 GPUs when one rank
+    // ran ahead of the others.  Leave VTB_SM_RESERVE SMs (default 16; create the NCCL communicator with max_ctas <= that)
+    // to whatever else must be able to start.
+    static const int reserve = [] {
+      const char* v = getenv("VTB_SM_RESERVE");
+      return v ? std::max(0, atoi(v)) : 16;
+    }();
+    const int cap = std::max(1, (std::max(1, num_sms()) - reserve) / g.chunks);
+    g.rows = std::min(g.rows, cap);
+  }
   if (g.chunks > 60) return fail(VTB_EINVAL, "vtb_bn_bwd_fused: too many channels");
   if (peers && !sync_args_ok(peers, c)) return fail(VTB_EINVAL, "vtb_bn_bwd_fused: bad SyncBN peers");
   SyncPeers sp = make_sync_peers(peers);
