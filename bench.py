@@ -394,12 +394,9 @@ def main() -> None:
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the SyncBN kernels leave VTB_SM_RESERVE (16) SMs free for the gradient all-reduce: keep NCCL inside them
-        opts = None
-        try:
-            opts = dist.ProcessGroupNCCL.Options()
-            opts.config.max_ctas = int(os.environ.get("VTB_SM_RESERVE", "16"))
-        except Exception:  # noqa: BLE001 - older / different torch builds: NCCL's default
-            opts = None
+        from vision_toolbox_b200.parallel import nccl_pg_options
+
+        opts = nccl_pg_options()
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     W = max(args.warmup, 3)
     K = args.steps

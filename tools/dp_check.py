@@ -58,7 +58,9 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    from vision_toolbox_b200.parallel import nccl_pg_options
+
+    dist.init_process_group("nccl", device_id=dev, pg_options=nccl_pg_options())
     nb = 8
     g = torch.Generator().manual_seed(7)
     X = torch.rand(nb * world, 3, 64, 64, generator=g).to(dev)

@@ -378,6 +378,24 @@ static WgradPlan plan_wgrad(const VtbConv* c) {
     const int waste = tiles * bpt - w.total_boxes;
     if (waste < best_waste) { best_waste = waste; best_bpt = bpt; best_tiles = tiles; }
   }
+  if (taps == 1) {
+    // 1x1 layers: the output is tiny (cout x cin) and the pixel axis carries all the parallelism, so the split count -
+    // and with it the fp32 partial traffic (splits x cout x cin x 4 B written, then read by the reduce kernel) - is what
+    // the tile width decides.  Measured (profiles/r02_wgrad_boxes_sweep.txt): the optimum keeps >= ~2500 pixels per split;
+    // e.g. 256->256 @11^2: 2 tiles x 74 splits 27.4 us, 8 tiles x 18 splits 15.5 us.  Widest tile that still does.
+    const int kpix_guess = 128;
+    const long long kblocks = (w.mpix + kpix_guess - 1) / kpix_guess;
+    int pick = 1;
+    for (int b = std::min(max_boxes, w.total_boxes); b >= 1; --b) {
+      if (w.total_boxes % b) continue;
+      const int tiles = (w.total_boxes / b) * ((c->cout + 127) / 128);
+      long long sp = std::max(1, sms / tiles);
+      sp = std::min<long long>(sp, std::max<long long>(1, kblocks / 2));
+      if (w.mpix / sp >= 2500) { pick = b; break; }
+    }
+    best_bpt = std::min(pick, w.total_boxes);
+    best_tiles = (w.total_boxes + best_bpt - 1) / best_bpt;
+  }
   static const int o_bpt = env_int("VTB_WG_BOXES");
   if (o_bpt > 0 && o_bpt <= max_boxes) { best_bpt = std::min(o_bpt, w.total_boxes); best_tiles = (w.total_boxes + best_bpt - 1) / best_bpt; }
   w.boxes_per_tile = best_bpt;

@@ -999,17 +999,17 @@ int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long lo
     return fail(VTB_EINVAL, "vtb_bn_bwd_fused: bad arguments");
   int c8 = c / 8;
   EwGeom g = bwd_fused_geom(pixels, c8);
+  // SyncBN: every block of this launch stays resident while the chunk's block 0 waits for the peers' sums.  A launch
+  // that holds EVERY SM can close a cross-rank wait cycle with a collective on another stream (rank A: this kernel
+  // resident, spinning for rank B; rank B: its NCCL kernel resident, waiting for A's NCCL kernel, which finds no SM
+  // on A; B's copy of this kernel cannot become co-resident next to B's NCCL blocks) - observed at 8 GPUs when one rank
+  // ran ahead of the others.  Leave VTB_SM_RESERVE SMs (default 16; create the NCCL communicator with max_ctas <= that,
+  // parallel.nccl_pg_options) to whatever else must be able to start.
+  static const int reserve = [] {
+    const char* v = getenv("VTB_SM_RESERVE");
+    return v ? std::max(0, atoi(v)) : 16;
+  }();
   if (peers != nullptr) {
-    // SyncBN: every block of this launch stays resident while the chunk's block 0 waits for the peers' sums.  A launch
-    // that holds EVERY SM can close a cross-rank wait cycle with a collective on another stream (rank A: this kernel
-    // resident, spinning for rank B; rank B: its NCCL kernel resident, waiting for A's NCCL kernel, which finds no SM
-    // on A; B's copy of this kernel cannot become co-resident next to B's NCCL blocks) - observed at 8 GPUs when one rank
-    // ran ahead of the others.  Leave VTB_SM_RESERVE SMs (default 16; create the NCCL communicator with max_ctas <= that)
-    // to whatever else must be able to start.
-    static const int reserve = [] {
-      const char* v = getenv("VTB_SM_RESERVE");
-      return v ? std::max(0, atoi(v)) : 16;
-    }();
     const int cap = std::max(1, (std::max(1, num_sms()) - reserve) / g.chunks);
     g.rows = std::min(g.rows, cap);
   }
@@ -1041,9 +1041,13 @@ int vtb_bn_bwd_fused(const void* dout, int lddo, const void* y, int ldy, long lo
   // weight-gradient GEMM on the side stream) finishes without waiting for this one, so every block becomes resident and
   // the hand-rolled grid barrier cannot deadlock - while the launch itself is cheaper than a cooperative one and its
   // blocks may take SMs as the previous kernel drains.  With SyncBN peers (cross-rank spin inside the kernel, NCCL
-  // kernels on another stream) the co-residency GUARANTEE of the cooperative launch is kept.  VTB_BWD_COOP=1 forces it.
-  static const bool force_coop = getenv("VTB_BWD_COOP") != nullptr && atoi(getenv("VTB_BWD_COOP")) != 0;
-  if (peers == nullptr && !force_coop) {
+  // kernels on another stream) the co-residency GUARANTEE of the cooperative launch is kept; it is also the faster one
+  // there (2 GPUs, weight gradients on the side stream: 14.77 ms per step against 14.96 ms with the ordinary launch,
+  // whose early-resident blocks spin on SMs the weight-gradient CTAs could use; profiles/r02_bench_2gpu_t11*.json).
+  // VTB_BWD_COOP=1 forces the cooperative launch everywhere, VTB_BWD_COOP=0 the ordinary one (needs the SM reserve).
+  static const int coop_env = getenv("VTB_BWD_COOP") ? atoi(getenv("VTB_BWD_COOP")) : -1;
+  const bool coop = coop_env == 1 || (peers != nullptr && !(coop_env == 0 && reserve > 0));
+  if (!coop) {
     cudaError_t e;
     if (relu)
       e = launch_pdl(bn_bwd_fused_kernel<true>, grid, block, sm, (cudaStream_t)stream, dout_p, lddo, y_p, ldy, pixels, c8, cv,

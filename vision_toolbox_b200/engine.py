@@ -671,13 +671,17 @@ class Runner:
         self._conv_ops = [op for op in graph.ops if op.kind == "conv"]
         # Weight-gradient GEMMs on a second stream (VTB_WGRAD_STREAM=0 switches it off): wgrad(i) only needs dy(i) and
         # x(i), so it fills the ramp-up / tail bubbles of the dependent chain bn_bwd -> dgrad -> bn_bwd ... on the main
-        # stream (15.47 -> 15.16 ms per CSPDarknet-53 step).  Single-process plans only: with more than one rank the
-        # SyncBN exchange kernels spin on their peers while holding SM resources, NCCL kernels wait on theirs, and a
-        # third stream that both depend on closes a cross-rank wait cycle (observed: exchange timeout at 2 GPUs).
+        # stream (15.47 -> 15.16 ms per CSPDarknet-53 step; with SyncBN it also fills the exchange waits: 15.15 -> 14.78 ms
+        # at 2 GPUs).  With more than one rank it needs the SM reserve (VTB_SM_RESERVE > 0, parallel.nccl_pg_options):
+        # without it a SyncBN kernel spinning for its peers on every SM, an NCCL kernel waiting for its peer and a third
+        # stream both depend on closed a cross-rank wait cycle (exchange timeout at 2 GPUs).  VTB_WGRAD_STREAM_MULTI=0
+        # keeps multi-rank plans on one stream.
         self._side = None
         multi_rank = dist_cfg is not None and dist_cfg.world > 1
+        multi_ok = (_os.environ.get("VTB_WGRAD_STREAM_MULTI", "1") == "1"
+                    and _os.environ.get("VTB_SM_RESERVE", "16").strip() not in ("0", ""))
         if (_os.environ.get("VTB_WGRAD_STREAM", "1") == "1" and not graph.f32 and device.type == "cuda"
-                and not multi_rank):
+                and (not multi_rank or multi_ok)):
             self._side = torch.cuda.Stream(device)
         self._dy_slots = 3 if self._side is not None else 1
         self._dy_free: list = []

@@ -80,6 +80,36 @@ class _HeadCEFn(torch.autograd.Function):
         return df, (None if direct else dW), (None if direct else db), None, None, None
 
 
+def sm_reserve() -> int:
+    """SMs the SyncBN kernels leave free for whatever else must be able to start (``VTB_SM_RESERVE``, default 16; the
+    library reads the same variable: csrc/elementwise.cu ``vtb_bn_bwd_fused``)."""
+    import os
+
+    try:
+        return max(0, int(os.environ.get("VTB_SM_RESERVE", "16")))
+    except ValueError:
+        return 16
+
+
+def nccl_pg_options():
+    """``pg_options`` for ``dist.init_process_group("nccl", ...)``: keeps NCCL's kernels within the SMs that the SyncBN
+    kernels leave free (``max_ctas`` = ``sm_reserve()``).  A SyncBN kernel that spins for its peers while holding every
+    SM, and a collective on another stream that cannot start next to it, can close a cross-rank wait cycle (seen at 8
+    GPUs); with the reserve NCCL can always start.  Returns None when the reserve is 0 or this torch build has no such
+    option (NCCL's defaults then apply)."""
+    import torch.distributed as dist
+
+    r = sm_reserve()
+    if r <= 0:
+        return None
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = r
+        return opts
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def split_decay_groups(modules: list[nn.Module]):
     """classifier.py:141-169 — weight decay on conv / linear weights only, none on norm parameters and biases."""
     decay, no_decay = [], []
