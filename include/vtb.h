@@ -339,7 +339,8 @@ int vtb_ese_bwd(const void* x, int ldx, int n, int hw, int c, const float* weigh
  * fwd: pooled [n][c] fp32 (spatial mean), logits [n][k] = pooled . weight^T + bias (fp32), row_loss [n], loss[0] = mean,
  *      dlogits [n][k] = d loss / d logits (saved for backward).  labels: int64 class indices.  4 launches.
  * bwd: dweight [k][c] (+)=, dbias [k] (+)=, df (NHWC bf16 view, may be NULL) = d loss / d f, all scaled by *gscale (the
- *      upstream gradient of the scalar loss; NULL = 1).  scratch: n*k + n*c floats.  5 launches. */
+ *      upstream gradient of the scalar loss; NULL = 1: it rides in the GEMMs' alpha).  scratch: n*k + n*c floats (only the
+ *      last n*c are used).  4 launches.  The three GEMMs run fp32 FMA tiles (BM x 64 x 16, BM = 32 | 64). */
 int vtb_head_ce_fwd(const void* f, int ldf, int n, int hw, int c, const float* weight, const float* bias, int k,
                     const long long* labels, float label_smoothing, float* pooled, float* logits, float* dlogits,
                     float* row_loss, float* loss, void* stream);

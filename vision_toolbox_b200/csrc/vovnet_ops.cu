@@ -243,6 +243,118 @@ small_gemm_kernel(const float* __restrict__ a, long long sai, long long sak, con
       }
     }
 }
+// ------------------------------------------------------------------ fp32 GEMM for the classifier head
+// C[i][j] = alpha * sum_k A(i,k) * B(k,j) with strided operands as above; BM x 64 tiles (BM = 32 | 64), 16-deep k steps,
+// 256 threads x (BM/16 x 4) results: 8 | 16 FMAs per pair of 16-byte shared-memory loads (the 32x32 kernel above issues
+// one load per FMA), next k step's operands prefetched into registers while the current one is multiplied.
+// alpha_dev (optional): device scalar multiplied into alpha (the upstream gradient of the loss).
+// EPI 0: store; 2: accumulate-or-store; 3: + bias[j]
+template <int BM, int EPI>
+__global__ void __launch_bounds__(256)
+tile_gemm_kernel(const float* __restrict__ a, long long sai, long long sak, const float* __restrict__ b, long long sbk,
+                 long long sbj, int M, int N, int K, float alpha, const float* __restrict__ alpha_dev,
+                 float* __restrict__ out, long long ldc, const float* __restrict__ bias, int accumulate) {
+  constexpr int BN = 64, BK = 16, RM = BM / 16, LA = BM * BK / 256, LB = BN * BK / 256;
+  pdl_wait();
+  pdl_trigger();
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  const bool a_kfast = (sak == 1), b_kfast = (sbk == 1);
+  float ra[LA], rb[LB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < LA; ++u) {
+      const int e = t + u * 256;
+      const int kk = a_kfast ? (e % BK) : (e / BM), ii = a_kfast ? (e / BK) : (e % BM);
+      const int gi = i0 + ii, gk = k0 + kk;
+      ra[u] = (gi < M && gk < K) ? __ldg(a + gi * sai + gk * sak) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int e = t + u * 256;
+      const int kk = b_kfast ? (e % BK) : (e / BN), jj = b_kfast ? (e / BK) : (e % BN);
+      const int gj = j0 + jj, gk = k0 + kk;
+      rb[u] = (gj < N && gk < K) ? __ldg(b + gk * sbk + gj * sbj) : 0.f;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < LA; ++u) {
+      const int e = t + u * 256;
+      const int kk = a_kfast ? (e % BK) : (e / BM), ii = a_kfast ? (e / BK) : (e % BM);
+      As[kk][ii] = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int e = t + u * 256;
+      const int kk = b_kfast ? (e % BK) : (e / BN), jj = b_kfast ? (e / BK) : (e % BN);
+      Bs[kk][jj] = rb[u];
+    }
+  };
+  float acc[RM][4];
+#pragma unroll
+  for (int u = 0; u < RM; ++u)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) acc[u][w] = 0.f;
+  fetch(0);
+  stash();
+  __syncthreads();
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const bool more = k0 + BK < K;
+    if (more) fetch(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[RM];
+      if constexpr (RM == 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        av[0] = a4.x; av[1] = a4.y; av[RM - 2] = a4.z; av[RM - 1] = a4.w;
+      } else {
+        const float2 a2 = *reinterpret_cast<const float2*>(&As[kk][ty * 2]);
+        av[0] = a2.x; av[1] = a2.y;
+      }
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+#pragma unroll
+      for (int u = 0; u < RM; ++u) {
+        acc[u][0] = fmaf(av[u], b4.x, acc[u][0]);
+        acc[u][1] = fmaf(av[u], b4.y, acc[u][1]);
+        acc[u][2] = fmaf(av[u], b4.z, acc[u][2]);
+        acc[u][3] = fmaf(av[u], b4.w, acc[u][3]);
+      }
+    }
+    __syncthreads();
+    if (more) {
+      stash();
+      __syncthreads();
+    }
+  }
+  const float al = alpha * (alpha_dev ? __ldg(alpha_dev) : 1.f);
+#pragma unroll
+  for (int u = 0; u < RM; ++u)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int gi = i0 + ty * RM + u, gj = j0 + tx * 4 + w;
+      if (gi >= M || gj >= N) continue;
+      float* dst = out + gi * ldc + gj;
+      const float v = acc[u][w] * al;
+      if (EPI == 3) *dst = v + bias[gj];
+      else if (EPI == 2) *dst = accumulate ? *dst + v : v;
+      else *dst = v;
+    }
+}
+// db[j] (+)= (*gscale) * sum_i dl[i][j]   (classifier head bias gradient)
+__global__ void head_dbias_kernel(const float* __restrict__ dl, int n, int k, const float* __restrict__ gscale,
+                                  float* __restrict__ db, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  float acc = 0.f;
+  for (int i = 0; i < n; ++i) acc += dl[(long long)i * k + j];
+  acc *= gscale ? __ldg(gscale) : 1.f;
+  db[j] = accumulate ? db[j] + acc : acc;
+}
 // db[co] (+)= sum_n dz[n][co]
 __global__ void ese_dbias_kernel(const float* __restrict__ dz, int n, int c, float* __restrict__ db, int accumulate) {
   pdl_wait();
@@ -471,16 +583,6 @@ __global__ void __launch_bounds__(256) head_loss_mean_kernel(const float* __rest
   if (threadIdx.x == 0) *loss = s / (float)n;
 }
 
-// out = in * (*gscale)   (upstream gradient of the scalar loss; gscale == nullptr: 1)
-__global__ void head_scale_kernel(const float* __restrict__ in, const float* __restrict__ gscale, long long total,
-                                  float* __restrict__ out) {
-  pdl_wait();
-  pdl_trigger();
-  const float g = gscale ? *gscale : 1.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-    out[i] = in[i] * g;
-}
-
 // df[n][pixel][c] = dpooled[n][c]   (gradient of the spatial mean; dpooled already carries the 1/hw factor)
 __global__ void head_broadcast_kernel(const float* __restrict__ dpooled, int hw, long long pixels, int c8,
                                       __nv_bfloat16* __restrict__ df, int lddf) {
@@ -614,8 +716,8 @@ int vtb_head_ce_fwd(const void* f, int ldf, int n, int hw, int c, const float* w
   launch_pdl(hw_reduce_kernel<false>, dim3((c8 + 31) / 32, n), dim3(256), 0, st, (const __nv_bfloat16*)f, ldf,
              (const __nv_bfloat16*)nullptr, 0, hw, c8, pooled, c, 1.f / (float)hw);
   // logits[n][k] = pooled[n][:] . weight[k][:] + bias[k]
-  launch_pdl(small_gemm_kernel<false, false, 3>, dim3((k + 31) / 32, (n + 31) / 32), dim3(256), 0, st, (const float*)pooled,
-             (long long)c, 1LL, weight, 1LL, (long long)c, n, k, c, 1.f, logits, (long long)k, bias, (float*)nullptr, 0);
+  launch_pdl(tile_gemm_kernel<32, 3>, dim3((k + 63) / 64, (n + 31) / 32), dim3(256), 0, st, (const float*)pooled, (long long)c,
+             1LL, weight, 1LL, (long long)c, n, k, c, 1.f, (const float*)nullptr, logits, (long long)k, bias, 0);
   launch_pdl(head_ce_kernel, dim3(n), dim3(256), 0, st, (const float*)logits, k, labels, label_smoothing, 1.f / (float)n, dlogits,
              row_loss);
   launch_pdl(head_loss_mean_kernel, dim3(1), dim3(256), 0, st, (const float*)row_loss, n, loss);
@@ -630,21 +732,17 @@ int vtb_head_ce_bwd(const float* pooled, const float* dlogits, const float* weig
       (df && !VVIEW_OK(df, lddf, c)))
     return fail(VTB_EINVAL, "vtb_head_ce_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  const long long nk = (long long)n * k;
-  float* dl = scratch;                 // [n][k]  dlogits * upstream gradient
-  float* dpooled = scratch + nk;       // [n][c]
-  launch_pdl(head_scale_kernel, dim3(vgrid(nk, 256)), dim3(256), 0, st, dlogits, gscale, nk, dl);
-  // dweight[k][c] (+)= sum_n dl[n][k] * pooled[n][c]
-  launch_pdl(small_gemm_kernel<false, false, 2>, dim3((c + 31) / 32, (k + 31) / 32), dim3(256), 0, st, (const float*)dl, 1LL,
-             (long long)k, pooled, (long long)c, 1LL, k, c, n, 1.f, dweight, (long long)c, (const float*)nullptr, (float*)nullptr,
-             accumulate);
-  launch_pdl(ese_dbias_kernel, dim3((k + 255) / 256), dim3(256), 0, st, (const float*)dl, n, k, dbias, accumulate);
-  int launches = 3;
+  // the upstream gradient of the scalar loss (gscale, a device scalar) rides in the GEMMs' alpha: no scaling pass
+  float* dpooled = scratch + (long long)n * k;   // [n][c]  (the first n*k floats of scratch are unused since round 2)
+  // dweight[k][c] (+)= g * sum_n dlogits[n][k] * pooled[n][c]
+  launch_pdl(tile_gemm_kernel<64, 2>, dim3((c + 63) / 64, (k + 63) / 64), dim3(256), 0, st, dlogits, 1LL, (long long)k, pooled,
+             (long long)c, 1LL, k, c, n, 1.f, gscale, dweight, (long long)c, (const float*)nullptr, accumulate);
+  launch_pdl(head_dbias_kernel, dim3((k + 127) / 128), dim3(128), 0, st, dlogits, n, k, gscale, dbias, accumulate);
+  int launches = 2;
   if (df != nullptr) {
-    // dpooled[n][c] = (1/hw) * sum_k dl[n][k] * weight[k][c]
-    launch_pdl(small_gemm_kernel<false, false, 0>, dim3((c + 31) / 32, (n + 31) / 32), dim3(256), 0, st, (const float*)dl,
-               (long long)k, 1LL, weight, (long long)c, 1LL, n, c, k, 1.f / (float)hw, dpooled, (long long)c,
-               (const float*)nullptr, (float*)nullptr, 0);
+    // dpooled[n][c] = (g / hw) * sum_k dlogits[n][k] * weight[k][c]
+    launch_pdl(tile_gemm_kernel<32, 0>, dim3((c + 63) / 64, (n + 31) / 32), dim3(256), 0, st, dlogits, (long long)k, 1LL, weight,
+               (long long)c, 1LL, n, c, k, 1.f / (float)hw, gscale, dpooled, (long long)c, (const float*)nullptr, 0);
     const long long pixels = (long long)n * hw;
     launch_pdl(head_broadcast_kernel, dim3(vgrid(pixels * (c / 8), 256)), dim3(256), 0, st, (const float*)dpooled, hw, pixels,
                c / 8, (__nv_bfloat16*)df, lddf);

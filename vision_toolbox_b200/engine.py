@@ -663,6 +663,7 @@ class Runner:
         self.L = _lib.lib()
         self.dist: Optional[DistConfig] = dist_cfg
         self.grad_sink = False
+        self.last_all_direct = False
         # ticket counters of the fused conv + BatchNorm-finalize kernels (self-cleaning, shared by all layers)
         self.tickets = torch.zeros(512, dtype=torch.int32, device=device)   # [0,256): conv kernels, [256,512): BN bwd
         # element type of the activation / gradient arenas and the entry points whose two precisions share a signature
@@ -1145,6 +1146,9 @@ class Runner:
                 pgrads.append(torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format))
                 direct.append(False)
         world = self.dist.world if (self.dist is not None and self.dist.sync_bn) else 1
+        # every parameter gradient of this backward OVERWRITES the caller's .grad storage (parallel.Trainer then skips
+        # zeroing its flat gradient buffer)
+        self.last_all_direct = bool(self.grad_sink and all(direct))
 
         # which gradient memory is already valid: buffer idx -> list of (c0, c1)
         init: dict[int, list[tuple[int, int]]] = {}

@@ -238,11 +238,14 @@ class Trainer:
         self.graph_launches = 0
         import os
 
-        # classifier head + loss through the C ABI (vtb_head_ce_*): correct (tests/test_gpu_parity.py) and 9 launches instead
-        # of ~35, but its fp32 SIMT GEMMs lose to cuBLAS on the 256 x 1000 x 1024 head: 15.10 vs 15.00 ms per step on the
-        # same box.  Off by default (VTB_NATIVE_HEAD=1 enables it) until the head GEMM runs on the tensor-core kernels.
-        self.native_head = (os.environ.get("VTB_NATIVE_HEAD", "0") == "1" and isinstance(head, nn.Linear)
-                            and head.bias is not None and head.weight.dtype == torch.float32)
+        # classifier head + loss through the C ABI (vtb_head_ce_*: pooling, 64-wide fp32 GEMM tiles, label-smoothed CE and
+        # their backward in 8 launches; parity: tests/test_gpu_parity.py) instead of ~35 torch / cuBLAS kernels, so that the
+        # step contains no library kernel.  VTB_NATIVE_HEAD=0 selects the torch composition.
+        self.native_head = (os.environ.get("VTB_NATIVE_HEAD", "1") == "1" and isinstance(head, nn.Linear)
+                            and head.bias is not None and head.weight.dtype == torch.float32
+                            and head.weight.device.type == "cuda")
+        self._zero_needed = True   # until a step has shown that every gradient is overwritten in place (see _step_eager)
+        self._used_native_head = False
         if process_group is not None:
             import torch.distributed as dist
 
@@ -335,15 +338,29 @@ class Trainer:
         f = self.backbone(x)  # (N, C, H, W) bf16 on CUDA
         if self.native_head and y.ndim == 1 and f.is_cuda and f.dtype == torch.bfloat16 and f.shape[1] % 8 == 0:
             # pooling + linear + label-smoothed CE in the native library (head gradients land in the flat buffer)
+            self._used_native_head = True
             return _HeadCEFn.apply(f, self.head.weight, self.head.bias, y, self.label_smoothing, True)
+        self._used_native_head = False
         pooled = f.float().mean(dim=(2, 3))  # AdaptiveAvgPool2d + Flatten (classifier.py:61-62)
         logits = self.head(pooled)
         return F.cross_entropy(logits, y, label_smoothing=self.label_smoothing)
 
+    def _all_grads_overwritten(self) -> bool:
+        """True when the step just run wrote EVERY gradient in place (native head + a native backbone plan in sink mode):
+        autograd accumulated nothing, so the flat buffer needs no zeroing before the next step (never-written entries keep
+        their initial zeros)."""
+        if not self._used_native_head:
+            return False
+        plans = self.backbone.__dict__.get("_vtb_plans", {})
+        runners = [r for r in plans.values() if r.g.need_grad]
+        return bool(runners) and all(r.last_all_direct for r in runners)
+
     def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        self.flat.zero_()
+        if self._zero_needed:
+            self.flat.zero_()
         loss = self.forward_loss(x, y)
         loss.backward()
+        self._zero_needed = not self._all_grads_overwritten()
         if self.world > 1:
             self._finish_exchange()
         self.opt.step()
