@@ -99,6 +99,25 @@ def test_bucket_ranges_cover_everything_in_order():
     assert all(e - a >= 100 for a, e in b[:-1])
 
 
+def test_overlap_bucket_ranges_keep_the_last_finishing_bucket_small():
+    """Backward completes the flat buffer from its end: the bucket at the start is the exposed one and must be small."""
+    sizes = [5, 100, 7, 300, 2, 2, 50]
+    for be, le in [(100, 10), (100, 120), (50, 1), (10_000, 10)]:
+        b = parallel.overlap_bucket_ranges(sizes, be, le)
+        assert b[0][0] == 0 and b[-1][1] == sum(sizes)
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        bounds = {0}
+        acc = 0
+        for s_ in sizes:
+            acc += s_
+            bounds.add(acc)
+        assert all(a in bounds and e in bounds for a, e in b)          # cut at parameter boundaries only
+        assert b[0][1] - b[0][0] <= max(le, sizes[0])                  # the exposed bucket is small
+        assert all(e - a >= min(be, sum(sizes) - b[0][1]) // 2 for a, e in b[1:])   # no confetti behind it
+    assert parallel.overlap_bucket_ranges([7], 100, 10) == [(0, 7)]
+    assert parallel.overlap_bucket_ranges([], 100, 10) == []
+
+
 def test_weight_decay_groups_follow_reference_rule():
     m, head = _model(0)
     decay, no_decay = parallel.split_decay_groups([m, head])

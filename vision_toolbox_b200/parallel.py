@@ -25,10 +25,11 @@ class _HeadCEFn(torch.autograd.Function):
 
     `f`: the backbone's last feature map - a logical (N, C, H, W) bf16 tensor with NHWC strides (what the native backbone
     returns).  `sink`: write the head's parameter gradients straight into the existing fp32 ``.grad`` tensors (Trainer's
-    flat all-reduce buffer, overwriting) instead of handing fresh tensors to autograd."""
+    flat all-reduce buffer, overwriting) instead of handing fresh tensors to autograd; `on_ready` is then told that they
+    are final (the gradient exchange of their bucket can start while the backbone's backward runs)."""
 
     @staticmethod
-    def forward(ctx, f, weight, bias, labels, label_smoothing: float, sink: bool):
+    def forward(ctx, f, weight, bias, labels, label_smoothing: float, sink: bool, on_ready=None):
         from . import _lib
         from ._lib import check
 
@@ -51,6 +52,7 @@ class _HeadCEFn(torch.autograd.Function):
         ctx.save_for_backward(pooled, dlogits, weight, bias)
         ctx.geom = (n, c, h, w, k)
         ctx.sink = sink
+        ctx.on_ready = on_ready   # callable([weight, bias]) once their gradients sit in .grad (Trainer's bucket overlap)
         ctx.need_df = f.requires_grad
         ctx.logits = logits
         return loss.view(())
@@ -77,7 +79,9 @@ class _HeadCEFn(torch.autograd.Function):
         check(L.vtb_head_ce_bwd(pooled.data_ptr(), dlogits.data_ptr(), weight.data_ptr(), n, h * w, c, k, g.data_ptr(),
                                 dW.data_ptr(), db.data_ptr(), 0, 0 if df is None else df.data_ptr(), c,
                                 scratch.data_ptr(), st), "vtb_head_ce_bwd")
-        return df, (None if direct else dW), (None if direct else db), None, None, None
+        if direct and ctx.on_ready is not None:
+            ctx.on_ready([weight, bias])
+        return df, (None if direct else dW), (None if direct else db), None, None, None, None
 
 
 def sm_reserve() -> int:
@@ -211,18 +215,51 @@ def bucket_ranges(sizes: list[int], bucket_elems: int) -> list[tuple[int, int]]:
     return out
 
 
+def overlap_bucket_ranges(sizes: list[int], bucket_elems: int, last_elems: int) -> list[tuple[int, int]]:
+    """Bucket layout for an exchange overlapped with backward.  Backward finishes parameters from the END of the flat
+    buffer towards its start, so the bucket at the START completes last and its all-reduce is the one nothing can hide:
+    it is kept small (about `last_elems`, cut at a parameter boundary); the rest is cut greedily from the end into buckets
+    of >= `bucket_elems` (the leftover joins the bucket next to the small one).  [(start, end)] in elements, ascending."""
+    total = sum(sizes)
+    if not sizes:
+        return []
+    head_end, j = 0, 0
+    while j < len(sizes) and (head_end == 0 or head_end + sizes[j] <= last_elems):
+        head_end += sizes[j]
+        j += 1
+    if head_end >= total:
+        return [(0, total)]
+    cuts, acc, end = [], 0, total
+    for s in reversed(sizes[j:]):
+        acc += s
+        if acc >= bucket_elems:
+            cuts.append((end - acc, end))
+            end -= acc
+            acc = 0
+    if acc > 0:
+        if cuts and acc < bucket_elems // 2:
+            a, e = cuts.pop()
+            cuts.append((head_end, e))       # a small leftover joins its neighbour
+        else:
+            cuts.append((head_end, end))
+    return [(0, head_end)] + cuts[::-1]
+
+
 class Trainer:
     """One data-parallel training step: forward, label-smoothed CE, backward, gradient mean, SGD.
 
     Gradient exchange: every parameter ``.grad`` is a view of ONE flat fp32 buffer, cut into ~``bucket_mb`` buckets.
     The native backward reports which parameter gradients are final (reverse layer order); as soon as a bucket is
     complete its all-reduce is enqueued on a side stream, so the exchange overlaps the rest of backward (what DDP's
-    reducer does for the reference, configs/base.yaml:19).  The head's bucket goes last.
+    reducer does for the reference, configs/base.yaml:19).  The native head reports its gradients first (they are the
+    first ones backward produces); the bucket that completes last - the stem side - is kept small (`last_bucket_mb`),
+    because its all-reduce is the only one that nothing overlaps.
     """
 
     def __init__(self, backbone: nn.Module, head: nn.Module, lr: float = 0.05, momentum: float = 0.9,
                  weight_decay: float = 2e-5, label_smoothing: float = 0.1, sync_bn: bool = True,
-                 process_group=None, bucket_mb: float = 25.0, mixup_cutmix: Optional[nn.Module] = None):
+                 process_group=None, bucket_mb: float = 25.0, mixup_cutmix: Optional[nn.Module] = None,
+                 last_bucket_mb: float = 1.0):
         self.backbone, self.head = backbone, head
         self.label_smoothing = label_smoothing
         # classifier.py:66-67, 86-87: RandomCutMixMixUp on the batch before the forward (vision_toolbox_b200.extras: sampled
@@ -267,7 +304,8 @@ class Trainer:
             off += n
         # the native backward writes backbone gradients straight into these views (engine.Runner grad_sink mode)
         backbone.__dict__["_vtb_grad_sink"] = True
-        self.buckets = bucket_ranges(sizes, int(bucket_mb * 1024 * 1024 / 4))
+        self.buckets = overlap_bucket_ranges(sizes, int(bucket_mb * 1024 * 1024 / 4),
+                                             int(min(last_bucket_mb, bucket_mb) * 1024 * 1024 / 4))
         # bucket bookkeeping for the overlap: parameters per bucket, the bucket of every parameter
         starts = [a for a, _ in self.buckets]
         self._bucket_of = {}
@@ -339,7 +377,8 @@ class Trainer:
         if self.native_head and y.ndim == 1 and f.is_cuda and f.dtype == torch.bfloat16 and f.shape[1] % 8 == 0:
             # pooling + linear + label-smoothed CE in the native library (head gradients land in the flat buffer)
             self._used_native_head = True
-            return _HeadCEFn.apply(f, self.head.weight, self.head.bias, y, self.label_smoothing, True)
+            ready = self._grads_ready if self.world > 1 else None
+            return _HeadCEFn.apply(f, self.head.weight, self.head.bias, y, self.label_smoothing, True, ready)
         self._used_native_head = False
         pooled = f.float().mean(dim=(2, 3))  # AdaptiveAvgPool2d + Flatten (classifier.py:61-62)
         logits = self.head(pooled)
