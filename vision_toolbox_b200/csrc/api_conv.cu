@@ -385,15 +385,19 @@ static WgradPlan plan_wgrad(const VtbConv* c) {
     // e.g. 256->256 @11^2: 2 tiles x 74 splits 27.4 us, 8 tiles x 18 splits 15.5 us.  Widest tile that still does.
     const int kpix_guess = 128;
     const long long kblocks = (w.mpix + kpix_guess - 1) / kpix_guess;
-    int pick = 1;
+    int pick = 0;
+    long long pick_px = -1;
     for (int b = std::min(max_boxes, w.total_boxes); b >= 1; --b) {
-      if (w.total_boxes % b) continue;
-      const int tiles = (w.total_boxes / b) * ((c->cout + 127) / 128);
+      const int nt = (w.total_boxes + b - 1) / b;
+      if ((nt * b - w.total_boxes) * 8 >= w.total_boxes) continue;   // > 12.5 % of the MMA columns would be padding
+      const int tiles = nt * ((c->cout + 127) / 128);
       long long sp = std::max(1, sms / tiles);
       sp = std::min<long long>(sp, std::max<long long>(1, kblocks / 2));
-      if (w.mpix / sp >= 2500) { pick = b; break; }
+      const long long px = w.mpix / sp;
+      if (px >= 2500) { pick = b; break; }
+      if (px > pick_px) { pick_px = px; pick = b; }                  // nothing qualifies: the fewest splits, widest first
     }
-    best_bpt = std::min(pick, w.total_boxes);
+    best_bpt = std::max(1, pick);
     best_tiles = (w.total_boxes + best_bpt - 1) / best_bpt;
   }
   static const int o_bpt = env_int("VTB_WG_BOXES");
@@ -921,6 +925,7 @@ static int wgrad_impl(const VtbConv* c, const void* dy, int lddy, const void* x,
   CUtensorMap tmDY, tmX;
   if (!tmap_tiled_2d(&tmDY, dy, c->cout, (uint64_t)w.mpix, (uint64_t)lddy * 2, w.ca, w.kpix, w.ca * 2))
     return fail(VTB_ECUDA, "vtb_conv_wgrad: tensor map for dy failed");
+  // (a tiled [pixels][cin] map for the X operand of 1x1 layers was measured: no difference, profiles/r02_wgrad_1x1_xtiled_sweep.txt)
   if (!tmap_im2col_nhwc(&tmX, x, c->cin, c->w, c->h, c->n, ldx, -c->pad, -c->pad, upper, upper, w.cc, w.kpix,
                         c->stride, w.cc * 2))
     return fail(VTB_ECUDA, "vtb_conv_wgrad: im2col tensor map for x failed");
