@@ -95,8 +95,13 @@ static ConvTiling plan_conv_tiling(long long M, int ncols, int total_k16) {
   t.n_blocks = ncols / t.block_n;
   // 256-row tiles halve the weight traffic per FLOP and double the bytes per TMA request; use them whenever
   // there are enough of them to occupy most of the machine
+  // Waves x tile time decides: a 256-row tile costs ~1.36x a 128-row one (the im2col request cadence does not depend on
+  // the box height), so 128-row tiles only win while all of them still fit ONE wave (profiles/r02_convs_vovnet_tiles.txt:
+  // 3x3 192->192 @14^2, 98 / 196 tiles: 20.3 us with 256 rows, 27.1 us with 128; 224->224 @7^2, 25 / 49 tiles: 24.6 / 18.1)
   const long long tiles256 = ((M + 255) / 256) * t.n_blocks;
-  t.block_m = (tiles256 * 4 >= (long long)sms * 3) ? 256 : 128;
+  const long long tiles128 = ((M + 127) / 128) * t.n_blocks;
+  const double cost256 = 1.36 * (double)((tiles256 + sms - 1) / sms), cost128 = (double)((tiles128 + sms - 1) / sms);
+  t.block_m = (cost256 <= cost128) ? 256 : 128;
   static const int o_bm = env_int("VTB_BLOCK_M");
   if (o_bm == 128 || o_bm == 256) t.block_m = o_bm;
   const long long tiles = ((M + t.block_m - 1) / t.block_m) * t.n_blocks;
