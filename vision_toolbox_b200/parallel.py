@@ -281,6 +281,7 @@ class Trainer:
         self.native_head = (os.environ.get("VTB_NATIVE_HEAD", "1") == "1" and isinstance(head, nn.Linear)
                             and head.bias is not None and head.weight.dtype == torch.float32
                             and head.weight.device.type == "cuda")
+        self._seed = None
         self._zero_needed = True   # until a step has shown that every gradient is overwritten in place (see _step_eager)
         self._used_native_head = False
         if process_group is not None:
@@ -398,7 +399,9 @@ class Trainer:
         if self._zero_needed:
             self.flat.zero_()
         loss = self.forward_loss(x, y)
-        loss.backward()
+        if self._seed is None or self._seed.device != loss.device or self._seed.dtype != loss.dtype:
+            self._seed = torch.ones((), dtype=loss.dtype, device=loss.device)
+        loss.backward(self._seed)   # a cached seed: autograd would launch a fill kernel for its own every step
         self._zero_needed = not self._all_grads_overwritten()
         if self.world > 1:
             self._finish_exchange()
