@@ -1,6 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-echo "=== memcheck: head kernels"; timeout 900 compute-sanitizer --tool memcheck --kernel-name regex:"tile_gemm|head_" python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "native_head" 2>&1 | tail -8 | tee gpurun_out/r02_sanitizer_memcheck_head.log
-echo "=== racecheck: head kernels"; timeout 900 compute-sanitizer --tool racecheck --kernel-name regex:"tile_gemm|head_" python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "native_head" 2>&1 | tail -8 | tee gpurun_out/r02_sanitizer_racecheck_head.log
+echo "=== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/r02_pytest_gpu_latest.log
+echo "=== bench default (optimizer overlap)"; timeout 300 python bench.py --no-cpu-baseline 2> gpurun_out/bench.err | tee gpurun_out/r02_bench_t14.json | cut -c1-200; tail -2 gpurun_out/bench.err
+echo "=== bench VTB_SGD_OVERLAP=0"; VTB_SGD_OVERLAP=0 timeout 300 python bench.py --no-cpu-baseline 2> gpurun_out/bench.err | tee gpurun_out/r02_bench_t14_nooverlap.json | cut -c1-200; tail -2 gpurun_out/bench.err
 echo done

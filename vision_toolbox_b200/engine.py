@@ -663,6 +663,7 @@ class Runner:
         self.L = _lib.lib()
         self.dist: Optional[DistConfig] = dist_cfg
         self.grad_sink = False
+        self.on_grads_ready = None   # single-process hook: callable(list[Parameter]) - gradients that are final
         self.last_all_direct = False
         # ticket counters of the fused conv + BatchNorm-finalize kernels (self-cleaning, shared by all layers)
         self.tickets = torch.zeros(512, dtype=torch.int32, device=device)   # [0,256): conv kernels, [256,512): BN bwd
@@ -737,13 +738,16 @@ class Runner:
         """(storage, version) of every convolution master weight of the plan."""
         return tuple((op.mod.conv.weight.data_ptr(), op.mod.conv.weight._version) for op in self._conv_ops)
 
-    def pack_job_table(self, srcs, sgd=None):
+    def pack_job_table(self, srcs, sgd=None, subset=None):
         """Device-resident VtbPackJob table of every convolution of the plan (+ the launches that walk it).  `sgd`:
-        callable(parameter) -> (gradient pointer, momentum pointer, weight decay) for vtb_sgd_pack_weights."""
+        callable(parameter) -> (gradient pointer, momentum pointer, weight decay) for vtb_sgd_pack_weights.  `subset`:
+        indices into the plan's convolutions (a table of just those, e.g. one gradient bucket)."""
         L = self.L
         convs = self._conv_ops
+        if subset is not None:
+            convs, srcs = [convs[i] for i in subset], [srcs[i] for i in subset]
         if True:
-            jobs = (_lib.VtbPackJob * len(convs))()
+            jobs = (_lib.VtbPackJob * max(1, len(convs)))()
             blk, launches = 0, []
             for j, (op, w) in enumerate(zip(convs, srcs)):
                 g = op.geom
@@ -1197,7 +1201,9 @@ class Runner:
 
         pending: list[tuple[TView, TView]] = []
         # gradient all-reduce overlap: only meaningful when gradients land directly in the caller's flat buffer
-        ready_cb = self.dist.on_grads_ready if (self.dist is not None and self.grad_sink and all(direct)) else None
+        # (single-process plans report too when the caller registered a hook: parallel.Trainer steps the optimizer per bucket)
+        hook = self.dist.on_grads_ready if self.dist is not None else self.on_grads_ready
+        ready_cb = hook if (self.grad_sink and all(direct)) else None
 
         def flush_pending(force_for: Optional[TView]) -> None:
             for item in list(pending):
@@ -1488,6 +1494,7 @@ def run_native(module: nn.Module, x: torch.Tensor) -> list[torch.Tensor]:
             plans.pop(next(iter(plans)))
     runner.dist = module.__dict__.get("_vtb_dist")
     runner.grad_sink = bool(module.__dict__.get("_vtb_grad_sink", False))
+    runner.on_grads_ready = module.__dict__.get("_vtb_on_grads_ready")
     with torch.cuda.device(x.device):
         if need_grad:
             outs = _NativeFn.apply(runner, x, *runner.g.params)

@@ -144,15 +144,22 @@ class NativeSGD:
         self.mom = {id(p): torch.zeros_like(p, memory_format=torch.contiguous_format) for p in params}
         self._runner = None
         self._tables = None
+        self._bucket_of, self._nb = {}, 1
+        self._done: set = set()
 
     def set_lr(self, lr: float) -> None:
         self.hyper[0] = lr
+
+    def set_buckets(self, bucket_of: dict, n: int) -> None:
+        """Group the parameters (id -> bucket index, `n` buckets): `step_bucket(b)` then updates one group on its own, so a
+        trainer can step every gradient bucket as soon as it is final (and reduced) while backward still runs."""
+        self._bucket_of, self._nb = dict(bucket_of), int(n)
+        self._tables = None
 
     def _build(self, runner) -> None:
         import ctypes as C
 
         from . import _lib
-        from ._lib import check
 
         L = _lib.lib()
         for p in self.params:
@@ -162,34 +169,48 @@ class NativeSGD:
         wd = lambda p: self.weight_decay if id(p) in self.decay_ids else 0.0
         packed = {id(op.mod.conv.weight) for op in runner._conv_ops}
         srcs = [op.mod.conv.weight.detach() for op in runner._conv_ops]
-        table, launches = runner.pack_job_table(
-            srcs, sgd=lambda p: (p.grad.data_ptr(), self.mom[id(p)].data_ptr(), wd(p)))
-        rest = [p for p in self.params if id(p) not in packed]
-        plain, blk, plain_launches = (_lib.VtbSgdJob * max(1, len(rest)))(), 0, []
-        for j, p in enumerate(rest):
-            plain[j] = _lib.VtbSgdJob(p.data_ptr(), p.grad.data_ptr(), self.mom[id(p)].data_ptr(), p.numel(), wd(p), blk)
-            blk += int(L.vtb_sgd_job_blocks(p.numel()))
-            if (j + 1) % 256 == 0 or j == len(rest) - 1:
-                plain_launches.append((j // 256 * 256, j % 256 + 1, blk))
-                blk = 0
-        ptab = torch.frombuffer(bytearray(bytes(plain)), dtype=torch.uint8).to(self.hyper.device)
+        sgd = lambda p: (p.grad.data_ptr(), self.mom[id(p)].data_ptr(), wd(p))
+        bucket = lambda p: self._bucket_of.get(id(p), 0) if self._nb > 1 else 0
+        groups = []
+        for b in range(max(1, self._nb)):
+            idx = [i for i, w in enumerate(srcs) if bucket(runner._conv_ops[i].mod.conv.weight) == b]
+            table, launches = runner.pack_job_table(srcs, sgd=sgd, subset=idx) if idx else (None, [])
+            rest = [p for p in self.params if id(p) not in packed and bucket(p) == b]
+            plain, blk, plain_launches = (_lib.VtbSgdJob * max(1, len(rest)))(), 0, []
+            for j, p in enumerate(rest):
+                plain[j] = _lib.VtbSgdJob(p.data_ptr(), p.grad.data_ptr(), self.mom[id(p)].data_ptr(), p.numel(), wd(p), blk)
+                blk += int(L.vtb_sgd_job_blocks(p.numel()))
+                if (j + 1) % 256 == 0 or j == len(rest) - 1:
+                    plain_launches.append((j // 256 * 256, j % 256 + 1, blk))
+                    blk = 0
+            ptab = torch.frombuffer(bytearray(bytes(plain)), dtype=torch.uint8).to(self.hyper.device)
+            groups.append((table, launches, ptab, plain_launches if rest else []))
         self._runner = runner
-        self._tables = (table, launches, ptab, plain_launches if rest else [], C.sizeof(_lib.VtbPackJob), C.sizeof(_lib.VtbSgdJob))
-        self._key = tuple(p.data_ptr() for p in self.params) + tuple(p.grad.data_ptr() for p in self.params)
+        self._tables = (groups, C.sizeof(_lib.VtbPackJob), C.sizeof(_lib.VtbSgdJob))
+        self._key = self._current_key()
+        self._done = set()
 
-    def step(self) -> None:
+    def _current_key(self):
+        return tuple(p.data_ptr() for p in self.params) + tuple(p.grad.data_ptr() for p in self.params)
+
+    def _training_runner(self):
+        plans = self.backbone.__dict__.get("_vtb_plans", {})
+        return next((r for r in plans.values() if r.g.need_grad and not r.g.f32), None)
+
+    def ready(self) -> bool:
+        """True when `step_bucket` can run right now: the job tables exist and still describe the live tensors (they are
+        built by the first `step()`)."""
+        return (self._tables is not None and self._runner is self._training_runner() and self._runner is not None
+                and self._key == self._current_key())
+
+    def step_bucket(self, b: int) -> None:
+        """Update the parameters of bucket `b` on the current stream (tables must be `ready()`); `step()` skips them."""
         from . import _lib
         from ._lib import check
 
         L = _lib.lib()
-        plans = self.backbone.__dict__.get("_vtb_plans", {})
-        runner = next((r for r in plans.values() if r.g.need_grad and not r.g.f32), None)
-        if runner is None:
-            raise RuntimeError("NativeSGD.step() needs a native training plan (run forward + backward first)")
-        key = tuple(p.data_ptr() for p in self.params) + tuple(p.grad.data_ptr() for p in self.params)
-        if self._tables is None or self._runner is not runner or self._key != key:
-            self._build(runner)
-        table, launches, ptab, plain_launches, rec, prec = self._tables
+        groups, rec, prec = self._tables
+        table, launches, ptab, plain_launches = groups[b]
         dev = self.hyper.device
         st = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
         for j0, n, blocks in launches:
@@ -197,6 +218,21 @@ class NativeSGD:
                   "vtb_sgd_pack_weights")
         for j0, n, blocks in plain_launches:
             check(L.vtb_sgd_step(ptab.data_ptr() + j0 * prec, n, blocks, self.hyper.data_ptr(), st), "vtb_sgd_step")
+        self._done.add(b)
+
+    def step(self) -> None:
+        runner = self._training_runner()
+        if runner is None:
+            raise RuntimeError("NativeSGD.step() needs a native training plan (run forward + backward first)")
+        if self._tables is None or self._runner is not runner or self._key != self._current_key():
+            if self._done:
+                raise RuntimeError("NativeSGD: parameters or gradients were re-allocated in the middle of a step")
+            self._build(runner)
+        for b in range(len(self._tables[0])):
+            if b not in self._done:
+                self.step_bucket(b)
+        self._done = set()
+        plans = self.backbone.__dict__.get("_vtb_plans", {})
         # the operands of `runner` are current; other plans of the module (other shapes / modes) re-pack as usual
         for r in plans.values():
             r._packs_token = r.pack_token() if r is runner else None
@@ -282,6 +318,7 @@ class Trainer:
                             and head.bias is not None and head.weight.dtype == torch.float32
                             and head.weight.device.type == "cuda")
         self._seed = None
+        self._zeroed = True
         self._zero_needed = True   # until a step has shown that every gradient is overwritten in place (see _step_eager)
         self._used_native_head = False
         if process_group is not None:
@@ -326,24 +363,57 @@ class Trainer:
         # at the start of every forward), torch SGD for CPU modules
         self.native_sgd = (dev.type == "cuda" and os.environ.get("VTB_NATIVE_SGD", "1") == "1"
                            and all(p.dtype == torch.float32 for p in self.params))
+        # optimizer overlap (opt-in, VTB_SGD_OVERLAP=1): a bucket's parameters are updated as soon as its gradients are
+        # final (and reduced) instead of after backward.  Safe - every reader of a layer's weights in this step (its dgrad)
+        # is enqueued before the layer reports, and the updating stream waits for that point of the main stream - but
+        # measured neutral (13.89 vs 13.85 ms on one GPU, 14.483 vs 14.487 ms on two; profiles/r02_bench_*_t14*.json): the
+        # update is HBM-bound and so is the end of backward (the 88^2 / 176^2 layers) it would have to hide under.
+        self.sgd_overlap = False
+        self._sgd_now = False
+        self._main_stream = None
         if self.native_sgd:
             self.opt = NativeSGD(backbone, self.params, decay, lr, momentum, weight_decay)
+            self.sgd_overlap = (os.environ.get("VTB_SGD_OVERLAP", "0") == "1" and self.native_head
+                                and (self.world == 1 or self.avg_in_collective))
+            if self.sgd_overlap:
+                self.opt.set_buckets(self._bucket_of, len(self.buckets))
+                if self.world == 1:
+                    backbone.__dict__["_vtb_on_grads_ready"] = self._grads_ready
         else:
             self.opt = torch.optim.SGD(
                 [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}],
                 lr=lr, momentum=momentum, fused=dev.type == "cuda")
 
     # -- gradient exchange
-    def _launch_bucket(self, b: int) -> None:
-        import torch.distributed as dist
+    def _after_main(self, stream) -> None:
+        """Make `stream` wait for everything the step's main stream has been given so far (the dgrads that read the weights a
+        bucket update is about to overwrite)."""
+        if self._main_stream is not None and stream != self._main_stream:
+            ev = torch.cuda.Event()
+            ev.record(self._main_stream)
+            stream.wait_event(ev)
 
+    def _launch_bucket(self, b: int) -> None:
         a, e = self.buckets[b]
         self._launched[b] = True
+        if self.world == 1:
+            # single process: nothing to exchange - the bucket's optimizer step, on the stream its gradients were produced on
+            if self._sgd_now:
+                self._after_main(torch.cuda.current_stream())
+                self.opt.step_bucket(b)
+            return
+        import torch.distributed as dist
+
         op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
-                self._works.append(dist.all_reduce(self.flat[a:e], op=op, group=self.group, async_op=True))
+                work = dist.all_reduce(self.flat[a:e], op=op, group=self.group, async_op=True)
+                self._works.append(work)
+                if self._sgd_now:
+                    self._after_main(self.comm_stream)
+                    work.wait()                 # orders the exchange stream (not the host) behind the collective
+                    self.opt.step_bucket(b)
         else:
             self._works.append(dist.all_reduce(self.flat[a:e], op=op, group=self.group, async_op=True))
 
@@ -361,12 +431,13 @@ class Trainer:
         for b in range(len(self.buckets) - 1, -1, -1):   # whatever the overlap did not cover (the head, CPU modules)
             if not self._launched[b]:
                 self._launch_bucket(b)
-        for w in self._works:
-            w.wait()
-        if self.comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
-        if not self.avg_in_collective:
-            self.flat.mul_(1.0 / self.world)
+        if self.world > 1:
+            for w in self._works:
+                w.wait()
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+            if not self.avg_in_collective:
+                self.flat.mul_(1.0 / self.world)
         self._works = []
         self._pending = list(self._bucket_size)
         self._launched = [False] * len(self.buckets)
@@ -378,9 +449,15 @@ class Trainer:
         if self.native_head and y.ndim == 1 and f.is_cuda and f.dtype == torch.bfloat16 and f.shape[1] % 8 == 0:
             # pooling + linear + label-smoothed CE in the native library (head gradients land in the flat buffer)
             self._used_native_head = True
-            ready = self._grads_ready if self.world > 1 else None
+            ready = self._grads_ready if (self.world > 1 or self.sgd_overlap) else None
             return _HeadCEFn.apply(f, self.head.weight, self.head.bias, y, self.label_smoothing, True, ready)
         self._used_native_head = False
+        if not self._zeroed:
+            # the flat buffer was not zeroed (the previous step overwrote every gradient in place), but autograd ACCUMULATES
+            # the torch head's gradients
+            for p in self.head.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
         pooled = f.float().mean(dim=(2, 3))  # AdaptiveAvgPool2d + Flatten (classifier.py:61-62)
         logits = self.head(pooled)
         return F.cross_entropy(logits, y, label_smoothing=self.label_smoothing)
@@ -396,16 +473,22 @@ class Trainer:
         return bool(runners) and all(r.last_all_direct for r in runners)
 
     def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self._zeroed = self._zero_needed
         if self._zero_needed:
             self.flat.zero_()
+        if self.sgd_overlap:
+            self._main_stream = torch.cuda.current_stream()
+            # per-bucket updates need the optimizer's job tables (built by the first step) and in-place gradients
+            self._sgd_now = (not self._zero_needed) and self.opt.ready()
         loss = self.forward_loss(x, y)
         if self._seed is None or self._seed.device != loss.device or self._seed.dtype != loss.dtype:
             self._seed = torch.ones((), dtype=loss.dtype, device=loss.device)
         loss.backward(self._seed)   # a cached seed: autograd would launch a fill kernel for its own every step
         self._zero_needed = not self._all_grads_overwritten()
-        if self.world > 1:
+        if self.world > 1 or self.sgd_overlap:
             self._finish_exchange()
         self.opt.step()
+        self._sgd_now = False
         return loss.detach()
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
