@@ -160,5 +160,40 @@ int main(int argc, char** argv) {
                     n, s[7] / n, s[0] / n, s[1] / n, s[2] / n, s[3] / n, s[4] / n, s[5] / n, s[6] / n, s[8] / n, s[9] / n, s[10] / n);
     }
   }
+  if (getenv("VTB_INTERLEAVE")) {
+    // Do kernels run slower when DIFFERENT kernels alternate (instruction caches, L2 state) than when one kernel replays
+    // back to back?  (a) fprop -> dgrad -> wgrad round-robin; (b) fprop alternating with a small unrelated kernel.
+    cudaStream_t cs; CK(cudaStreamCreate(&cs));
+    __nv_bfloat16 *ga, *gb; CK(cudaMalloc(&ga, 1 << 20)); CK(cudaMalloc(&gb, 1 << 20));
+    CK(cudaMemset(ga, 0, 1 << 20)); CK(cudaMemset(gb, 0, 1 << 20));
+    for (int mode = 0; mode < 3; ++mode) {
+      cudaGraph_t graph; cudaGraphExec_t exec;
+      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      for (int i = 0; i < 20; ++i) {
+        if (mode == 0) {
+          CV(vtb_conv_fprop(&c, x, c.cin, wf, y, c.cout, stats, nullptr, nullptr, 0, nullptr, 0, cs));
+          CV(vtb_conv_dgrad(&c, dy, c.cout, wd, dx, c.cin, 0, cs));
+          CV(vtb_conv_wgrad(&c, dy, c.cout, x, c.cin, ws, dw, c.cin, 0, cs));
+        } else if (mode == 1) {
+          CV(vtb_conv_fprop(&c, x, c.cin, wf, y, c.cout, stats, nullptr, nullptr, 0, nullptr, 0, cs));
+          CV(vtb_grad_add(ga, 64, gb, 64, 4096, 64, 0, cs));
+        } else {
+          CV(vtb_grad_add(ga, 64, gb, 64, 4096, 64, 0, cs));
+        }
+      }
+      CK(cudaStreamEndCapture(cs, &graph));
+      CK(cudaGraphInstantiate(&exec, graph, 0));
+      CK(cudaGraphLaunch(exec, cs)); CK(cudaStreamSynchronize(cs));
+      cudaEventRecord(e0, cs);
+      for (int r = 0; r < 5; ++r) CK(cudaGraphLaunch(exec, cs));
+      cudaEventRecord(e1, cs);
+      CK(cudaStreamSynchronize(cs));
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      const char* what[3] = {"fprop+dgrad+wgrad round-robin", "fprop + small unrelated kernel", "small unrelated kernel alone"};
+      printf("interleave: %-32s %8.1f us per iteration\n", what[mode], ms * 1e3 / 100);
+      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+    }
+    cudaStreamDestroy(cs);
+  }
   return 0;
 }

@@ -1,7 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-echo "=== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/r02_pytest_gpu_latest.log
-echo "=== bench default (optimizer overlap)"; timeout 300 python bench.py --no-cpu-baseline 2> gpurun_out/bench.err | tee gpurun_out/r02_bench_t14.json | cut -c1-200; tail -2 gpurun_out/bench.err
-echo "=== bench VTB_SGD_OVERLAP=0"; VTB_SGD_OVERLAP=0 timeout 300 python bench.py --no-cpu-baseline 2> gpurun_out/bench.err | tee gpurun_out/r02_bench_t14_nooverlap.json | cut -c1-200; tail -2 gpurun_out/bench.err
-echo done
+for g in "256 11 11 256 256 1 1 0" "256 22 22 128 128 1 1 0" "256 11 11 256 256 3 1 1" "256 6 6 512 512 3 1 1"; do
+  echo "--- $g"; VTB_INTERLEAVE=1 VTB_GRAPH=1 timeout 120 tools/bench_conv $g 10 2>&1 | grep -E "graph replay|interleave" | grep -v "dgradbn\|dgr+acc" | sed 's/(host-free, back to back)//g'
+done 2>&1 | tee gpurun_out/r02_convs_interleave.txt

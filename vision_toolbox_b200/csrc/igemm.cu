@@ -738,16 +738,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             double sx = 0.0, sq = 0.0;
             const float* src = p.stats_partial + (size_t)(n0 + col) * 2;
             const size_t rstride = (size_t)p.cout * 2;
-            // 8 independent loads in flight per thread (a dependent add right behind each load would serialise them)
-            for (int r = g; r < nrows; r += 8 * G) {
-              float2 v[8];
+            // 16 independent loads in flight per thread (a dependent add right behind each load would serialise them; this
+            // loop is the serial tail of the launch: every other CTA has left, the next kernel waits for the coefficients)
+            for (int r = g; r < nrows; r += 16 * G) {
+              float2 v[16];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
+              for (int u = 0; u < 16; ++u) {
                 const int rr = r + u * G;
                 v[u] = (rr < nrows) ? __ldcg(reinterpret_cast<const float2*>(src + (size_t)rr * rstride)) : make_float2(0.f, 0.f);
               }
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
+              for (int u = 0; u < 16; ++u) {
                 sx += (double)v[u].x;
                 sq += (double)v[u].y;
               }
