@@ -154,6 +154,17 @@ typedef struct VtbBnTrain {
   float* running_mean2;
   float* running_var2;
   long long* num_batches_tracked2;
+  /* Fused normalise (optional, act_out != NULL; single unit only: split must be 0): once the statistics are final the
+   * same launch also writes act_out = [relu](y*scale + shift) [+ act_residual] (NHWC bf16 views with pitches act_ld /
+   * act_ldr) - components.py:36-39 (+ the residual add of darknet.py:28) without a separate vtb_bn_act launch: every
+   * thread block re-reads the raw tiles it produced (L2) after its n-block's coefficients were published.  Needs all
+   * thread blocks of the launch co-resident (the grid never exceeds the SM count; do not run another persistent kernel
+   * that pins SMs next to it).  y is still written (BatchNorm backward reads it). */
+  void* act_out;
+  int act_ld;
+  int act_relu;
+  const void* act_residual;
+  int act_ldr;
 } VtbBnTrain;
 int vtb_conv_fprop_bn(const VtbConv* c, const void* x, int ldx, const void* wf, void* y, int ldy, float* stats_partial,
                       const VtbBnTrain* bn, void* stream);

@@ -164,6 +164,10 @@ class InterpreterLib:
                 r_v.mul_(1 - b.momentum).add_(b.momentum * unbiased.float())
             if nbt:
                 _flat(nbt, 1, torch.int64).add_(1)
+        if getattr(b, "act_out", None):   # fused normalise: the unit's vtb_bn_act in the same call
+            assert not b.split
+            self._vtb_bn_act(y, ldy, out.shape[0], g.cout, b.scale, b.shift, b.act_relu, b.act_residual, b.act_ldr,
+                             b.act_out, b.act_ld, st)
 
     @staticmethod
     def _bn_sets(cout, b):

@@ -80,6 +80,12 @@ def _views(name, a, es):
         v = [(a[1], a[2], pin, g.cin, "r"), (y[0], y[1], pout, g.cout, "w")]
         if base == "vtb_conv_fprop" and not f32 and a[10]:      # eval-mode fused epilogue: + residual
             v.append((a[10], a[11], pout, g.cout, "r"))
+        if base == "vtb_conv_fprop_bn" and not f32:
+            bn = a[7]._obj if hasattr(a[7], "_obj") else a[7]
+            if getattr(bn, "act_out", None):                    # fused normalise: the unit's activation (+ residual)
+                v.append((bn.act_out, bn.act_ld, pout, g.cout, "w"))
+                if bn.act_residual:
+                    v.append((bn.act_residual, bn.act_ldr, pout, g.cout, "r"))
         return v
     if base == "vtb_conv_dgrad":
         g, pin, pout = _geom(a[0])
@@ -272,6 +278,13 @@ def test_launch_counts_cspdarknet53(monkeypatch):
     pairs = sum(op.kind == "conv" and op.pair is not None for op in g.ops)
     # default plan: one fused reduce + apply BatchNorm-backward kernel per unit, plain dgrads
     assert bwd["vtb_bn_bwd_fused"] == units and bwd["vtb_conv_dgrad"] == units - pairs - 1 and bwd["vtb_conv_dgrad_bn"] == 0
+    # fused normalise (VTB_FUSED_NORM=1): the normalise + ReLU (+ residual) pass of every single unit rides in its
+    # convolution's launch; only the two units of each side-by-side pair keep their vtb_bn_act
+    monkeypatch.setenv("VTB_FUSED_NORM", "1")
+    g, calls, n_fwd = _dry_run(backbones.cspdarknet53(), (2, 3, 64, 64), False)
+    fwd = Counter(n for n, _ in calls[:n_fwd])
+    assert fwd["vtb_conv_fprop_bn"] == units - pairs and fwd["vtb_bn_act"] == 2 * pairs
+    monkeypatch.setenv("VTB_FUSED_NORM", "0")
     # opt-in plan (VTB_DGRAD_BN=1): the BatchNorm-backward sums ride in the dgrad epilogues
     monkeypatch.setenv("VTB_DGRAD_BN", "1")
     g, calls, n_fwd = _dry_run(backbones.cspdarknet53(), (2, 3, 64, 64), False)

@@ -127,7 +127,37 @@ def test_native_library_is_what_ran():
     with torch.no_grad():
         m(g["x"].cuda())
     torch.cuda.synchronize()
-    assert _lib.launch_count() - before >= 4  # layout conversion, weight pack, conv, finalize, normalise
+    assert _lib.launch_count() - before >= 3  # layout conversion, weight pack, conv + finalize, normalise (own launch unless fused)
+
+
+@pytest.mark.parametrize("name", ["model_cspdarknet", "model_darknet", "model_vovnet_ese", "stage_csp_2_16_32"])
+def test_fused_normalise_in_the_conv_launch_is_bit_identical(name, monkeypatch):
+    """VTB_FUSED_NORM=1 (opt-in; VtbBnTrain.act_*): the unit's normalise + ReLU (+ residual) pass runs inside its
+    convolution's launch - every thread block applies the finished coefficients to the tiles it produced.  Same arithmetic
+    on the same numbers: feature maps, running statistics and gradients equal the default plan bit for bit."""
+    from vision_toolbox_b200 import _lib
+
+    g = load_golden(name)
+    res = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("VTB_FUSED_NORM", fused)
+        m = _native(name, g, train=True)
+        x = g["x"].cuda().requires_grad_(True)
+        before = _lib.launch_count()
+        outs = module_outputs(m, x)
+        sum((o.float() * c.cuda()).sum() for o, c in zip(outs, g["cotangents"])).backward()
+        torch.cuda.synchronize()
+        res.append(([o.detach().clone() for o in outs], x.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters()},
+                    {k: v.clone() for k, v in m.state_dict().items() if "running" in k}, _lib.launch_count() - before))
+    (o0, dx0, g0, s0, n0), (o1, dx1, g1, s1, n1) = res
+    assert n1 < n0                                   # the normalise launches of the single units are gone
+    for a, b in zip(o0, o1):
+        assert torch.equal(a, b)
+    assert torch.equal(dx0, dx1)
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), k
 
 
 def test_forward_is_deterministic_and_repeatable():

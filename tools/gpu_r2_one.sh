@@ -1,6 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for g in "256 11 11 256 256 1 1 0" "256 22 22 128 128 1 1 0" "256 11 11 256 256 3 1 1" "256 6 6 512 512 3 1 1"; do
-  echo "--- $g"; VTB_INTERLEAVE=1 VTB_GRAPH=1 timeout 120 tools/bench_conv $g 10 2>&1 | grep -E "graph replay|interleave" | grep -v "dgradbn\|dgr+acc" | sed 's/(host-free, back to back)//g'
-done 2>&1 | tee gpurun_out/r02_convs_interleave.txt
+echo "=== pytest parity subset with VTB_FUSED_NORM=1"; VTB_FUSED_NORM=1 timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_benchscale.py -m gpu -q 2>&1 | tail -4
+echo "=== bench VTB_FUSED_NORM=1"; VTB_FUSED_NORM=1 timeout 300 python bench.py --no-cpu-baseline 2> gpurun_out/bench.err | tee gpurun_out/r02_bench_t16_fusednorm.json | cut -c1-200; tail -2 gpurun_out/bench.err
+echo "=== bench default"; timeout 300 python bench.py --no-cpu-baseline 2> gpurun_out/bench.err | tee gpurun_out/r02_bench_t16.json | cut -c1-200; tail -2 gpurun_out/bench.err
+echo "=== layers VTB_FUSED_NORM=1"; VTB_FUSED_NORM=1 timeout 300 python tools/layer_profile.py cspdarknet53 > gpurun_out/r02_layers_fusednorm.txt 2>&1; grep -E "fprop|bn_act" gpurun_out/r02_layers_fusednorm.txt | head -24 | cut -c1-120

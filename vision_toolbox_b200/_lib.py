@@ -29,7 +29,9 @@ class VtbBnTrain(C.Structure):
                 ("num_batches_tracked", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("tickets", C.c_void_p), ("sync", C.c_void_p),
                 ("split", C.c_int), ("gamma2", C.c_void_p), ("beta2", C.c_void_p), ("running_mean2", C.c_void_p),
-                ("running_var2", C.c_void_p), ("num_batches_tracked2", C.c_void_p)]
+                ("running_var2", C.c_void_p), ("num_batches_tracked2", C.c_void_p),
+                ("act_out", C.c_void_p), ("act_ld", C.c_int), ("act_relu", C.c_int), ("act_residual", C.c_void_p),
+                ("act_ldr", C.c_int)]
 
 
 class VtbBnBwdLayer(C.Structure):

@@ -622,6 +622,18 @@ static int fprop_impl(const VtbConv* c, const void* x, int ldx, const void* wf, 
     }
     if (bn->sync && !sync_args_ok(bn->sync, c->cout)) return fail(VTB_EINVAL, "vtb_conv_fprop_bn: bad SyncBN peers");
     p.sync = make_sync_peers(bn->sync);
+    if (bn->act_out != nullptr) {   // fused normalise (+ReLU, + residual) in the same launch
+      if (bn->split > 0 || bn->act_ld < c->cout || bn->act_ld % 8 || (reinterpret_cast<uintptr_t>(bn->act_out) & 15) ||
+          (bn->act_residual && (bn->act_ldr < c->cout || bn->act_ldr % 8 ||
+                                (reinterpret_cast<uintptr_t>(bn->act_residual) & 15))) ||
+          c->cout / tl.block_n > 64 || tl.grid > std::max(1, num_sms()))
+        return fail(VTB_EINVAL, "vtb_conv_fprop_bn: bad fused-normalise arguments");
+      p.fn_out = (__nv_bfloat16*)bn->act_out;
+      p.fn_ldo = bn->act_ld;
+      relu = bn->act_relu;
+      residual = bn->act_residual;
+      ldr = bn->act_ldr;
+    }
   }
   p.scale = scale;
   p.shift = shift;

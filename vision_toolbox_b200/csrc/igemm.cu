@@ -225,6 +225,151 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused normalise (+ReLU, + residual) tail of a training fprop (ConvIgemmParams::fn_out): called by the 16 epilogue warps
+// after the statistics / finalisation code.  The coefficients of an n-block are final once its last CTA has written them;
+// every CTA of the n-block then applies them to the tiles it produced itself (still in L2).  __noinline__: its registers
+// must not count against the main loop's.  Everything it needs comes BY VALUE: a reference to the kernel's parameter
+// block turns every field access into a generic load (ncu: the top stall of the first version).
+// ------------------------------------------------------------------------------------------------
+struct FnArgs {
+  const __nv_bfloat16* y;          // raw conv output (this launch's `out`)
+  const __nv_bfloat16* res;        // residual or nullptr
+  __nv_bfloat16* out;              // destination view
+  const float* scale;
+  const float* shift;
+  unsigned int* tickets;
+  int ldy, ldr, ldo, relu, block_m, block_n, M, nmb, mstep;   // nmb / mstep: num_m_blocks / m_step of the launch
+};
+__device__ __noinline__ void fused_normalise_tail(FnArgs a, int et, int n_blk, int n0, int m_first, bool last, float2* slots) {
+  constexpr int NT = kEpiWarps * 32;
+  volatile unsigned int* ready = a.tickets + 128 + n_blk;
+  unsigned int* depart = a.tickets + 192 + n_blk;
+  if (last) {
+    __threadfence();                         // scale / shift (threads et < block_n) visible device-wide
+    named_bar_sync(1, NT);
+    if (et == 0) *ready = 1u;
+  } else if (et == 0) {
+    const long long t0 = clock64();
+    while (*ready == 0u) {
+      if (clock64() - t0 > 200000000000LL) __trap();   // ~100 s: a co-residency assumption was violated
+    }
+    __threadfence();
+  }
+  named_bar_sync(1, NT);
+  // All tiles of this CTA form ONE index space, walked with FU independent 16-byte loads in flight per thread: a per-tile
+  // loop would expose one memory round trip per tile (16 KB tiles on the few-channel layers).
+  const int cpr = a.block_n / 8;                                         // 16-byte chunks per tile row
+  const int my_tiles = (a.nmb - m_first + a.mstep - 1) / a.mstep;
+  const int rows_total = my_tiles * a.block_m;                           // rows of all my tiles, tile after tile
+  const bool has_res = a.res != nullptr;
+  const bool relu = a.relu != 0;
+  auto apply = [&](const uint4& yq, const uint4& rq, const float (&sc)[8], const float (&sh)[8], uint32_t pix, int cc) {
+    const uint32_t yw[4] = {yq.x, yq.y, yq.z, yq.w};
+    const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f0 = fmaf(bf16lo(yw[j]), sc[2 * j], sh[2 * j]), f1 = fmaf(bf16hi(yw[j]), sc[2 * j + 1], sh[2 * j + 1]);
+      if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+      if (has_res) {   // the reference adds two bf16 tensors: round first, then add
+        f0 = __bfloat162float(__float2bfloat16_rn(f0)) + bf16lo(rw[j]);
+        f1 = __bfloat162float(__float2bfloat16_rn(f1)) + bf16hi(rw[j]);
+      }
+      ow[j] = pack_bf16x2(f0, f1);
+    }
+    *reinterpret_cast<uint4*>(a.out + (size_t)pix * a.ldo + n0 + cc) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  };
+  // row index over my tiles -> pixel (block_m is 128 or 256)
+  const int bm_shift = (a.block_m == 256) ? 8 : 7;
+  auto pixel_of = [&](int rowg) -> uint32_t {
+    const int tl = rowg >> bm_shift;
+    return (uint32_t)((m_first + tl * a.mstep) * a.block_m + (rowg & (a.block_m - 1)));
+  };
+  if ((cpr & (cpr - 1)) == 0 && cpr <= NT) {
+    // power-of-two tile width: the channel chunk of a thread is loop-invariant (coefficients in registers) and its rows
+    // advance by a constant step - no division in the loop
+    const int cc = (et & (cpr - 1)) * 8;
+    const int rstep = NT / cpr;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldcg(a.scale + n0 + cc + j);
+      sh[j] = __ldcg(a.shift + n0 + cc + j);
+    }
+    const __nv_bfloat16* ycol = a.y + n0 + cc;
+    if (!has_res) {
+      constexpr int FU = 8;
+      for (int r0 = et / cpr; r0 < rows_total; r0 += rstep * FU) {
+        uint4 yv[FU];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+          const int rg = r0 + u * rstep;
+          const uint32_t pix = pixel_of(rg);
+          yv[u] = (rg < rows_total && pix < (uint32_t)a.M) ? __ldcg(reinterpret_cast<const uint4*>(ycol + (size_t)pix * a.ldy))
+                                                           : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+          const int rg = r0 + u * rstep;
+          const uint32_t pix = pixel_of(rg);
+          if (rg < rows_total && pix < (uint32_t)a.M) apply(yv[u], make_uint4(0u, 0u, 0u, 0u), sc, sh, pix, cc);
+        }
+      }
+    } else {
+      constexpr int FU = 4;
+      const __nv_bfloat16* rcol = a.res + n0 + cc;
+      for (int r0 = et / cpr; r0 < rows_total; r0 += rstep * FU) {
+        uint4 yv[FU], rv[FU];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+          const int rg = r0 + u * rstep;
+          const uint32_t pix = pixel_of(rg);
+          const bool ok = rg < rows_total && pix < (uint32_t)a.M;
+          yv[u] = ok ? __ldcg(reinterpret_cast<const uint4*>(ycol + (size_t)pix * a.ldy)) : make_uint4(0u, 0u, 0u, 0u);
+          rv[u] = ok ? __ldg(reinterpret_cast<const uint4*>(rcol + (size_t)pix * a.ldr)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+          const int rg = r0 + u * rstep;
+          const uint32_t pix = pixel_of(rg);
+          if (rg < rows_total && pix < (uint32_t)a.M) apply(yv[u], rv[u], sc, sh, pix, cc);
+        }
+      }
+    }
+  } else {
+    // general tile width (160 / 192 / 224 channels): coefficients staged in shared memory, one item at a time
+    float2* cf = slots;   // [block_n] (scale, shift)
+    for (int cidx = et; cidx < a.block_n; cidx += NT)
+      cf[cidx] = make_float2(__ldcg(a.scale + n0 + cidx), __ldcg(a.shift + n0 + cidx));
+    named_bar_sync(1, NT);
+    const int total_items = rows_total * cpr;
+    for (int gi = et; gi < total_items; gi += NT) {
+      const int rg = gi / cpr;
+      const int cc = (gi - rg * cpr) * 8;
+      const uint32_t pix = pixel_of(rg);
+      if (pix >= (uint32_t)a.M) continue;
+      const uint4 yq = __ldcg(reinterpret_cast<const uint4*>(a.y + (size_t)pix * a.ldy + n0 + cc));
+      const uint4 rq = has_res ? __ldg(reinterpret_cast<const uint4*>(a.res + (size_t)pix * a.ldr + n0 + cc))
+                               : make_uint4(0u, 0u, 0u, 0u);
+      float sc[8], sh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 c = cf[cc + j];
+        sc[j] = c.x;
+        sh[j] = c.y;
+      }
+      apply(yq, rq, sc, sh, pix, cc);
+    }
+  }
+  // the last CTA of the n-block to get here re-arms the flags (nobody spins on `ready` any more)
+  named_bar_sync(1, NT);
+  if (et == 0 && atomicAdd(depart, 1u) == (unsigned int)(a.mstep - 1)) {
+    *depart = 0u;
+    *ready = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // conv_igemm_kernel
 //
 // Persistent, warp-specialised. One tile = block_m (128 | 256) output pixels x block_n channels; a CTA keeps ONE
@@ -830,6 +975,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (pc == 0 && nbt != nullptr) *nbt += 1;
           }
           if (et == 0) p.tickets[n_blk] = 0u;       // self-cleaning: ready for the next launch
+        }
+        if (EPI != kEpiBwd && p.fn_out != nullptr) {
+          FnArgs fa;
+          fa.y = p.out; fa.res = p.residual; fa.out = p.fn_out; fa.scale = p.bn_scale; fa.shift = p.bn_shift;
+          fa.tickets = p.tickets; fa.ldy = p.ldo; fa.ldr = p.ldr; fa.ldo = p.fn_ldo; fa.relu = p.relu;
+          fa.block_m = p.block_m; fa.block_n = p.block_n; fa.M = p.M; fa.nmb = num_m_blocks; fa.mstep = m_step;
+          fused_normalise_tail(fa, et, n_blk, n0, m_first, last, reinterpret_cast<float2*>(slots));
         }
       }
     }

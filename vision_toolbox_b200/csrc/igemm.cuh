@@ -93,6 +93,12 @@ struct ConvIgemmParams {
   float* bn_running_mean2;
   float* bn_running_var2;
   long long* bn_nbt2;
+  // Fused normalise (fprop with in-kernel finalisation only; fn_out != nullptr): once the coefficients of its n-block are
+  // final, every CTA re-reads the raw tiles it produced (L2) and writes fn_out = [relu](y*scale+shift) [+ residual] - the
+  // unit's vtb_bn_act pass without its launch.  Uses `relu`, `residual`, `ldr` below and tickets[128 + n_blk] ("ready"),
+  // tickets[192 + n_blk] ("departed"); needs every CTA of the launch co-resident (grid <= SMs, one CTA per SM).
+  __nv_bfloat16* fn_out;
+  int fn_ldo;
   // SyncBN: peer-mapped exchange buffers (world <= 1: single-GPU statistics); bn_count is then the GLOBAL count and
   // tickets[64] counts the finished n-block exchanges of the launch
   SyncPeers sync;

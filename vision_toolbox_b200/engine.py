@@ -678,6 +678,9 @@ class Runner:
         # without it a SyncBN kernel spinning for its peers on every SM, an NCCL kernel waiting for its peer and a third
         # stream both depend on closed a cross-rank wait cycle (exchange timeout at 2 GPUs).  VTB_WGRAD_STREAM_MULTI=0
         # keeps multi-rank plans on one stream.
+        # normalise + ReLU (+ residual) of a unit inside its convolution's launch (VTB_FUSED_NORM=1; single units of bf16
+        # plans): the conv kernel's CTAs apply the finished coefficients to their own tiles after a flag wait
+        self.fused_norm = _os.environ.get("VTB_FUSED_NORM", "0") == "1" and not graph.f32
         self._side = None
         multi_rank = dist_cfg is not None and dist_cfg.world > 1
         multi_ok = (_os.environ.get("VTB_WGRAD_STREAM_MULTI", "1") == "1"
@@ -913,9 +916,15 @@ class Runner:
             bn = VtbBnTrain(count * world, norm.weight.data_ptr(), norm.bias.data_ptr(), norm.eps, mom, rm, rv, nbt,
                             f("mean"), f("invstd"), f("scale"), f("shift"), self.tickets.data_ptr(),
                             C.addressof(peer_sync) if peer_sync is not None else None)
+            if self.fused_norm:
+                # the normalise + ReLU (+ residual) pass rides in the same launch (VtbBnTrain.act_*): no vtb_bn_act
+                bn.act_out, bn.act_ld, bn.act_relu = abase + out.byte_offset(), out.ld, int(op.relu)
+                bn.act_residual, bn.act_ldr = (res_p or None), res_ld
             check(L.vtb_conv_fprop_bn(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(),
                                       abase + y.byte_offset(), y.ld, f("partial_f"), C.byref(bn), st),
                   "vtb_conv_fprop_bn")
+            if self.fused_norm:
+                return
         else:
             check(L.vtb_conv_fprop(C.byref(geom), abase + x.byte_offset(), x.ld, wf.data_ptr(),
                                    abase + y.byte_offset(), y.ld, f("partial_f") if use_batch_stats else 0, 0, 0, 0, 0,
