@@ -1,13 +1,12 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench (both arms), launch list under ncu. Outputs -> gpurun_out/
+# end-of-round validation on one GPU: tests, smoke, headline bench (+ CPU baseline), reference arm, every BASELINE config
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-echo "=== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
-echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
-echo "=== bench"; timeout 900 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-echo "=== ncu launches"; timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv python tools/one_step.py cspdarknet53 256 176 2 > gpurun_out/ncu_run.log 2>&1; tail -3 gpurun_out/ncu_run.log
-echo "=== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>> gpurun_out/bench.err | tee gpurun_out/bench_ref.json
-echo "=== ncu full: 128->128 3x3 fprop/dgrad (tools/bench_conv)"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -c 2 -f -o gpurun_out/prof_conv3x3_128 tools/bench_conv 256 22 22 128 128 3 1 1 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_igemm -c 1 -f -o gpurun_out/prof_wgrad3x3_128 tools/bench_conv 256 22 22 128 128 3 1 1 >> gpurun_out/ncu_full.log 2>&1
-timeout 300 python tools/layer_profile.py cspdarknet53 > gpurun_out/layers.txt 2>&1; head -12 gpurun_out/layers.txt
+T=${1:-final}
+echo "=== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/r02_pytest_gpu_$T.log
+echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/r02_smoke_$T.log
+echo "=== bench (default flags)"; timeout 900 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/r02_bench_$T.json | cut -c1-300; tail -2 gpurun_out/bench.err
+echo "=== bench --impl reference"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2> gpurun_out/bench_ref.err | tee gpurun_out/r02_bench_ref_$T.json | cut -c1-300; tail -2 gpurun_out/bench_ref.err
+echo "=== configs"; : > gpurun_out/r02_bench_configs_$T.jsonl
+for c in C2 C3 C4 C5; do timeout 600 python bench.py --config $c --no-cpu-baseline 2>> gpurun_out/bench.err | tee -a gpurun_out/r02_bench_configs_$T.jsonl | cut -c1-160; done
+echo done

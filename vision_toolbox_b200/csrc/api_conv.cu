@@ -102,6 +102,8 @@ static ConvTiling plan_conv_tiling(long long M, int ncols, int total_k16) {
   const long long tiles128 = ((M + 127) / 128) * t.n_blocks;
   const double cost256 = 1.36 * (double)((tiles256 + sms - 1) / sms), cost128 = (double)((tiles128 + sms - 1) / sms);
   t.block_m = (cost256 <= cost128) ? 256 : 128;
+  static const bool old_rule = getenv("VTB_BLOCKM_RULE") && !strcmp(getenv("VTB_BLOCKM_RULE"), "r1");   // A/B: round-1 rule
+  if (old_rule) t.block_m = (tiles256 * 4 >= (long long)sms * 3) ? 256 : 128;
   static const int o_bm = env_int("VTB_BLOCK_M");
   if (o_bm == 128 || o_bm == 256) t.block_m = o_bm;
   const long long tiles = ((M + t.block_m - 1) / t.block_m) * t.n_blocks;
