@@ -106,6 +106,25 @@ def test_train_backward(name, x_grad, dgrad_bn, monkeypatch):
         assert e_ours < 2.0 * e_ref + 1e-2, (name, k, e_ours, e_ref)     # SURVEY.md Appendix B criterion
 
 
+@pytest.mark.parametrize("name", ["block_darknet_32", "model_cspdarknet", "model_vovnet_ese", "unit_3x3s2_32_32_odd"])
+def test_fused_normalise_plan_is_the_same_function(name, monkeypatch):
+    """VTB_FUSED_NORM=1: the unit's normalise + ReLU (+ residual) pass rides in vtb_conv_fprop_bn (VtbBnTrain.act_*) instead
+    of its own vtb_bn_act call - forward maps, statistics and gradients are those of the default plan, bit for bit."""
+    g = load_golden(name)
+    res = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("VTB_FUSED_NORM", fused)
+        m, graph, outs, grads, gx = _run(name, g, True, True, True)
+        res.append((outs, grads, gx, {k: v.clone() for k, v in m.state_dict().items() if "running" in k}))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    for k in res[0][1]:
+        assert torch.equal(res[0][1][k], res[1][1][k]), k
+    assert torch.equal(res[0][2], res[1][2])
+    for k in res[0][3]:
+        assert torch.equal(res[0][3][k], res[1][3][k]), k
+
+
 def test_pairing_and_gathered_stem_do_not_change_the_result():
     """The plan-level transformations are exact rewrites: same numbers with and without them (up to the summation order of
     the torch kernels the interpreter uses)."""
