@@ -163,7 +163,10 @@ def test_fp32_config_c1_darknet19_batch8_224():
     names = [k for k, _ in m.named_parameters()]
     for k, p in m.named_parameters():
         e_ours, e_ref = rel_err(p.grad, g64[k]), rel_err(g32[k], g64[k])
-        assert e_ours < 10.0 * e_ref + 1e-4, (k, e_ours, e_ref)
+        # 10x the fp32 oracle's own error, or - where the oracle happens to have no mask flip in this tensor and the kernels
+        # have one (or vice versa) - the size of such a flip: a single ReLU-mask disagreement in a 392-sample BatchNorm
+        # layer moves that layer's gradient tensors by ~1e-3 of their norm
+        assert e_ours < max(10.0 * e_ref + 1e-4, 5e-3), (k, e_ours, e_ref)
         worst = max(worst, e_ours)
     cat = lambda d: torch.cat([d[k].detach().double().cpu().flatten() for k in names])
     ours_all = torch.cat([p.grad.detach().double().cpu().flatten() for _, p in m.named_parameters()])

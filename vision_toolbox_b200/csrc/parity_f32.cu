@@ -31,7 +31,7 @@ struct F32Geom {
 //   MODE 1  dgrad : C[m = in pixel ][n = cin]       = sum_{k = (tap, co)}  dy[pixel'(m, tap)][co] * w[co][n][tap]
 //   MODE 2  wgrad : C[m = cout     ][n = (tap, ci)] = sum_{k = out pixel}  dy[k][m]               * x[pixel(k, tap)][ci]
 //                   (K split over blockIdx.z, one fp32 partial tile per split, summed in order by f32_wgrad_reduce_kernel)
-// Each result is one sequential fp32 FMA chain over K: error ~ sqrt(K) * 2^-24, far inside the 1e-4 budget.
+// Each result: fp32 FMA chains of kBK terms added into an fp64 running sum (error ~ 2^-24 of the term magnitudes).
 // ------------------------------------------------------------------------------------------------
 constexpr int kBM = 64, kBN = 64, kBK = 16;
 
@@ -105,11 +105,14 @@ f32_conv_gemm_kernel(const F32Geom g, const float* __restrict__ a_src, int lda, 
   const long long m0 = (long long)blockIdx.x * kBM, n0 = (long long)blockIdx.y * kBN;
   const long long kbeg = (long long)blockIdx.z * k_per_split;
   const long long kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
-  float acc[4][4];
+  // Two-level accumulation: fp32 FMA chains of kBK terms, added into fp64 running sums.  One sequential fp32 chain over the
+  // whole K (up to 9216 here) loses ~sqrt(K) ulps; at the real layer sizes that flips enough ReLU masks against the
+  // reference to move gradients by 1e-3 (tests/test_real_shapes.py) - oneDNN's blocked accumulation does not.
+  double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
   for (long long k0 = kbeg; k0 < kend; k0 += kBK) {
 #pragma unroll
@@ -123,6 +126,11 @@ f32_conv_gemm_kernel(const F32Geom g, const float* __restrict__ a_src, int lda, 
       Bs[kb][nn] = f32_fetch_b<MODE>(g, b_src, ldb, k0 + kb, n0 + nn, kend, N);
     }
     __syncthreads();
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < kBK; ++kk) {
       float av[4], bv[4];
@@ -133,8 +141,12 @@ f32_conv_gemm_kernel(const F32Geom g, const float* __restrict__ a_src, int lda, 
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += (double)part[i][j];
     __syncthreads();
   }
 #pragma unroll
@@ -145,11 +157,12 @@ f32_conv_gemm_kernel(const F32Geom g, const float* __restrict__ a_src, int lda, 
     for (int j = 0; j < 4; ++j) {
       const long long n = n0 + tx * 4 + j;
       if (n >= N) continue;
+      const float r = (float)acc[i][j];
       if (MODE == 2) {
-        out[((long long)blockIdx.z * M + m) * N + n] = acc[i][j];   // partial tile of this split
+        out[((long long)blockIdx.z * M + m) * N + n] = r;   // partial tile of this split
       } else {
         float* dst = out + m * ldo + n;
-        *dst = accumulate ? *dst + acc[i][j] : acc[i][j];
+        *dst = accumulate ? *dst + r : r;
       }
     }
   }
@@ -167,9 +180,9 @@ __global__ void f32_wgrad_reduce_kernel(const float* __restrict__ ws, int splits
     const int ci = (int)(t % cin_real);
     const int co = (int)(t / cin_real);
     const long long ncols = (long long)taps * cin_real;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[((long long)s * cout + co) * ncols + (long long)tap * cin_real + ci];
-    dw[i] = accumulate ? dw[i] + acc : acc;
+    double acc = 0.0;
+    for (int s = 0; s < splits; ++s) acc += (double)ws[((long long)s * cout + co) * ncols + (long long)tap * cin_real + ci];
+    dw[i] = accumulate ? dw[i] + (float)acc : (float)acc;
   }
 }
 
