@@ -125,7 +125,8 @@ class ProfilingLib:
         fn = getattr(self._real, name)
         if not name.startswith("vtb_") or name in ("vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows",
                                                    "vtb_conv_wgrad_workspace_bytes", "vtb_launch_count", "vtb_pack_job_blocks", "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w",
-                                                   "vtb_conv_tiling_info", "vtb_bn_bwd_fused_rows"):
+                                                   "vtb_conv_tiling_info", "vtb_bn_bwd_fused_rows", "vtb_sgd_job_blocks", "vtb_version",
+                                                   "vtb_num_sms", "vtb_bn_sync_buffer_bytes"):
             return fn
 
         def wrapped(*args):
@@ -518,7 +519,12 @@ def main() -> None:
         r.L = prof       # EVERY rank runs the instrumented step (same host pacing on all ranks); rank 0 reports it
     barrier()
     torch.cuda._sleep(30_000_000)  # let the host run ahead so event intervals contain no launch gaps
-    trainer._step_eager(dev_x[0], dev_y[0])   # eager on purpose: per-call events cannot be recorded inside a graph replay
+    real_lib_fn = _lib.lib
+    _lib.lib = lambda: prof      # the head / loss / optimizer entry points look the library up at call time
+    try:
+        trainer._step_eager(dev_x[0], dev_y[0])   # eager on purpose: per-call events cannot be recorded inside a graph replay
+    finally:
+        _lib.lib = real_lib_fn
     barrier()
     for r, sd_ in zip(runners, sides):
         r.L = _lib.lib()
