@@ -125,6 +125,65 @@ def test_fused_normalise_plan_is_the_same_function(name, monkeypatch):
         assert torch.equal(res[0][3][k], res[1][3][k]), k
 
 
+@pytest.mark.parametrize("nb", [1, 4])
+def test_native_sgd_job_tables_against_torch_sgd(nb):
+    """parallel.NativeSGD (vtb_sgd_pack_weights / vtb_sgd_step job tables, one set per gradient bucket) through the
+    interpreter: after two steps the parameters equal torch.optim.SGD's (momentum 0.9, weight decay on conv weights only),
+    whether the optimizer steps everything at once (nb = 1) or bucket by bucket in any order (nb = 4)."""
+    import copy
+
+    from vision_toolbox_b200 import parallel
+
+    name = "model_cspdarknet"
+    g = load_golden(name)
+    m = BUILDERS[name]()
+    m.load_state_dict(g["state_dict"])
+    m.train()
+    ref = copy.deepcopy(m)
+    graph = engine.Graph(True, True, False, pair_ok=True, col_stem=True)
+    t_in = graph.input_image(*g["x"].shape)
+    for t in m._emit(graph, t_in):
+        graph.mark_output(t)
+    graph.finalize()
+    lib = InterpreterLib()
+    with mock.patch.object(engine._lib, "lib", return_value=lib):
+        runner = engine.Runner(graph, torch.device("cpu"))
+        runner._stream = lambda: 0
+        m.__dict__["_vtb_plans"] = {"train": runner}
+        params = list(m.parameters())
+        decay, no_decay = parallel.split_decay_groups([m])
+        opt = parallel.NativeSGD(m, params, decay, lr=0.1, momentum=0.9, weight_decay=1e-2)
+        if nb > 1:
+            opt.set_buckets({id(p): i % nb for i, p in enumerate(params)}, nb)
+        rdecay, rno = parallel.split_decay_groups([ref])
+        ropt = torch.optim.SGD([{"params": rdecay, "weight_decay": 1e-2}, {"params": rno, "weight_decay": 0.0}],
+                               lr=0.1, momentum=0.9)
+        gen = torch.Generator().manual_seed(3)
+        for step in range(2):
+            for p, q in zip(params, ref.parameters()):
+                gr = torch.randn(p.shape, generator=gen)
+                if p.grad is None:
+                    p.grad = gr            # the job tables hold the gradients' addresses: later steps write in place
+                else:
+                    p.grad.copy_(gr)
+                q.grad = gr.clone()
+            if nb > 1 and step == 1:
+                assert opt.ready()
+                for b in (2, 0, 3):             # some buckets early, in any order; step() finishes the rest
+                    opt.step_bucket(b)
+            opt.step()
+            ropt.step()
+        for (k, p), q in zip(m.named_parameters(), ref.parameters()):
+            assert rel_err(p, q) < 2e-6, k
+        # the bf16 operands the fused step left behind are those of the new weights: same forward as a fresh re-pack
+        with torch.no_grad():
+            a = [o.float().clone() for o in runner.forward(g["x"])[0]]
+            runner._packs_token = None
+            b = [o.float().clone() for o in runner.forward(g["x"])[0]]
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+
+
 def test_pairing_and_gathered_stem_do_not_change_the_result():
     """The plan-level transformations are exact rewrites: same numbers with and without them (up to the summation order of
     the torch kernels the interpreter uses)."""
