@@ -118,6 +118,20 @@ def test_overlap_bucket_ranges_keep_the_last_finishing_bucket_small():
     assert parallel.overlap_bucket_ranges([], 100, 10) == []
 
 
+def test_sm_reserve_and_nccl_options(monkeypatch):
+    """VTB_SM_RESERVE is read by both sides (library: BatchNorm-backward grid; Python: NCCL's CTA cap).  0 switches the cap
+    off - NCCL rejects maxCTAs = 0, so no options object must be produced - and garbage falls back to the default."""
+    monkeypatch.setenv("VTB_SM_RESERVE", "0")
+    assert parallel.sm_reserve() == 0 and parallel.nccl_pg_options() is None
+    monkeypatch.setenv("VTB_SM_RESERVE", "nonsense")
+    assert parallel.sm_reserve() == 16
+    monkeypatch.setenv("VTB_SM_RESERVE", "24")
+    assert parallel.sm_reserve() == 24
+    opts = parallel.nccl_pg_options()
+    if opts is not None:                       # torch builds without ProcessGroupNCCL.Options give None
+        assert opts.config.max_ctas == 24
+
+
 def test_weight_decay_groups_follow_reference_rule():
     m, head = _model(0)
     decay, no_decay = parallel.split_decay_groups([m, head])
