@@ -174,6 +174,14 @@ int vtb_conv_fprop_bn(const VtbConv* c, const void* x, int ldx, const void* wf, 
  * OSA branches: darknet.py:28,53 ; vovnet.py:55,61) with bf16 rounding of each addend like autograd. */
 int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
                    void* stream);
+/* The same dgrad for a 3x3 / stride-2 / pad-1 convolution with even H and W and few channels (cin <= 64), as ONE dense
+ * GEMM over 2x2 super-pixels of dx instead of four output-parity phase launches that each stream the whole dy:
+ * 16/9 of the minimal FLOPs (7 of 16 weight blocks are zero) but dy is read once - a win where the layer is HBM-bound.
+ * dx must be dense (lddx == cin).  workspace: vtb_conv_dgrad_s2_workspace_bytes(c) bytes (0: geometry not supported, use
+ * vtb_conv_dgrad), 128-byte aligned; it receives the merged weight matrix [4*cin][4*cout] cut from wd by this call. */
+size_t vtb_conv_dgrad_s2_workspace_bytes(const VtbConv* c);
+int vtb_conv_dgrad_s2(const VtbConv* c, const void* dy, int lddy, const void* wd, void* workspace, void* dx, int lddx,
+                      int accumulate, void* stream);
 /* dgrad that ALSO starts the BatchNorm(+ReLU) backward of the layer(s) that produced x (autograd chain
  * ConvolutionBackward0 -> ReluBackward0 -> NativeBatchNormBackward0 of components.py:26-39): when this call is the
  * LAST contribution to dx, dx is the complete gradient `g` of the producer's output.  The epilogue then reads the

@@ -22,7 +22,8 @@ BF16 = torch.bfloat16
 HOST_ONLY = {"vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows", "vtb_bn_bwd_fused_rows", "vtb_conv_out_hw",
              "vtb_conv_wgrad_workspace_bytes", "vtb_f32_conv_wgrad_workspace_bytes", "vtb_f32_bn_rows",
              "vtb_pack_job_blocks", "vtb_launch_count", "vtb_version", "vtb_num_sms", "vtb_bn_sync_buffer_bytes",
-             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info", "vtb_sgd_job_blocks"}
+             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info", "vtb_sgd_job_blocks",
+             "vtb_conv_dgrad_s2_workspace_bytes"}
 
 
 def _flat(ptr: int, n: int, dt: torch.dtype) -> torch.Tensor:
@@ -185,6 +186,12 @@ class InterpreterLib:
         gx = gx.permute(0, 2, 3, 1).reshape(g.n * g.h * g.w, g.cin)
         dst = _view(dx, lddx, gx.shape[0], g.cin)
         dst.copy_(((_r(gx) + dst.float()) if accumulate else gx).to(BF16))
+
+    def _vtb_conv_dgrad_s2(self, geom, dy, lddy, wd, ws, dx, lddx, accumulate, st):
+        """Stride-2 dgrad as one GEMM over 2x2 super-pixels: the same function of (dy, wd) as vtb_conv_dgrad."""
+        g = _obj(geom)
+        assert g.k == 3 and g.stride == 2 and g.pad == 1 and g.h % 2 == 0 and g.w % 2 == 0 and lddx == g.cin and ws
+        self._vtb_conv_dgrad(geom, dy, lddy, wd, dx, lddx, accumulate, st)
 
     def _vtb_conv_dgrad_bn(self, geom, dy, lddy, wd, dx, lddx, accumulate, bn, st):
         """dgrad, then the BatchNorm(+ReLU) backward sums of the producer layer(s) against the COMPLETED dx (vtb.h)."""

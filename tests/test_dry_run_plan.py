@@ -22,7 +22,8 @@ from vision_toolbox_b200.backbones.darknet import CSPDarknetStage
 HOST_ONLY = {"vtb_last_error", "vtb_conv_stats_rows", "vtb_bn_bwd_rows", "vtb_bn_bwd_fused_rows", "vtb_conv_out_hw",
              "vtb_conv_wgrad_workspace_bytes", "vtb_f32_conv_wgrad_workspace_bytes", "vtb_f32_bn_rows",
              "vtb_pack_job_blocks", "vtb_launch_count", "vtb_version", "vtb_num_sms", "vtb_bn_sync_buffer_bytes",
-             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info", "vtb_sgd_job_blocks"}
+             "vtb_conv_dgrad_stats_rows", "vtb_conv_dgrad_panel_w", "vtb_conv_tiling_info", "vtb_sgd_job_blocks",
+             "vtb_conv_dgrad_s2_workspace_bytes"}
 
 
 class RecordingLib:
@@ -91,6 +92,9 @@ def _views(name, a, es):
         g, pin, pout = _geom(a[0])
         dx, ld, acc = (a[5], a[6], a[7]) if f32 else (a[4], a[5], a[6])
         return [(a[1], a[2], pout, g.cout, "r"), (dx, ld, pin, g.cin, "rw" if acc else "w")]
+    if base == "vtb_conv_dgrad_s2":
+        g, pin, pout = _geom(a[0])
+        return [(a[1], a[2], pout, g.cout, "r"), (a[5], a[6], pin, g.cin, "rw" if a[7] else "w")]
     if base == "vtb_conv_dgrad_bn":
         g, pin, pout = _geom(a[0])
         bn = a[7]._obj if hasattr(a[7], "_obj") else a[7]
@@ -276,8 +280,15 @@ def test_launch_counts_cspdarknet53(monkeypatch):
     bwd = Counter(n for n, _ in calls[n_fwd:])
     units = sum(op.kind == "conv" for op in g.ops)
     pairs = sum(op.kind == "conv" and op.pair is not None for op in g.ops)
-    # default plan: one fused reduce + apply BatchNorm-backward kernel per unit, plain dgrads
-    assert bwd["vtb_bn_bwd_fused"] == units and bwd["vtb_conv_dgrad"] == units - pairs - 1 and bwd["vtb_conv_dgrad_bn"] == 0
+    # default plan: one fused reduce + apply BatchNorm-backward kernel per unit, plain dgrads - the two few-channel
+    # stride-2 layers (32 -> 64, 64 -> 128; 128 -> 256 and wider stay on the four-phase path) as one GEMM over 2x2 super-pixels
+    assert bwd["vtb_bn_bwd_fused"] == units and bwd["vtb_conv_dgrad_bn"] == 0
+    assert bwd["vtb_conv_dgrad"] + bwd["vtb_conv_dgrad_s2"] == units - pairs - 1 and bwd["vtb_conv_dgrad_s2"] == 2
+    monkeypatch.setenv("VTB_DGRAD_S2_MERGED", "0")
+    _, calls0, n_fwd0 = _dry_run(backbones.cspdarknet53(), (2, 3, 64, 64), False)
+    bwd0 = Counter(n for n, _ in calls0[n_fwd0:])
+    assert bwd0["vtb_conv_dgrad"] == units - pairs - 1 and bwd0["vtb_conv_dgrad_s2"] == 0
+    monkeypatch.delenv("VTB_DGRAD_S2_MERGED")
     # fused normalise (VTB_FUSED_NORM=1): the normalise + ReLU (+ residual) pass of every single unit rides in its
     # convolution's launch; only the two units of each side-by-side pair keep their vtb_bn_act
     monkeypatch.setenv("VTB_FUSED_NORM", "1")

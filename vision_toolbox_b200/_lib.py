@@ -96,6 +96,8 @@ SIGNATURES = {
     "vtb_conv_fprop": (_i, [_cp, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i, _p]),
     "vtb_conv_fprop_bn": (_i, [_cp, _p, _i, _p, _p, _i, _p, C.POINTER(VtbBnTrain), _p]),
     "vtb_conv_dgrad": (_i, [_cp, _p, _i, _p, _p, _i, _i, _p]),
+    "vtb_conv_dgrad_s2_workspace_bytes": (C.c_size_t, [_cp]),
+    "vtb_conv_dgrad_s2": (_i, [_cp, _p, _i, _p, _p, _p, _i, _i, _p]),
     "vtb_conv_dgrad_stats_rows": (_i, [_cp]),
     "vtb_conv_dgrad_panel_w": (_i, [_cp]),
     "vtb_conv_dgrad_bn": (_i, [_cp, _p, _i, _p, _p, _i, _i, C.POINTER(VtbDgradBn), _p]),

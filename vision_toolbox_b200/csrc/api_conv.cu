@@ -826,6 +826,7 @@ static int dgrad_impl(const VtbConv* c, const void* dy, int lddy, const void* wd
       q.OH = c->h;
       q.OW = c->w;
       q.os = 2;
+      q.os_w = 2;
       q.oph = ph;
       q.opw = pq;
       q.ldo = lddx;
@@ -870,6 +871,98 @@ static int dgrad_impl(const VtbConv* c, const void* dy, int lddy, const void* wd
 int vtb_conv_dgrad(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,
                    void* stream) {
   return dgrad_impl(c, dy, lddy, wd, dx, lddx, accumulate, nullptr, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stride-2 dgrad (k = 3, pad = 1, even H and W) as ONE dense GEMM over 2x2 "super-pixels" instead of four phase launches
+// that each stream the whole dY:   dX[n][2i+a][2j+b][ci] = sum_{dh,dw in {0,1}} sum_co dY[n][i+dh][j+dw][co] * W'[(a,b,ci)][(dh,dw,co)]
+// with W'[(a,b,ci)][(dh,dw,co)] = W[co][ci][r(a,dh)][s(b,dw)], r(0,0) = 1, r(1,1) = 0, r(1,0) = 2, (0,1): no such tap -> 0
+// (7 of the 16 (a,b,dh,dw) blocks are zero: 16/9 of the minimal FLOPs - worth it only where the layer is HBM-bound, i.e.
+// few channels).  M = N*(H/2)*(W/2) super-pixels, GEMM N = 4*Cin as two n-blocks (a = 0, 1) of 2*Cin columns (b, ci):
+// with lddx == Cin those are the 2*Cin contiguous elements of pixels (2i+a, 2j) and (2i+a, 2j+1).
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_dgrad_s2_kernel(const __nv_bfloat16* __restrict__ wd, int cin, int cout, __nv_bfloat16* __restrict__ wp) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = 16LL * cin * cout;
+  const int K = 4 * cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kcol = (int)(i % K);
+    const int row = (int)(i / K);
+    const int co = kcol % cout, t = kcol / cout, dh = t >> 1, dw = t & 1;
+    const int ci = row % cin, ab = row / cin, a = ab >> 1, b = ab & 1;
+    const int r = (a == 0) ? (dh == 0 ? 1 : -1) : (dh == 1 ? 0 : 2);
+    const int sx = (b == 0) ? (dw == 0 ? 1 : -1) : (dw == 1 ? 0 : 2);
+    wp[i] = (r < 0 || sx < 0) ? __float2bfloat16(0.f) : wd[((size_t)ci * 9 + (r * 3 + sx)) * cout + co];
+  }
+}
+
+static bool dgrad_s2_ok(const VtbConv* c) {
+  return conv_ok(c) && c->k == 3 && c->stride == 2 && c->pad == 1 && c->h % 2 == 0 && c->w % 2 == 0 && c->cin <= 64 &&
+         block_of(2 * c->cin) == 2 * c->cin;
+}
+
+size_t vtb_conv_dgrad_s2_workspace_bytes(const VtbConv* c) {
+  return dgrad_s2_ok(c) ? (size_t)16 * c->cin * c->cout * sizeof(__nv_bfloat16) : 0;
+}
+
+int vtb_conv_dgrad_s2(const VtbConv* c, const void* dy, int lddy, const void* wd, void* workspace, void* dx, int lddx,
+                      int accumulate, void* stream) {
+  if (!dgrad_s2_ok(c) || !dy || !wd || !workspace || !dx) return fail(VTB_EINVAL, "vtb_conv_dgrad_s2: unsupported geometry or bad arguments");
+  if (lddy < c->cout || lddy % 8 || lddx != c->cin) return fail(VTB_EINVAL, "vtb_conv_dgrad_s2: bad pitch (dx must be dense: lddx == cin)");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 127) != 0) return fail(VTB_EINVAL, "vtb_conv_dgrad_s2: workspace must be 128-byte aligned");
+  if (!driver_api().ok) return fail(VTB_ENODEV, "cuTensorMapEncode* not available from this driver");
+  int ho, wo;
+  out_hw(c, &ho, &wo);   // == h/2, w/2
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long welems = 16LL * c->cin * c->cout;
+  launch_pdl(pack_dgrad_s2_kernel, dim3((unsigned)std::min<long long>((welems + 255) / 256, 1024)), dim3(256), 0, st,
+             (const __nv_bfloat16*)wd, c->cin, c->cout, (__nv_bfloat16*)workspace);
+  ConvIgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.cin = c->cout;          // channels per window tap of the activation operand (dY)
+  p.cout = 4 * c->cin;      // GEMM N
+  p.kc = chunk_of(c->cout);
+  p.M = c->n * ho * wo;
+  ConvTiling tl = plan_conv_tiling(p.M, 2 * c->cin, 4 * c->cout / 16);
+  if (tl.block_n != 2 * c->cin) return fail(VTB_EINVAL, "vtb_conv_dgrad_s2: internal tiling error");
+  {
+    const int sms = std::max(1, num_sms() > 0 ? num_sms() : 148);
+    const long long tiles = ((p.M + tl.block_m - 1) / tl.block_m) * 2;
+    tl.n_blocks = 2;
+    tl.grid = (int)std::max<long long>(2, std::min<long long>(tiles, sms) / 2 * 2);
+  }
+  apply_tiling(p, tl);
+  p.a_tiled = 0;
+  p.Wq = wo;
+  p.Hp = ho;
+  p.stride = 1;
+  p.lower_w = p.lower_h = 0;
+  p.ntaps = 4;
+  for (int t = 0; t < 4; ++t) {
+    p.tap_oh[t] = (uint16_t)(t >> 1);
+    p.tap_ow[t] = (uint16_t)(t & 1);
+    p.tap_kofs[t] = t * c->cout;
+  }
+  p.store_mode = accumulate ? kStoreScatterAdd : kStoreScatter;
+  p.out = (__nv_bfloat16*)dx;
+  p.OH = c->h;
+  p.OW = c->w / 2;          // super-pixel columns
+  p.os = 2;                 // row step; the n-block index supplies the row parity (merge_n)
+  p.os_w = 1;
+  p.oph = 0;
+  p.opw = 0;
+  p.ldo = 2 * lddx;         // one super-pixel = two pixels
+  p.merge_n = 1;
+  CUtensorMap tmA, tmB, tmD;
+  if (!tmap_tiled_2d(&tmB, workspace, (uint64_t)4 * c->cout, (uint64_t)4 * c->cin, (uint64_t)4 * c->cout * 2, p.kc, p.block_n, p.kc * 2))
+    return fail(VTB_ECUDA, "vtb_conv_dgrad_s2: tensor map for the merged weights failed");
+  tmD = tmB;   // unused in scatter mode, but must be a valid map
+  // window taps (dh, dw) in {0,1}^2 over dY, rows / columns past the edge read as zero (lower corner 0, upper corner 0)
+  if (!tmap_im2col_nhwc(&tmA, dy, c->cout, wo, ho, c->n, lddy, 0, 0, 0, 0, p.kc, p.block_m, 1, p.kc * 2))
+    return fail(VTB_ECUDA, "vtb_conv_dgrad_s2: im2col tensor map for dy failed");
+  count_launch(2);
+  return check_cuda(launch_conv_igemm(tmA, tmB, tmD, p, tl.grid, st), "conv_igemm_kernel(dgrad s2 merged)");
 }
 
 int vtb_conv_dgrad_bn(const VtbConv* c, const void* dy, int lddy, const void* wd, void* dx, int lddx, int accumulate,

@@ -661,7 +661,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int t = mm / p.Wq;
             const int pp = t % p.Hp;
             const int img = t / p.Hp;
-            px = (img * p.OH + pp * p.os + p.oph) * p.OW + q * p.os + p.opw;
+            px = (img * p.OH + pp * p.os + p.oph + (p.merge_n ? n_blk : 0)) * p.OW + q * p.os_w + p.opw;
           }
         }
         pix[r] = px;
@@ -676,7 +676,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               if (pix[r] >= 0) {
-                if (add) prefetch_l2(p.out + (size_t)pix[r] * p.ldo + colp);
+                if (add) prefetch_l2(p.out + (size_t)pix[r] * p.ldo + colp - (p.merge_n ? n_blk * p.block_n : 0));
                 if (EPI == kEpiBwd) {
                   const int L = (p.bwd_split > 0 && colp >= p.bwd_split) ? 1 : 0;
                   prefetch_l2(p.bwd_y[L] + (size_t)pix[r] * p.bwd_ldy[L] + (colp - (L ? p.bwd_split : 0)));
@@ -699,7 +699,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t taddr = acc0 + pi * pw;
         long long tp_ld = 0, tp_cvt = 0;
         const int colp = n0 + pi * pw;            // first column of this panel
-        __nv_bfloat16* gcol = p.out + colp;
+        __nv_bfloat16* gcol = p.out + colp - (p.merge_n ? n_blk * p.block_n : 0);
         BwdCols bw;
         bw.y = nullptr; bw.ldy = 0; bw.scale = bw.shift = nullptr; bw.relu = 0;
         uint4 early[4];

@@ -65,9 +65,11 @@ struct ConvIgemmParams {
   // epilogue
   int store_mode;
   int panel_w;      // columns per staged output panel (16/32/64), divides block_n
-  // scatter mode: pixel (img,p,q) -> out + ((img*OH + p*os + oph)*OW + q*os + opw)*ldo
+  // scatter mode: pixel (img,p,q) -> out + ((img*OH + p*os + oph)*OW + q*os_w + opw)*ldo   (os: row step, os_w: column step)
+  // merge_n != 0 (stride-2 dgrad as ONE GEMM over 2x2 super-pixels, api_conv.cu): n-block b writes output row parity
+  // oph + b and its block_n columns start at column 0 of the (two-pixel) super-pixel, i.e. at out - b * block_n
   __nv_bfloat16* out;
-  int OH, OW, os, oph, opw, ldo;
+  int OH, OW, os, os_w, oph, opw, ldo, merge_n;
   // per-channel batch statistics of the bf16-rounded result: [rows][cout][2] (sum, sumsq),
   // rows = gridDim.x / n_blocks: one per CTA; every (row, channel) is written exactly once
   float* stats_partial;

@@ -681,6 +681,9 @@ class Runner:
         # normalise + ReLU (+ residual) of a unit inside its convolution's launch (VTB_FUSED_NORM=1; single units of bf16
         # plans): the conv kernel's CTAs apply the finished coefficients to their own tiles after a flag wait
         self.fused_norm = _os.environ.get("VTB_FUSED_NORM", "0") == "1" and not graph.f32
+        # stride-2 dgrad of the few-channel layers as one GEMM over 2x2 super-pixels (VTB_DGRAD_S2_MERGED, csrc/api_conv.cu)
+        self.dgrad_s2 = _os.environ.get("VTB_DGRAD_S2_MERGED", "1") == "1" and not graph.f32
+        self._s2_ws: dict = {}
         self._side = None
         multi_rank = dist_cfg is not None and dist_cfg.world > 1
         multi_ok = (_os.environ.get("VTB_WGRAD_STREAM_MULTI", "1") == "1"
@@ -1396,6 +1399,19 @@ class Runner:
             mark(x)
         self._residual_grad(op, gp, gld, is_init, mark, st)
 
+    def _dgrad_s2_workspace(self, op: ConvOp, geom, lddx: int):
+        """Workspace of the merged stride-2 dgrad of `op` (vtb_conv_dgrad_s2), or None when the layer does not qualify:
+        3x3 / stride 2 / pad 1, even H and W, cin <= 64, dense input gradient (pitch == channels)."""
+        key = id(op)
+        if key not in self._s2_ws:
+            ws = None
+            if geom.k == 3 and geom.stride == 2 and geom.pad == 1 and lddx == geom.cin:
+                nbytes = int(self.L.vtb_conv_dgrad_s2_workspace_bytes(C.byref(geom)))
+                if nbytes > 0:
+                    ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._s2_ws[key] = ws
+        return self._s2_ws[key]
+
     def _dgrad(self, op: ConvOp, geom, dybase: int, lddy: int, wd, abase: int, gp, gld, is_init, pgrads, run, st) -> None:
         """dgrad of `op` (or of a side-by-side pair, `geom` = the pair geometry) into its input; when the plan marked this
         write as the last contribution to the producers' output gradient it also reduces their BatchNorm-backward sums."""
@@ -1404,6 +1420,12 @@ class Runner:
         world = self.dist.world if (self.dist is not None and self.dist.sync_bn) else 1
         peer_sync = self.dist.sync if (world > 1 and self.dist is not None) else None
         if op.dgrad_bn is None or not (world == 1 or peer_sync is not None):
+            ws2 = self._dgrad_s2_workspace(op, geom, gld(x)) if self.dgrad_s2 else None
+            if ws2 is not None:
+                # 3x3 stride-2 layer with few channels: one dense GEMM over 2x2 super-pixels (dy read once, not 4 times)
+                check(L.vtb_conv_dgrad_s2(C.byref(geom), dybase, lddy, wd.data_ptr(), ws2.data_ptr(), gp(x), gld(x),
+                                          int(is_init(x)), st), "vtb_conv_dgrad_s2")
+                return
             check(L.vtb_conv_dgrad(C.byref(geom), dybase, lddy, wd.data_ptr(), gp(x), gld(x), int(is_init(x)), st),
                   "vtb_conv_dgrad")
             return
